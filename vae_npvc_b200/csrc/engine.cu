@@ -1,0 +1,453 @@
+// Plan interpreter + C-ABI of libnpvc_b200.so (see include/npvc_b200.h).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "kernels.cuh"
+#include "plan.h"
+
+using namespace npvc;
+
+struct npvc_handle {
+  Plan plan;
+  int64_t max_chunk = 16384;
+  int32_t* d_pack_src = nullptr;
+  int32_t* d_unpack_ptr = nullptr;
+  int32_t* d_unpack_idx = nullptr;
+  bool tables_on_device = false;
+  int64_t launches = 0;
+  int64_t last_chunk = 0; bool last_train = false;
+  int sm_count = 148;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& m) { g_err = m; return code; }
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(NPVC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+namespace {
+
+struct Ctx {
+  npvc_handle* h; float* ws; int64_t chunk_cap; bool train;
+  const float* theta; float* grad; const float* x; const int64_t* y; const float* eps;
+  int64_t n;          // frames in this chunk
+  int64_t n_total;    // frames the loss means span
+  cudaStream_t st;
+};
+
+float* resolve(const Ctx& c, const Ref& r) {
+  const Plan& p = c.h->plan;
+  switch (r.space) {
+    case SP_WS: return c.ws + p.buf_offset(r.buf, c.chunk_cap, c.train);
+    case SP_THETA: return const_cast<float*>(c.theta) + r.off;
+    case SP_GRAD: return c.grad ? c.grad + r.off : nullptr;
+    case SP_AW: return c.ws + r.off;
+    case SP_ADW: return c.ws + p.buf_offset(p.buf_adw, c.chunk_cap, c.train) + r.off;
+    case SP_USER:
+      if (r.buf == U_X) return const_cast<float*>(c.x);
+      if (r.buf == U_EPS) return const_cast<float*>(c.eps);
+      return nullptr;
+    default: return nullptr;
+  }
+}
+DView dview(const Ctx& c, const View& v) {
+  DView d; d.p = resolve(c, v.ref); d.fs = v.fs; d.R = v.R; d.rs = v.rs; d.off = v.off; d.flen = v.flen; d.pred = v.pred;
+  return d;
+}
+bool view_vec_ok(const DView& d) {
+  return !d.pred && ((reinterpret_cast<uintptr_t>(d.p) & 15) == 0) && (d.fs % 4 == 0) && (d.rs % 4 == 0) && (d.off % 4 == 0);
+}
+
+template <int BN>
+void launch_gemm_bn(const GemmArgs& g, bool scalar, cudaStream_t st) {
+  dim3 grid((unsigned)((g.rows + 127) / 128), (unsigned)((g.N + BN - 1) / BN));
+  if (scalar) gemm_view_kernel<BN, true><<<grid, 256, 0, st>>>(g);
+  else gemm_view_kernel<BN, false><<<grid, 256, 0, st>>>(g);
+}
+void launch_gemm(const GemmArgs& g, bool scalar, cudaStream_t st) {
+  if (g.N >= 96) launch_gemm_bn<128>(g, scalar, st);
+  else if (g.N >= 48) launch_gemm_bn<64>(g, scalar, st);
+  else if (g.N >= 24) launch_gemm_bn<32>(g, scalar, st);
+  else launch_gemm_bn<16>(g, scalar, st);
+}
+
+template <int BTK, int BTN>
+void launch_wgrad_t(WgradArgs g, bool scalar, int sms, cudaStream_t st) {
+  int tk = (g.K + BTK - 1) / BTK, tn = (g.N + BTN - 1) / BTN;
+  g.tiles_n = tn;
+  long long tiles = (long long)tk * tn;
+  long long splits = (4LL * sms + tiles - 1) / tiles;
+  long long max_splits = (g.rows + 63) / 64;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long rps = (g.rows + splits - 1) / splits;
+  rps = (rps + 15) / 16 * 16;
+  splits = (g.rows + rps - 1) / rps;
+  g.rows_per_split = rps;
+  dim3 grid((unsigned)tiles, (unsigned)splits);
+  if (scalar) wgrad_view_kernel<BTK, BTN, true><<<grid, 256, 0, st>>>(g);
+  else wgrad_view_kernel<BTK, BTN, false><<<grid, 256, 0, st>>>(g);
+}
+template <int BTK>
+void launch_wgrad_k(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
+  if (g.N > 64) launch_wgrad_t<BTK, 128>(g, scalar, sms, st);
+  else if (g.N > 32) launch_wgrad_t<BTK, 64>(g, scalar, sms, st);
+  else if (g.N > 16) launch_wgrad_t<BTK, 32>(g, scalar, sms, st);
+  else launch_wgrad_t<BTK, 16>(g, scalar, sms, st);
+}
+void launch_wgrad(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
+  if (g.K > 64) launch_wgrad_k<128>(g, scalar, sms, st);
+  else if (g.K > 16) launch_wgrad_k<64>(g, scalar, sms, st);
+  else launch_wgrad_k<16>(g, scalar, sms, st);
+}
+
+int run_op(Ctx& c, const Op& o) {
+  npvc_handle* h = c.h; const Plan& p = h->plan; cudaStream_t st = c.st;
+  switch (o.kind) {
+    case OP_PACK: {
+      long long n = p.arena_w;
+      pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.theta, h->d_pack_src, c.ws, n);
+      h->launches++; break;
+    }
+    case OP_UNPACK: {
+      long long n = p.n_params;
+      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.ws + p.buf_offset(p.buf_adw, c.chunk_cap, c.train), h->d_unpack_ptr, h->d_unpack_idx, c.grad, n);
+      h->launches++; break;
+    }
+    case OP_GEMM: {
+      GemmArgs g; g.A = dview(c, o.A); g.K = o.K; g.B = resolve(c, o.B); g.ldb = o.ldb; g.N = o.N; g.C = dview(c, o.C);
+      g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R;
+      g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
+      g.table = resolve(c, o.table); g.labels = reinterpret_cast<const long long*>(c.y); g.table_ld = o.table_ld;
+      if (g.rows <= 0) break;
+      if (g.table && !g.labels) return fail(NPVC_ERR_ARG, "labels (y) required");
+      launch_gemm(g, !view_vec_ok(g.A), st); h->launches++; break;
+    }
+    case OP_WGRAD: {
+      WgradArgs g; g.A = dview(c, o.A); g.K = o.K; g.D = dview(c, o.C); g.N = o.N; g.out = resolve(c, o.B); g.ld = o.ldb;
+      g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R; g.rows_per_split = 0; g.tiles_n = 0;
+      if (g.rows <= 0) break;
+      if (!view_vec_ok(g.D)) return fail(NPVC_ERR_ARG, "wgrad dC view must be 16B aligned: " + o.name);
+      launch_wgrad(g, !view_vec_ok(g.A), h->sm_count, st); h->launches++; break;
+    }
+    case OP_LN_FWD: {
+      LnFwdArgs g; g.in = resolve(c, o.in); g.xhat = c.train ? resolve(c, o.xhat) : nullptr; g.aout = resolve(c, o.aout);
+      g.rstd = resolve(c, o.rstd); g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta);
+      g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
+      ln_fwd_kernel<<<(unsigned)c.n, 256, (size_t)o.L * sizeof(float), st>>>(g); h->launches++; break;
+    }
+    case OP_LN_BWD: {
+      LnBwdArgs g; g.dy = resolve(c, o.in); g.xhat = resolve(c, o.xhat); g.rstd = resolve(c, o.rstd);
+      g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta); g.dc = resolve(c, o.aout);
+      g.dgamma = resolve(c, o.dgamma); g.dbeta = resolve(c, o.dbeta); g.dbias = resolve(c, o.dbias);
+      g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
+      long long blocks = (long long)h->sm_count * 8; if (blocks > c.n) blocks = c.n;
+      ln_bwd_kernel<<<(unsigned)blocks, 256, (size_t)3 * o.Cn * sizeof(float), st>>>(g); h->launches++; break;
+    }
+    case OP_SAMPLE: {
+      const int z = o.i0, fpb = 8;
+      double* acc = reinterpret_cast<double*>(c.ws + p.buf_offset(p.buf_acc, c.chunk_cap, c.train));
+      sample_kl_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 2 * z, 0, st>>>(
+          resolve(c, o.r0), c.eps, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), c.eps ? acc : nullptr, z, c.n, fpb);
+      h->launches++; break;
+    }
+    case OP_SAMPLE_BWD: {
+      const int z = o.i0, fpb = 16;
+      sample_bwd_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 2 * z, 0, st>>>(
+          resolve(c, o.r0), c.eps, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), z, c.n, fpb, 1.0f / (float)c.n_total);
+      h->launches++; break;
+    }
+    case OP_RECON: {
+      double* acc = reinterpret_cast<double*>(c.ws + p.buf_offset(p.buf_acc, c.chunk_cap, c.train)) + 1;
+      const int wpb = 8;
+      recon_kernel<<<(unsigned)((c.n + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+          c.x, resolve(c, o.r1), c.grad ? resolve(c, o.r2) : nullptr, c.grad ? resolve(c, o.r3) : nullptr, acc,
+          o.i0, o.i1, 1, c.n, 1.0f / (float)c.n_total);
+      h->launches++; break;
+    }
+    case OP_SEGSUM: {
+      const int fpb = 64; size_t sm = (size_t)o.i0 * o.i1 * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) { cudaFuncSetAttribute(segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+      if (sm > 200 * 1024) return fail(NPVC_ERR_ARG, "y_dim * merge width too large for segsum shared memory");
+      segsum_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 256, sm, st>>>(
+          resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb);
+      h->launches++; break;
+    }
+    case OP_COLSUM: {
+      colsum_kernel<<<(unsigned)((o.i0 + 255) / 256), 256, 0, st>>>(resolve(c, o.r0), resolve(c, o.r1), o.i0, o.i1);
+      h->launches++; break;
+    }
+    case OP_ZERO: {
+      long long cnt = o.per_frame_count ? o.count * c.n : o.count;
+      CUDA_TRY(cudaMemsetAsync(resolve(c, o.r0), 0, (size_t)cnt * sizeof(float), st));
+      break;
+    }
+    default: return fail(NPVC_ERR_ARG, "unknown op kind");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(NPVC_ERR_CUDA, "launch " + o.name + ": " + cudaGetErrorString(e));
+  return NPVC_OK;
+}
+
+int run_phase(Ctx& c, int phase) {
+  for (const Op& o : c.h->plan.ops) {
+    if (o.phase != phase) continue;
+    if (!c.grad && (o.kind == OP_UNPACK)) continue;
+    int rc = run_op(c, o);
+    if (rc) return rc;
+  }
+  return NPVC_OK;
+}
+
+int ensure_tables(npvc_handle* h) {
+  if (h->tables_on_device) return NPVC_OK;
+  int dev = 0, cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) return fail(NPVC_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  const Plan& p = h->plan;
+  CUDA_TRY(cudaMalloc(&h->d_pack_src, p.pack_src.size() * 4));
+  CUDA_TRY(cudaMalloc(&h->d_unpack_ptr, p.unpack_ptr.size() * 4));
+  CUDA_TRY(cudaMalloc(&h->d_unpack_idx, (p.unpack_idx.size() + 1) * 4));
+  CUDA_TRY(cudaMemcpy(h->d_pack_src, p.pack_src.data(), p.pack_src.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_unpack_ptr, p.unpack_ptr.data(), p.unpack_ptr.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_unpack_idx, p.unpack_idx.data(), p.unpack_idx.size() * 4, cudaMemcpyHostToDevice));
+  h->tables_on_device = true;
+  return NPVC_OK;
+}
+
+int check_ws(npvc_handle* h, int64_t n, bool train, int64_t ws_bytes, const void* ws) {
+  if (!h) return fail(NPVC_ERR_ARG, "null handle");
+  if (!ws) return fail(NPVC_ERR_ARG, "null workspace");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(NPVC_ERR_ARG, "workspace must be 256-byte aligned");
+  int64_t need = npvc_workspace_bytes(h, n, train ? 1 : 0);
+  if (ws_bytes < need) {
+    char m[160]; snprintf(m, sizeof m, "workspace too small: %lld < %lld bytes", (long long)ws_bytes, (long long)need);
+    return fail(NPVC_ERR_WORKSPACE, m);
+  }
+  return NPVC_OK;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* npvc_last_error(void) { return g_err.c_str(); }
+const char* npvc_version(void) { return "npvc_b200 0.1 (sm_100a)"; }
+
+int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
+  if (!arch || !out) return fail(NPVC_ERR_ARG, "null argument");
+  npvc_handle* h = new npvc_handle();
+  std::string err = build_plan(*arch, h->plan);
+  if (!err.empty()) { delete h; return fail(NPVC_ERR_ARG, "unsupported architecture: " + err); }
+  if (max_chunk > 0) h->max_chunk = max_chunk;
+  *out = h;
+  return NPVC_OK;
+}
+
+void npvc_destroy(npvc_handle* h) {
+  if (!h) return;
+  if (h->tables_on_device) { cudaFree(h->d_pack_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); }
+  delete h;
+}
+
+int64_t npvc_param_count(const npvc_handle* h) { return h ? h->plan.n_params : 0; }
+int32_t npvc_param_tensors(const npvc_handle* h) { return h ? (int32_t)h->plan.params.size() : 0; }
+int npvc_param_table(const npvc_handle* h, npvc_param_desc* out, int32_t max) {
+  if (!h || !out) return fail(NPVC_ERR_ARG, "null argument");
+  int n = (int)h->plan.params.size(); if (n > max) n = max;
+  for (int i = 0; i < n; i++) {
+    const Param& q = h->plan.params[i];
+    memset(&out[i], 0, sizeof(npvc_param_desc));
+    strncpy(out[i].name, q.name.c_str(), sizeof(out[i].name) - 1);
+    out[i].offset = q.off; out[i].size = q.size; out[i].rank = q.rank;
+    for (int d = 0; d < 4; d++) out[i].shape[d] = q.shape[d];
+    out[i].fan_in = q.fan_in; out[i].fan_out = q.fan_out; out[i].init = q.init;
+  }
+  return NPVC_OK;
+}
+
+int64_t npvc_workspace_bytes(const npvc_handle* h, int64_t n, int32_t train) {
+  if (!h || n < 0) return -1;
+  int64_t chunk = n < h->max_chunk ? n : h->max_chunk;
+  if (chunk < 1) chunk = 1;
+  return h->plan.ws_floats(chunk, train != 0) * 4;
+}
+
+const char* npvc_plan_json(const npvc_handle* h) { return h ? h->plan.json.c_str() : ""; }
+
+int64_t npvc_plan_table(const npvc_handle* h, const char* name, int32_t* out, int64_t max) {
+  if (!h || !name) return -1;
+  const std::vector<int32_t>* v = nullptr;
+  if (!strcmp(name, "pack_src")) v = &h->plan.pack_src;
+  else if (!strcmp(name, "unpack_ptr")) v = &h->plan.unpack_ptr;
+  else if (!strcmp(name, "unpack_idx")) v = &h->plan.unpack_idx;
+  if (!v) return -1;
+  if (out) { int64_t n = (int64_t)v->size() < max ? (int64_t)v->size() : max; memcpy(out, v->data(), n * 4); }
+  return (int64_t)v->size();
+}
+
+int64_t npvc_launch_count(const npvc_handle* h) { return h ? h->launches : 0; }
+
+int npvc_pack_weights(npvc_handle* h, const float* d_theta, void* d_ws, int64_t ws_bytes, void* stream) {
+  int rc = check_ws(h, 1, false, ws_bytes, d_ws); if (rc) return rc;
+  if (!d_theta) return fail(NPVC_ERR_ARG, "null theta");
+  rc = ensure_tables(h); if (rc) return rc;
+  Ctx c{h, (float*)d_ws, 1, false, d_theta, nullptr, nullptr, nullptr, nullptr, 0, 1, (cudaStream_t)stream};
+  return run_phase(c, PH_PACK);
+}
+
+int npvc_encode(npvc_handle* h, const float* d_theta, const float* d_x, int64_t n, float* d_mu, float* d_lv,
+                void* d_ws, int64_t ws_bytes, void* stream) {
+  int rc = check_ws(h, n, false, ws_bytes, d_ws); if (rc) return rc;
+  if (!d_theta || !d_x || n < 0) return fail(NPVC_ERR_ARG, "bad argument");
+  rc = ensure_tables(h); if (rc) return rc;
+  const Plan& p = h->plan; cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cap = n < h->max_chunk ? (n > 0 ? n : 1) : h->max_chunk; const int z = p.arch.z_dim;
+  for (int64_t c0 = 0; c0 < n; c0 += cap) {
+    int64_t m = n - c0 < cap ? n - c0 : cap;
+    Ctx c{h, (float*)d_ws, cap, false, d_theta, nullptr, d_x + c0 * p.arch.in_h, nullptr, nullptr, m, n, st};
+    rc = run_phase(c, PH_ENC); if (rc) return rc;
+    rc = run_phase(c, PH_SAMPLE); if (rc) return rc;
+    if (d_mu) CUDA_TRY(cudaMemcpyAsync(d_mu + c0 * z, c.ws + p.buf_offset(p.buf_mu, cap, false), (size_t)m * z * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_lv) CUDA_TRY(cudaMemcpyAsync(d_lv + c0 * z, c.ws + p.buf_offset(p.buf_lv, cap, false), (size_t)m * z * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  h->last_chunk = cap; h->last_train = false;
+  return NPVC_OK;
+}
+
+int npvc_sample(npvc_handle* h, const float* d_mu, const float* d_lv, const float* d_eps, int64_t n, float* d_z, void* stream) {
+  if (!h || !d_mu || !d_lv || !d_eps || !d_z) return fail(NPVC_ERR_ARG, "null argument");
+  int rc = ensure_tables(h); if (rc) return rc;
+  long long tot = n * h->plan.arch.z_dim;
+  if (tot > 0) {
+    sample_only_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_mu, d_lv, d_eps, d_z, tot);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return NPVC_OK;
+}
+
+int npvc_decode(npvc_handle* h, const float* d_theta, const float* d_z, const int64_t* d_y, int64_t n, float* d_xh,
+                void* d_ws, int64_t ws_bytes, void* stream) {
+  int rc = check_ws(h, n, false, ws_bytes, d_ws); if (rc) return rc;
+  if (!d_theta || !d_z || !d_y || !d_xh || n < 0) return fail(NPVC_ERR_ARG, "bad argument");
+  rc = ensure_tables(h); if (rc) return rc;
+  const Plan& p = h->plan; cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cap = n < h->max_chunk ? (n > 0 ? n : 1) : h->max_chunk; const int z = p.arch.z_dim, H = p.arch.in_h;
+  for (int64_t c0 = 0; c0 < n; c0 += cap) {
+    int64_t m = n - c0 < cap ? n - c0 : cap;
+    Ctx c{h, (float*)d_ws, cap, false, d_theta, nullptr, nullptr, d_y + c0, nullptr, m, n, st};
+    CUDA_TRY(cudaMemcpyAsync(c.ws + p.buf_offset(p.buf_z, cap, false), d_z + c0 * z, (size_t)m * z * 4, cudaMemcpyDeviceToDevice, st));
+    rc = run_phase(c, PH_DEC); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_xh + c0 * H, c.ws + p.buf_offset(p.buf_xh, cap, false), (size_t)m * H * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  h->last_chunk = cap; h->last_train = false;
+  return NPVC_OK;
+}
+
+int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, const int64_t* d_y, const float* d_eps,
+                      int64_t n, float* d_z, float* d_mu, float* d_lv, float* d_xh, float* d_losses, float* d_grad,
+                      int32_t repack, void* d_ws, int64_t ws_bytes, void* stream) {
+  int rc = check_ws(h, n, true, ws_bytes, d_ws); if (rc) return rc;
+  if (!d_theta || !d_x || !d_y || !d_eps || n < 1) return fail(NPVC_ERR_ARG, "bad argument");
+  rc = ensure_tables(h); if (rc) return rc;
+  const Plan& p = h->plan; cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cap = n < h->max_chunk ? n : h->max_chunk; const int z = p.arch.z_dim, H = p.arch.in_h;
+  float* ws = (float*)d_ws;
+  CUDA_TRY(cudaMemsetAsync(ws + p.buf_offset(p.buf_acc, cap, true), 0, 8 * 4, st));
+  if (d_grad) {
+    CUDA_TRY(cudaMemsetAsync(d_grad, 0, (size_t)p.n_params * 4, st));
+    CUDA_TRY(cudaMemsetAsync(ws + p.buf_offset(p.buf_adw, cap, true), 0, (size_t)p.arena_dw * 4, st));
+    CUDA_TRY(cudaMemsetAsync(ws + p.buf_offset(p.buf_dptab, cap, true), 0, (size_t)p.bufs[p.buf_dptab].fixed * 4, st));
+  }
+  if (repack) {
+    Ctx c{h, ws, cap, true, d_theta, nullptr, nullptr, nullptr, nullptr, 0, n, st};
+    rc = run_phase(c, PH_PACK); if (rc) return rc;
+  }
+  for (int64_t c0 = 0; c0 < n; c0 += cap) {
+    int64_t m = n - c0 < cap ? n - c0 : cap;
+    Ctx c{h, ws, cap, true, d_theta, d_grad, d_x + c0 * H, d_y + c0, d_eps + c0 * z, m, n, st};
+    for (int ph : {PH_ENC, PH_SAMPLE, PH_DEC, PH_LOSS}) { rc = run_phase(c, ph); if (rc) return rc; }
+    if (d_grad) { rc = run_phase(c, PH_BWD); if (rc) return rc; }
+    struct { float* dst; int buf; int w; } outs[4] = {{d_z, p.buf_z, z}, {d_mu, p.buf_mu, z}, {d_lv, p.buf_lv, z}, {d_xh, p.buf_xh, H}};
+    for (auto& o : outs)
+      if (o.dst) CUDA_TRY(cudaMemcpyAsync(o.dst + c0 * o.w, ws + p.buf_offset(o.buf, cap, true), (size_t)m * o.w * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (d_grad) {
+    Ctx c{h, ws, cap, true, d_theta, d_grad, nullptr, nullptr, nullptr, 0, n, st};
+    rc = run_phase(c, PH_FINAL); if (rc) return rc;
+  }
+  if (d_losses) {
+    finalize_losses_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(ws + p.buf_offset(p.buf_acc, cap, true)), d_losses, 1.0 / (double)n);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->last_chunk = cap; h->last_train = true;
+  return NPVC_OK;
+}
+
+int npvc_adam_step(npvc_handle* h, float* d_theta, const float* d_grad, float* d_m, float* d_v, int64_t n_params,
+                   int64_t step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!h || !d_theta || !d_grad || !d_m || !d_v || step < 1) return fail(NPVC_ERR_ARG, "bad argument");
+  int rc = ensure_tables(h); if (rc) return rc;
+  double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) / (1.0 - std::pow((double)beta1, (double)step));
+  adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_theta, d_grad, d_m, d_v, n_params, (float)lr_t, beta1, beta2, eps, grad_scale);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return NPVC_OK;
+}
+
+int npvc_tanhize_forward(npvc_handle* h, const float* d_x, const float* d_xmin, const float* d_xmax, int64_t n, int32_t dim, float* d_out, void* stream) {
+  if (!h || !d_x || !d_xmin || !d_xmax || !d_out) return fail(NPVC_ERR_ARG, "null argument");
+  int rc = ensure_tables(h); if (rc) return rc;
+  long long tot = n * dim;
+  if (tot > 0) { tanhize_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_xmin, d_xmax, d_out, n, dim); h->launches++; }
+  CUDA_TRY(cudaGetLastError());
+  return NPVC_OK;
+}
+int npvc_tanhize_backward(npvc_handle* h, const float* d_x, const float* d_xmin, const float* d_xmax, int64_t n, int32_t dim, float* d_out, void* stream) {
+  if (!h || !d_x || !d_xmin || !d_xmax || !d_out) return fail(NPVC_ERR_ARG, "null argument");
+  int rc = ensure_tables(h); if (rc) return rc;
+  long long tot = n * dim;
+  if (tot > 0) { tanhize_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_xmin, d_xmax, d_out, n, dim); h->launches++; }
+  CUDA_TRY(cudaGetLastError());
+  return NPVC_OK;
+}
+
+int npvc_unpack_records(npvc_handle* h, const float* d_records, int64_t n, int32_t rec_floats, int32_t sp_dim,
+                        const float* d_xmin, const float* d_xmax, float* d_x, int64_t* d_y, void* stream) {
+  if (!h || !d_records || !d_x || !d_y || sp_dim > rec_floats) return fail(NPVC_ERR_ARG, "bad argument");
+  int rc = ensure_tables(h); if (rc) return rc;
+  long long tot = n * sp_dim;
+  if (tot > 0) {
+    unpack_records_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_records, n, rec_floats, sp_dim, d_xmin, d_xmax, d_x, reinterpret_cast<long long*>(d_y));
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return NPVC_OK;
+}
+
+int64_t npvc_debug_buffer(npvc_handle* h, const char* name, const void* d_ws, float* d_out, int64_t n, void* stream) {
+  if (!h || !name || !d_ws) return -1;
+  const Plan& p = h->plan;
+  for (int i = 0; i < (int)p.bufs.size(); i++) {
+    if (p.bufs[i].name != name) continue;
+    if (p.bufs[i].train_only && !h->last_train) return -2;
+    int64_t per = p.bufs[i].per_frame, cnt = p.bufs[i].fixed + per * (n < h->last_chunk ? n : h->last_chunk);
+    if (d_out) cudaMemcpyAsync(d_out, (const float*)d_ws + p.buf_offset(i, h->last_chunk, h->last_train), (size_t)cnt * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return per ? per : p.bufs[i].fixed;
+  }
+  if (!strcmp(name, "arena_w")) {
+    if (d_out) cudaMemcpyAsync(d_out, d_ws, (size_t)p.arena_w * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return p.arena_w;
+  }
+  return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,641 @@
+// CUDA-core kernels of the ConvVAE hot path (sm_100a).  The tensor-core (tcgen05) GEMM lives in
+// umma_gemm.cuh; everything here is fp32 FFMA / bandwidth-shaped work.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace npvc {
+
+// Strided row view (see plan.h): element (row, k) lives at
+//   p + (row / R) * fs + (row % R) * rs + off + k,  valid (when pred) iff 0 <= (row%R)*rs+off+k < flen
+struct DView {
+  float* p; long long fs; int R, rs, off, flen, pred;
+};
+
+__device__ __forceinline__ float lrelu_f(float x) { return fmaxf(x, 0.02f * x); }
+
+#define NPVC_LN_EPS 1e-5f
+// util/layers.py:7: EPSILON = 1e-6 (fp32), used as exp(0) + EPSILON
+#define NPVC_ONE_PLUS_EPS (1.0f + 1e-6f)
+#define NPVC_LOG_2PI 1.8378770664093453f
+
+// =============================================================================================
+// (F) C[rows,N] = A_view[rows,K] . B[K,N] + bias + table[label]   -- 128 x BN tile, BK = 16
+// =============================================================================================
+struct GemmArgs {
+  DView A; int K; const float* B; int ldb; int N; DView C; long long rows;
+  const float* bias0; const float* bias1; const float* bias2; int bias_mod;
+  const float* table; const long long* labels; int table_ld;
+};
+
+template <int BN, bool ASCALAR>
+__global__ void __launch_bounds__(256) gemm_view_kernel(GemmArgs g) {
+  constexpr int BM = 128, BK = 16, TN = BN / 16, LDA = BM + 4;
+  constexpr int NB4 = (4 * BN + 255) / 256;            // float4 B loads per thread
+  __shared__ __align__(16) float As[2][BK][LDA];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // A loader: thread -> rows (lrow, lrow+64), k-quad kq
+  const int lrow = tid >> 2, kq = tid & 3;
+  const float* aptr[2]; int ainf[2];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    long long r = m0 + lrow + 64 * h;
+    if (r < g.rows) {
+      long long f = r / g.A.R; int j = (int)(r - f * g.A.R);
+      ainf[h] = j * g.A.rs + g.A.off;
+      aptr[h] = g.A.p + f * g.A.fs + ainf[h];
+    } else { aptr[h] = nullptr; ainf[h] = 0; }
+  }
+  float4 ra[2]; float4 rb[NB4];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      int k = k0 + kq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (aptr[h] != nullptr) {
+        if (!ASCALAR) {
+          if (k < g.K) {
+            v = *reinterpret_cast<const float4*>(aptr[h] + k);
+            if (k + 3 >= g.K) { if (k + 1 >= g.K) v.y = 0.f; if (k + 2 >= g.K) v.z = 0.f; v.w = 0.f; }
+          }
+        } else {
+          float t[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            int kk = k + i; bool ok = kk < g.K;
+            if (g.A.pred) { int q = ainf[h] + kk; ok = ok && q >= 0 && q < g.A.flen; }
+            t[i] = ok ? aptr[h][kk] : 0.f;
+          }
+          v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      ra[h] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < NB4; it++) {
+      int i = tid + it * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < 4 * BN) {
+        int kk = i / (BN / 4), nq = i % (BN / 4);
+        int k = k0 + kk, n = n0 + nq * 4;
+        if (k < g.K && n < g.N) v = *reinterpret_cast<const float4*>(g.B + (long long)k * g.ldb + n);
+      }
+      rb[it] = v;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      As[buf][kq * 4 + 0][lrow + 64 * h] = ra[h].x; As[buf][kq * 4 + 1][lrow + 64 * h] = ra[h].y;
+      As[buf][kq * 4 + 2][lrow + 64 * h] = ra[h].z; As[buf][kq * 4 + 3][lrow + 64 * h] = ra[h].w;
+    }
+#pragma unroll
+    for (int it = 0; it < NB4; it++) {
+      int i = tid + it * 256;
+      if (i < 4 * BN) { int kk = i / (BN / 4), nq = i % (BN / 4); *reinterpret_cast<float4*>(&Bs[buf][kk][nq * 4]) = rb[it]; }
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+  const int nk = (g.K + BK - 1) / BK;
+  load_tiles(0); store_tiles(0); __syncthreads();
+  for (int kt = 0; kt < nk; kt++) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      float a[8], b[TN];
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      if (TN == 8) {
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][BN / 2 + tx * 4]);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4 % TN] = b1.x; b[5 % TN] = b1.y; b[6 % TN] = b1.z; b[7 % TN] = b1.w;
+      } else if (TN == 4) {
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        b[0] = b0.x; b[1 % TN] = b0.y; b[2 % TN] = b0.z; b[3 % TN] = b0.w;
+      } else if (TN == 2) {
+        float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][kk][tx * 2]);
+        b[0] = b0.x; b[1 % TN] = b0.y;
+      } else {
+        b[0] = Bs[buf][kk][tx];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) { store_tiles(buf ^ 1); __syncthreads(); }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int m = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
+    const long long r = m0 + m;
+    if (r >= g.rows) continue;
+    const long long f = r / g.C.R; const int j = (int)(r - f * g.C.R);
+    const int inf = j * g.C.rs + g.C.off;
+    float* cp = g.C.p + f * g.C.fs + inf;
+    const float* trow = g.table ? g.table + (long long)g.labels[f] * g.table_ld : nullptr;
+    constexpr int NG = (TN == 8) ? 2 : 1;            // column groups
+    constexpr int GW = (TN == 8) ? 4 : TN;           // group width
+#pragma unroll
+    for (int gi = 0; gi < NG; gi++) {
+      const int cbase = n0 + ((TN == 8) ? (gi * (BN / 2) + tx * 4) : (tx * TN));
+      float v[GW];
+#pragma unroll
+      for (int j2 = 0; j2 < GW; j2++) {
+        const int n = cbase + j2;
+        float t = acc[i][gi * GW + j2];
+        if (n < g.N) {
+          const int bi = n % g.bias_mod;
+          if (g.bias0) t += g.bias0[bi];
+          if (g.bias1) t += g.bias1[bi];
+          if (g.bias2) t += g.bias2[bi];
+          if (trow) t += trow[n];
+        }
+        v[j2] = t;
+      }
+      bool full = (cbase + GW <= g.N);
+      if (g.C.pred) full = full && (inf + cbase >= 0) && (inf + cbase + GW <= g.C.flen);
+      if (GW == 4 && full && ((reinterpret_cast<uintptr_t>(cp + cbase) & 15) == 0)) {
+        *reinterpret_cast<float4*>(cp + cbase) = make_float4(v[0], v[1 % GW], v[2 % GW], v[3 % GW]);
+      } else {
+#pragma unroll
+        for (int j2 = 0; j2 < GW; j2++) {
+          const int n = cbase + j2;
+          bool ok = n < g.N;
+          if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
+          if (ok) cp[n] = v[j2];
+        }
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// (W) dB[K,N] += A_view[rows,K]^T . D_view[rows,N]   -- BTK x BTN tile, split over row ranges
+// =============================================================================================
+struct WgradArgs {
+  DView A; int K; DView D; int N; float* out; int ld; long long rows; long long rows_per_split; int tiles_n;
+};
+
+template <int BTK, int BTN, bool ASCALAR>
+__global__ void __launch_bounds__(256) wgrad_view_kernel(WgradArgs g) {
+  constexpr int BR = 16, TK = BTK / 16, TNN = BTN / 16;
+  constexpr int NA4 = (BR * BTK / 4 + 255) / 256, ND4 = (BR * BTN / 4 + 255) / 256;
+  __shared__ __align__(16) float As[2][BR][BTK];
+  __shared__ __align__(16) float Ds[2][BR][BTN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tile_k = blockIdx.x / g.tiles_n, tile_n = blockIdx.x % g.tiles_n;
+  const int kt0 = tile_k * BTK, nt0 = tile_n * BTN;
+  const long long rbeg = (long long)blockIdx.y * g.rows_per_split;
+  long long rend = rbeg + g.rows_per_split; if (rend > g.rows) rend = g.rows;
+  if (rbeg >= rend) return;
+
+  float4 ra[NA4], rd[ND4];
+  auto load_tiles = [&](long long r0) {
+#pragma unroll
+    for (int it = 0; it < NA4; it++) {
+      int i = tid + it * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < BR * BTK / 4) {
+        int rr = i / (BTK / 4), q = i % (BTK / 4);
+        long long r = r0 + rr; int k = kt0 + q * 4;
+        if (r < rend && k < g.K) {
+          long long f = r / g.A.R; int j = (int)(r - f * g.A.R);
+          int inf = j * g.A.rs + g.A.off;
+          const float* ap = g.A.p + f * g.A.fs + inf;
+          if (!ASCALAR) {
+            v = *reinterpret_cast<const float4*>(ap + k);
+          } else {
+            float t[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              int kk = k + e; bool ok = kk < g.K;
+              if (g.A.pred) { int qq = inf + kk; ok = ok && qq >= 0 && qq < g.A.flen; }
+              t[e] = ok ? ap[kk] : 0.f;
+            }
+            v = make_float4(t[0], t[1], t[2], t[3]);
+          }
+        }
+      }
+      ra[it] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < ND4; it++) {
+      int i = tid + it * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < BR * BTN / 4) {
+        int rr = i / (BTN / 4), q = i % (BTN / 4);
+        long long r = r0 + rr; int n = nt0 + q * 4;
+        if (r < rend && n < g.N) {
+          long long f = r / g.D.R; int j = (int)(r - f * g.D.R);
+          v = *reinterpret_cast<const float4*>(g.D.p + f * g.D.fs + j * g.D.rs + g.D.off + n);
+        }
+      }
+      rd[it] = v;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int it = 0; it < NA4; it++) {
+      int i = tid + it * 256;
+      if (i < BR * BTK / 4) { int rr = i / (BTK / 4), q = i % (BTK / 4); *reinterpret_cast<float4*>(&As[buf][rr][q * 4]) = ra[it]; }
+    }
+#pragma unroll
+    for (int it = 0; it < ND4; it++) {
+      int i = tid + it * 256;
+      if (i < BR * BTN / 4) { int rr = i / (BTN / 4), q = i % (BTN / 4); *reinterpret_cast<float4*>(&Ds[buf][rr][q * 4]) = rd[it]; }
+    }
+  };
+
+  float acc[TK][TNN];
+#pragma unroll
+  for (int i = 0; i < TK; i++)
+#pragma unroll
+    for (int j = 0; j < TNN; j++) acc[i][j] = 0.f;
+
+  const long long nit = (rend - rbeg + BR - 1) / BR;
+  load_tiles(rbeg); store_tiles(0); __syncthreads();
+  for (long long itr = 0; itr < nit; itr++) {
+    const int buf = (int)(itr & 1);
+    if (itr + 1 < nit) load_tiles(rbeg + (itr + 1) * BR);
+#pragma unroll
+    for (int rr = 0; rr < BR; rr++) {
+      float a[TK], d[TNN];
+      if (TK == 8) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][rr][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[buf][rr][BTK / 2 + ty * 4]);
+        a[0] = a0.x; a[1 % TK] = a0.y; a[2 % TK] = a0.z; a[3 % TK] = a0.w; a[4 % TK] = a1.x; a[5 % TK] = a1.y; a[6 % TK] = a1.z; a[7 % TK] = a1.w;
+      } else if (TK == 4) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][rr][ty * 4]);
+        a[0] = a0.x; a[1 % TK] = a0.y; a[2 % TK] = a0.z; a[3 % TK] = a0.w;
+      } else if (TK == 2) {
+        float2 a0 = *reinterpret_cast<const float2*>(&As[buf][rr][ty * 2]);
+        a[0] = a0.x; a[1 % TK] = a0.y;
+      } else { a[0] = As[buf][rr][ty]; }
+      if (TNN == 8) {
+        float4 d0 = *reinterpret_cast<const float4*>(&Ds[buf][rr][tx * 4]);
+        float4 d1 = *reinterpret_cast<const float4*>(&Ds[buf][rr][BTN / 2 + tx * 4]);
+        d[0] = d0.x; d[1 % TNN] = d0.y; d[2 % TNN] = d0.z; d[3 % TNN] = d0.w; d[4 % TNN] = d1.x; d[5 % TNN] = d1.y; d[6 % TNN] = d1.z; d[7 % TNN] = d1.w;
+      } else if (TNN == 4) {
+        float4 d0 = *reinterpret_cast<const float4*>(&Ds[buf][rr][tx * 4]);
+        d[0] = d0.x; d[1 % TNN] = d0.y; d[2 % TNN] = d0.z; d[3 % TNN] = d0.w;
+      } else if (TNN == 2) {
+        float2 d0 = *reinterpret_cast<const float2*>(&Ds[buf][rr][tx * 2]);
+        d[0] = d0.x; d[1 % TNN] = d0.y;
+      } else { d[0] = Ds[buf][rr][tx]; }
+#pragma unroll
+      for (int i = 0; i < TK; i++)
+#pragma unroll
+        for (int j = 0; j < TNN; j++) acc[i][j] = fmaf(a[i], d[j], acc[i][j]);
+    }
+    if (itr + 1 < nit) { store_tiles(buf ^ 1); __syncthreads(); }
+  }
+#pragma unroll
+  for (int i = 0; i < TK; i++) {
+    int kl = (TK == 8) ? ((i < 4) ? ty * 4 + i : BTK / 2 + ty * 4 + (i - 4)) : (ty * TK + i);
+    int k = kt0 + kl;
+    if (k >= g.K) continue;
+#pragma unroll
+    for (int j = 0; j < TNN; j++) {
+      int nl = (TNN == 8) ? ((j < 4) ? tx * 4 + j : BTN / 2 + tx * 4 + (j - 4)) : (tx * TNN + j);
+      int n = nt0 + nl;
+      if (n < g.N) atomicAdd(g.out + (long long)k * g.ld + n, acc[i][j]);
+    }
+  }
+}
+
+// =============================================================================================
+// block reductions
+// =============================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the block (blockDim.x multiple of 32, <= 1024); result broadcast to all threads
+__device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) { float t = (lane < nw) ? red[lane] : 0.f; t = warp_sum(t); if (lane == 0) red[32] = t; }
+  __syncthreads();
+  return red[32];
+}
+
+// =============================================================================================
+// Layernorm + lrelu forward  (util/layers.py:10-44,147-149): one block per frame
+// =============================================================================================
+struct LnFwdArgs {
+  const float* in; float* xhat; float* aout; float* rstd; const float* gamma; const float* beta;
+  int L, Cn, out_flen, out_off; long long frames;
+};
+
+__global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs g) {
+  extern __shared__ __align__(16) float sm[];     // L floats
+  __shared__ float red[40];
+  const long long f = blockIdx.x;
+  const float* x = g.in + f * g.L;
+  const int L4 = g.L >> 2;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L4; i += blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<float4*>(sm)[i] = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = block_sum(s, red) / (float)g.L;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < L4; i += blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(sm)[i];
+    float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = block_sum(q, red) / (float)g.L;
+  const float rs = rsqrtf(var + NPVC_LN_EPS);
+  if (threadIdx.x == 0) g.rstd[f] = rs;
+  float* xo = g.xhat ? g.xhat + f * g.L : nullptr;
+  float* ao = g.aout + f * g.out_flen;
+  const int off4 = g.out_off >> 2, F4 = g.out_flen >> 2;
+  for (int i = threadIdx.x; i < F4; i += blockDim.x) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ii = i - off4;
+    if (ii >= 0 && ii < L4) {
+      float4 v = reinterpret_cast<const float4*>(sm)[ii];
+      const int c = (ii * 4) % g.Cn;
+      float4 h = make_float4((v.x - mean) * rs, (v.y - mean) * rs, (v.z - mean) * rs, (v.w - mean) * rs);
+      if (xo) reinterpret_cast<float4*>(xo)[ii] = h;
+      o.x = lrelu_f(fmaf(h.x, g.gamma[c], g.beta[c]));
+      o.y = lrelu_f(fmaf(h.y, g.gamma[c + 1], g.beta[c + 1]));
+      o.z = lrelu_f(fmaf(h.z, g.gamma[c + 2], g.beta[c + 2]));
+      o.w = lrelu_f(fmaf(h.w, g.gamma[c + 3], g.beta[c + 3]));
+    }
+    reinterpret_cast<float4*>(ao)[i] = o;
+  }
+}
+
+// =============================================================================================
+// Layernorm + lrelu backward: dy (grad wrt the activation) -> dc (grad wrt the conv output, written
+// into a zero-padded frame), dgamma, dbeta, dbias.  Persistent blocks, grid-stride over frames.
+// =============================================================================================
+struct LnBwdArgs {
+  const float* dy; const float* xhat; const float* rstd; const float* gamma; const float* beta;
+  float* dc; float* dgamma; float* dbeta; float* dbias;
+  int L, Cn, out_flen, out_off; long long frames;
+};
+
+__global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
+  extern __shared__ float chs[];                  // 3 * Cn
+  __shared__ float red[40];
+  for (int i = threadIdx.x; i < 3 * g.Cn; i += blockDim.x) chs[i] = 0.f;
+  const int L4 = g.L >> 2;
+  const bool fixed = ((blockDim.x * 4) % g.Cn) == 0;   // thread -> channel mapping constant across i
+  float adg[4] = {0, 0, 0, 0}, adb[4] = {0, 0, 0, 0}, adc[4] = {0, 0, 0, 0};
+  const int off4 = g.out_off >> 2, F4 = g.out_flen >> 2;
+  const float invL = 1.0f / (float)g.L;
+  __syncthreads();
+  for (long long f = blockIdx.x; f < g.frames; f += gridDim.x) {
+    const float4* dy4 = reinterpret_cast<const float4*>(g.dy + f * g.L);
+    const float4* xh4 = reinterpret_cast<const float4*>(g.xhat + f * g.L);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < L4; i += blockDim.x) {
+      float4 d = dy4[i], h = xh4[i];
+      const int c = (i * 4) % g.Cn;
+      float dv[4] = {d.x, d.y, d.z, d.w}, hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        float gm = g.gamma[c + e];
+        float u = fmaf(hv[e], gm, g.beta[c + e]);
+        float du = dv[e] * (u >= 0.f ? 1.0f : 0.02f);
+        float dxh = du * gm;
+        s1 += dxh; s2 += dxh * hv[e];
+      }
+    }
+    s1 = block_sum(s1, red) * invL;
+    s2 = block_sum(s2, red) * invL;
+    const float rs = g.rstd[f];
+    float4* dc4 = reinterpret_cast<float4*>(g.dc + f * g.out_flen);
+    for (int i = threadIdx.x; i < F4; i += blockDim.x) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ii = i - off4;
+      if (ii >= 0 && ii < L4) {
+        float4 d = dy4[ii], h = xh4[ii];
+        const int c = (ii * 4) % g.Cn;
+        float dv[4] = {d.x, d.y, d.z, d.w}, hv[4] = {h.x, h.y, h.z, h.w}, ov[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          float gm = g.gamma[c + e];
+          float u = fmaf(hv[e], gm, g.beta[c + e]);
+          float du = dv[e] * (u >= 0.f ? 1.0f : 0.02f);
+          float dxh = du * gm;
+          ov[e] = rs * (dxh - s1 - hv[e] * s2);
+          if (fixed) { adg[e] += du * hv[e]; adb[e] += du; adc[e] += ov[e]; }
+          else { atomicAdd(&chs[c + e], du * hv[e]); atomicAdd(&chs[g.Cn + c + e], du); atomicAdd(&chs[2 * g.Cn + c + e], ov[e]); }
+        }
+        o = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      }
+      dc4[i] = o;
+    }
+  }
+  if (fixed) {
+    // thread t handles float4 index ii = t + it*blockDim - off4, so its channels are
+    // (4t - out_off) mod Cn + {0..3} for every it when blockDim*4 % Cn == 0
+    const int c = (int)(((long long)threadIdx.x * 4 - g.out_off) % g.Cn + g.Cn) % g.Cn;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      atomicAdd(&chs[c + e], adg[e]); atomicAdd(&chs[g.Cn + c + e], adb[e]); atomicAdd(&chs[2 * g.Cn + c + e], adc[e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < g.Cn; i += blockDim.x) {
+    atomicAdd(&g.dgamma[i], chs[i]); atomicAdd(&g.dbeta[i], chs[g.Cn + i]); atomicAdd(&g.dbias[i], chs[2 * g.Cn + i]);
+  }
+}
+
+// =============================================================================================
+// sampler + KL  (util/layers.py:152-156,170-183); blockDim = 2z threads, thread = column
+// =============================================================================================
+__global__ void sample_kl_kernel(const float* hz, const float* eps, float* mu, float* lv, float* zout,
+                                 double* acc_kl, int z, long long frames, int frames_per_block) {
+  __shared__ float red[40];
+  const int col = threadIdx.x;
+  const long long f0 = (long long)blockIdx.x * frames_per_block;
+  float kl = 0.f;
+  for (int i = 0; i < frames_per_block; i++) {
+    long long f = f0 + i; if (f >= frames) break;
+    float v = hz[f * 2 * z + col];
+    if (col < z) { mu[f * z + col] = v; }
+    else {
+      const int d = col - z;
+      lv[f * z + d] = v;
+      float m = hz[f * 2 * z + d];
+      float ev = expf(v);
+      if (eps) zout[f * z + d] = fmaf(eps[f * z + d], sqrtf(ev), m);
+      kl += 0.5f * (-v + (ev + m * m) / NPVC_ONE_PLUS_EPS - 1.0f);
+    }
+  }
+  if (acc_kl) { float t = block_sum(kl, red); if (threadIdx.x == 0) atomicAdd(acc_kl, (double)t); }
+}
+
+// GaussianSampleLayer alone (util/layers.py:152-156)
+__global__ void sample_only_kernel(const float* mu, const float* lv, const float* eps, float* z, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = fmaf(eps[i], sqrtf(expf(lv[i])), mu[i]);
+}
+
+// dz, eps, (mu|lv) -> (dmu|dlv); column sums -> head-bias grads.  inv_n = 1 / (frames the means span)
+__global__ void sample_bwd_kernel(const float* dz, const float* eps, const float* hz, float* dhz, float* dbh,
+                                  int z, long long frames, int frames_per_block, float inv_n) {
+  const int col = threadIdx.x;
+  const long long f0 = (long long)blockIdx.x * frames_per_block;
+  float cs = 0.f;
+  for (int i = 0; i < frames_per_block; i++) {
+    long long f = f0 + i; if (f >= frames) break;
+    float o;
+    if (col < z) {
+      float m = hz[f * 2 * z + col];
+      o = dz[f * z + col] + m / NPVC_ONE_PLUS_EPS * inv_n;
+    } else {
+      const int d = col - z;
+      float l = hz[f * 2 * z + col];
+      float ev = expf(l);
+      o = dz[f * z + d] * eps[f * z + d] * 0.5f * sqrtf(ev) + 0.5f * (ev / NPVC_ONE_PLUS_EPS - 1.0f) * inv_n;
+    }
+    dhz[f * 2 * z + col] = o; cs += o;
+  }
+  atomicAdd(&dbh[col], cs);
+}
+
+// =============================================================================================
+// Gaussian log-density + d/dxh  (util/layers.py:159-167): one warp per frame
+// =============================================================================================
+__global__ void recon_kernel(const float* x, const float* xh, float* dxh, float* dbias, double* acc_logp,
+                             int H, int ld, int Co, long long frames, float inv_n) {
+  __shared__ float red[40];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long f = (long long)blockIdx.x * nw + w;
+  float lp = 0.f, db = 0.f;
+  if (f < frames) {
+    for (int i = lane; i < ld; i += 32) {
+      float g = 0.f;
+      if (i < H) {
+        float d = xh[f * H + i] - x[f * H + i];
+        lp += -0.5f * (NPVC_LOG_2PI + d * d / NPVC_ONE_PLUS_EPS);
+        g = d / NPVC_ONE_PLUS_EPS * inv_n;
+        db += g;
+      }
+      if (dxh) dxh[f * ld + i] = g;
+    }
+  }
+  float t = block_sum(lp, red);
+  if (threadIdx.x == 0) atomicAdd(acc_logp, (double)t);
+  if (dbias) {   // Co == 1 on this path (single output channel)
+    float s = block_sum(db, red);
+    if (threadIdx.x == 0) atomicAdd(dbias, s);
+  }
+}
+
+// =============================================================================================
+// per-speaker row sums: out[y[f], :] += in[f, :]   (dynamic smem: ny * N floats)
+// =============================================================================================
+__global__ void segsum_kernel(const float* in, const long long* y, float* out, int N, int ny,
+                              long long frames, int frames_per_block) {
+  extern __shared__ float acc[];
+  for (int i = threadIdx.x; i < ny * N; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const long long f0 = (long long)blockIdx.x * frames_per_block;
+  for (int i = 0; i < frames_per_block; i++) {
+    long long f = f0 + i; if (f >= frames) break;
+    int s = (int)y[f];
+    if (s < 0 || s >= ny) continue;
+    for (int c = threadIdx.x; c < N; c += blockDim.x) acc[s * N + c] += in[f * N + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ny * N; i += blockDim.x) { float v = acc[i]; if (v != 0.f) atomicAdd(&out[i], v); }
+}
+
+__global__ void colsum_kernel(const float* in, float* out, int N, int rows) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; r++) s += in[(long long)r * N + c];
+  out[c] += s;
+}
+
+// =============================================================================================
+// pack / unpack / adam / finalize / tanhize / records
+// =============================================================================================
+__global__ void pack_kernel(const float* theta, const int* src, float* arena, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { int s = src[i]; arena[i] = (s >= 0) ? theta[s] : 0.f; }
+}
+
+__global__ void unpack_kernel(const float* adw, const int* ptr, const int* idx, float* grad, long long n) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int b = ptr[t], e = ptr[t + 1];
+  if (b == e) return;
+  float s = 0.f;
+  for (int i = b; i < e; i++) s += adw[idx[i]];
+  grad[t] += s;
+}
+
+// TF-form Adam (trainer/vae.py:16-24): theta -= lr_t * m / (sqrt(v) + eps)
+__global__ void adam_kernel(float* theta, const float* grad, float* m, float* v, long long n,
+                            float lr_t, float b1, float b2, float eps, float gscale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = grad[i] * gscale;
+  float mm = b1 * m[i] + (1.0f - b1) * g;
+  float vv = b2 * v[i] + (1.0f - b2) * g * g;
+  m[i] = mm; v[i] = vv;
+  theta[i] -= lr_t * mm / (sqrtf(vv) + eps);
+}
+
+__global__ void finalize_losses_kernel(const double* acc, float* losses, double inv_n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double kl = acc[0] * inv_n, lp = acc[1] * inv_n;
+    losses[0] = (float)(-lp + kl); losses[1] = (float)kl; losses[2] = (float)lp;
+  }
+}
+
+__global__ void tanhize_fwd_kernel(const float* x, const float* xmin, const float* xmax, float* out, long long n, int dim) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dim) return;
+  int d = (int)(i % dim);
+  float t = (x[i] - xmin[d]) / (xmax[d] - xmin[d]);
+  out[i] = fminf(fmaxf(t, 0.f), 1.f) * 2.f - 1.f;
+}
+__global__ void tanhize_bwd_kernel(const float* x, const float* xmin, const float* xmax, float* out, long long n, int dim) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dim) return;
+  int d = (int)(i % dim);
+  out[i] = (x[i] * 0.5f + 0.5f) * (xmax[d] - xmin[d]) + xmin[d];
+}
+// analyzer.py:111-127: record = [sp(513) | ap(513) | f0 | en | spk]; feature = Tanhize(sp), speaker = int64(last)
+__global__ void unpack_records_kernel(const float* rec, long long n, int rec_floats, int sp_dim,
+                                      const float* xmin, const float* xmax, float* x, long long* y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * sp_dim) return;
+  long long f = i / sp_dim; int d = (int)(i - f * sp_dim);
+  float v = rec[f * rec_floats + d];
+  if (xmin) { float t = (v - xmin[d]) / (xmax[d] - xmin[d]); v = fminf(fmaxf(t, 0.f), 1.f) * 2.f - 1.f; }
+  x[i] = v;
+  if (d == 0) y[f] = (long long)rec[f * rec_floats + rec_floats - 1];
+}
+
+}  // namespace npvc

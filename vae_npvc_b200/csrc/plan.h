@@ -1,0 +1,101 @@
+// Launch plan of the ConvVAE hot path: buffers, strided row views, operand packs and the op list.
+// Pure host C++ (no CUDA): built once from the architecture in npvc_create(), interpreted by
+// engine.cu on the GPU and by tests/plan_interp.py in numpy on the CPU.
+//
+// Every layer of the reference graph (model/vae.py:72-103) is one of three GEMM forms over
+// channels-last, per-frame zero-padded activations (frames stay in the batch dimension, F5/F6):
+//   (F) C[rows,N]  = A_view[rows,K] . B[K,N]          rows = (frame, position)
+//   (W) dB[K,N]   += A_view[rows,K]^T . dC_view[rows,N]
+// where A_view row (frame f, j) is the CONTIGUOUS window of K floats starting at
+// f*frame_stride + j*row_stride + off of a padded channels-last buffer (an im2col that costs
+// nothing: strided conv windows overlap in memory).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/npvc_b200.h"
+
+namespace npvc {
+
+enum Space { SP_NONE = 0, SP_WS = 1, SP_THETA = 2, SP_GRAD = 3, SP_AW = 4, SP_ADW = 5, SP_USER = 6 };
+enum UserSlot { U_X = 0, U_Y = 1, U_EPS = 2 };
+enum Phase { PH_PACK = 0, PH_ENC = 1, PH_SAMPLE = 2, PH_DEC = 3, PH_LOSS = 4, PH_BWD = 5, PH_FINAL = 6 };
+enum OpKind {
+  OP_GEMM = 0, OP_WGRAD = 1, OP_LN_FWD = 2, OP_LN_BWD = 3, OP_SAMPLE = 4, OP_SAMPLE_BWD = 5,
+  OP_RECON = 6, OP_SEGSUM = 7, OP_COLSUM = 8, OP_ZERO = 9, OP_PACK = 10, OP_UNPACK = 11
+};
+
+struct Ref {
+  int space = SP_NONE;
+  int buf = -1;        // SP_WS: buffer index; SP_USER: slot
+  int64_t off = 0;     // float offset (theta / grad / arena spaces)
+};
+
+struct View {
+  Ref ref;
+  int R = 1;           // rows per frame
+  int64_t fs = 0;      // frame stride (floats)
+  int rs = 0;          // row stride (floats)
+  int off = 0;         // in-frame offset of column 0 of row 0 (may be negative)
+  int flen = 0;        // valid in-frame range [0, flen) (used when pred)
+  int pred = 0;        // predicate every element on the in-frame range
+};
+
+struct Buf {
+  std::string name;
+  int64_t per_frame = 0;   // floats per frame
+  int64_t fixed = 0;       // floats independent of n
+  int train_only = 0;
+};
+
+struct Op {
+  int kind = 0, phase = 0;
+  std::string name;
+  // GEMM / WGRAD
+  View A, C;             // WGRAD: C is the dC view
+  int K = 0, N = 0;
+  Ref B; int ldb = 0;    // GEMM: B operand; WGRAD: output dB
+  Ref bias[3]; int bias_mod = 1;
+  Ref table; int table_ld = 0;   // + labels (U_Y): C[r,:] += table[y[r], :]
+  int64_t rows_fixed = 0;        // >0: row count independent of n (A is not per-frame)
+  int a_scalar = 0;              // A needs the scalar (unaligned / predicated) loader
+  // LN_FWD / LN_BWD
+  Ref in, xhat, aout, rstd, gamma, beta, dgamma, dbeta, dbias;
+  int L = 0, Cn = 0, out_flen = 0, out_off = 0;
+  // misc
+  Ref r0, r1, r2, r3;
+  int64_t count = 0; int per_frame_count = 0;
+  int i0 = 0, i1 = 0;
+};
+
+struct Param {
+  std::string name;
+  int64_t off = 0, size = 0;
+  int rank = 0; int shape[4] = {0, 0, 0, 0};
+  int fan_in = 0, fan_out = 0, init = 0;
+};
+
+struct Plan {
+  npvc_arch arch;
+  std::vector<Param> params;
+  int64_t n_params = 0;
+  std::vector<Buf> bufs;
+  std::vector<Op> ops;
+  int64_t arena_w = 0;       // floats: packed operand matrices (fwd part first)
+  int64_t arena_dw = 0;      // floats: packed weight gradients (mirror of the fwd part; ws buffer "arena_dw")
+  std::vector<int32_t> pack_src;     // [arena_w]  theta index or -1
+  std::vector<int32_t> unpack_ptr;   // [n_params+1] CSR over theta
+  std::vector<int32_t> unpack_idx;   // positions in arena_dw
+  int buf_z = -1, buf_mu = -1, buf_lv = -1, buf_xh = -1, buf_acc = -1, buf_hz = -1, buf_adw = -1, buf_dptab = -1;
+  int out_dim = 0;           // 513
+  std::string json;
+
+  int64_t ws_floats(int64_t chunk, bool train) const;
+  int64_t buf_offset(int b, int64_t chunk, bool train) const;   // float offset inside ws
+};
+
+// Returns empty string on success, else an error message.
+std::string build_plan(const npvc_arch& a, Plan& p);
+
+}  // namespace npvc
