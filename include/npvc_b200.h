@@ -143,6 +143,12 @@ int npvc_unpack_records(npvc_handle* h, const float* d_records, int64_t n, int32
                         int32_t sp_dim, const float* d_xmin, const float* d_xmax,
                         float* d_x, int64_t* d_y, void* stream);
 
+/* Per-op device timing (bench.py roofline): enable != 0 brackets every op of the following calls
+ * with CUDA events on the launching stream; npvc_profile_json() synchronises those events and
+ * returns [{"name","kind","calls","ms","rows","K","N"}...] aggregated per op, then clears them. */
+int npvc_profile_enable(npvc_handle* h, int32_t enable);
+const char* npvc_profile_json(npvc_handle* h);
+
 /* Debug: copy a named workspace buffer of the LAST pass (first chunk) to a device pointer.
  * Returns its float count per frame (negative on error). */
 int64_t npvc_debug_buffer(npvc_handle* h, const char* name, const void* d_ws, float* d_out,

@@ -1,0 +1,198 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the fp64 oracle on the same
+seeded inputs.  Tolerances (written here, SURVEY 8c / north_star): per-tensor max|a-b|/max|b|
+<= 1e-4 for z, mu, logsigma^2, xh; <= 1e-3 for gradients and post-Adam parameters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import convvae_ref as R
+
+pytestmark = pytest.mark.gpu
+TOL_OUT, TOL_GRAD = 1e-4, 1e-3
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "convvae_vcc2016_n4.npz")
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+@pytest.fixture(scope="module")
+def eng(arch):
+    from vae_npvc_b200.engine import Engine
+    return Engine(arch, "cuda:0")
+
+
+def _dev_inputs(eng, arch, n, seed=1, n_speakers=None):
+    x, y, eps = R.make_inputs(arch, n, seed=seed, n_speakers=n_speakers)
+    d = eng.device
+    return (x, y, eps, torch.tensor(x, dtype=torch.float32, device=d), torch.tensor(y, device=d),
+            torch.tensor(eps, dtype=torch.float32, device=d))
+
+
+def _check_against_oracle(eng, arch, n, seed=1, n_speakers=None):
+    P = R.init_params(arch, 0)
+    x, y, eps, xd, yd, ed = _dev_inputs(eng, arch, n, seed, n_speakers)
+    theta = torch.tensor(R.flatten_params(arch, P), device=eng.device)
+    grad = torch.full_like(theta, float("nan"))
+    out = eng.loss_fwd_bwd(theta, xd, yd, ed, grad=grad)
+    torch.cuda.synchronize()
+    # oracle sees the same fp32-rounded inputs and weights
+    P32 = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in P.items()}
+    ref = R.forward(arch, P32, x.astype(np.float32), y, eps.astype(np.float32), with_grads=True)
+    for k in ("z", "mu", "lv", "xh"):
+        assert rel(out[k], ref[k]) <= TOL_OUT, (k, rel(out[k], ref[k]))
+    lo = out["losses"].cpu().numpy()
+    for i, k in enumerate(("G", "D_KL", "logP")):
+        assert abs(lo[i] - ref[k]) <= 1e-5 * abs(ref[k]) + 1e-6, k
+    gref = R.flatten_params(arch, ref["grads"], np.float64)
+    g = grad.cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all()
+    for t in eng.table:
+        sl = slice(t["offset"], t["offset"] + t["size"])
+        den = np.abs(gref[sl]).max()
+        if den == 0:
+            assert np.abs(g[sl]).max() == 0, t["name"]
+        else:
+            assert np.abs(g[sl] - gref[sl]).max() / den <= TOL_GRAD, t["name"]
+    return theta, grad, gref, P32
+
+
+@pytest.mark.parametrize("n", [1, 8, 37])
+def test_loss_fwd_bwd_matches_oracle(eng, arch, n):
+    _check_against_oracle(eng, arch, n)
+
+
+def test_single_speaker_batch(eng, arch):
+    """cfg1 shape: all labels 0 -> the other 9 embedding rows get exactly zero gradient."""
+    _check_against_oracle(eng, arch, 16, n_speakers=1)
+
+
+def test_golden_fixture(eng, arch):
+    g = np.load(GOLD)
+    P = R.init_params(arch, 0)
+    x, y, eps, xd, yd, ed = _dev_inputs(eng, arch, int(g["n"]))
+    theta = torch.tensor(R.flatten_params(arch, P), device=eng.device)
+    grad = torch.empty_like(theta)
+    out = eng.loss_fwd_bwd(theta, xd, yd, ed, grad=grad)
+    for k in ("z", "mu", "lv", "xh"):
+        assert rel(out[k], g[k]) <= TOL_OUT, k
+    assert rel(grad[::int(g["stride"])], g["grad_sample"]) <= TOL_GRAD
+    m = torch.zeros_like(theta); v = torch.zeros_like(theta)
+    eng.adam_step(theta, grad, m, v, 1, 1e-4, 0.5, 0.999)
+    assert rel(theta[::int(g["stride"])], g["adam_theta_sample"]) <= 1e-5
+
+
+def test_adam_steps_match_tf_form(eng, arch):
+    theta, grad, gref, P32 = _check_against_oracle(eng, arch, 8)
+    th = R.flatten_params(arch, P32, np.float64); m = np.zeros_like(th); v = np.zeros_like(th)
+    md = torch.zeros_like(theta); vd = torch.zeros_like(theta)
+    for t in (1, 2, 3):
+        eng.adam_step(theta, grad, md, vd, t, 1e-4, 0.5, 0.999, 1e-8, 0.5)       # grad_scale 1/2 (two ranks)
+        th, m, v = R.adam_step(th, 0.5 * gref, m, v, t, 1e-4, 0.5, 0.999)
+    assert rel(theta, th) <= 1e-5 and rel(md, m) <= TOL_GRAD and rel(vd, v) <= 2 * TOL_GRAD
+
+
+def test_chunked_equals_unchunked(arch, eng):
+    from vae_npvc_b200.engine import Engine
+    small = Engine(arch, "cuda:0", max_chunk=16)
+    P = R.init_params(arch, 0)
+    x, y, eps, xd, yd, ed = _dev_inputs(eng, arch, 40)
+    theta = torch.tensor(R.flatten_params(arch, P), device=eng.device)
+    g1 = torch.empty_like(theta); g2 = torch.empty_like(theta)
+    o1 = eng.loss_fwd_bwd(theta, xd, yd, ed, grad=g1)
+    o2 = small.loss_fwd_bwd(theta, xd, yd, ed, grad=g2)
+    for k in ("z", "mu", "lv", "xh"):
+        assert torch.equal(o1[k], o2[k]), k                      # per-frame results are bit-identical
+    assert rel(o2["losses"], o1["losses"].cpu().numpy()) < 1e-6
+    assert rel(g2, g1.cpu().numpy()) < 1e-4                      # summation order over frames differs
+
+
+def test_encode_decode_match_oracle(eng, arch):
+    """convert.py path: encode -> mu (no sampling), decode(z, y_target)."""
+    P = R.init_params(arch, 0)
+    P32 = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in P.items()}
+    x, y, eps, xd, yd, ed = _dev_inputs(eng, arch, 23)
+    theta = torch.tensor(R.flatten_params(arch, P), device=eng.device)
+    mu, lv = eng.encode(theta, xd)
+    mu_ref, lv_ref = R.encode(arch, P32, x.astype(np.float32))
+    assert rel(mu, mu_ref) <= TOL_OUT and rel(lv, lv_ref) <= TOL_OUT
+    yt = torch.full_like(yd, 9)
+    xh = eng.decode(theta, mu, yt)
+    xh_ref = R.decode(arch, P32, mu.cpu().numpy().astype(np.float64), np.full(23, 9))
+    assert rel(xh, xh_ref.reshape(23, -1)) <= TOL_OUT
+    z = eng.sample(mu, lv, ed)
+    assert rel(z, mu_ref + eps.astype(np.float32) * np.sqrt(np.exp(lv_ref))) <= TOL_OUT
+
+
+def test_full_size_properties(eng, arch):
+    """cfg2 size (N = 64*256 = 16,384): size-independent properties instead of an oracle run --
+    frame permutation equivariance (F5/F6), finite outputs, losses = mean of per-frame terms,
+    and agreement of a 64-frame slice with the oracle."""
+    n = 16384
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.rand(n, 513, generator=g) * 2 - 1).cuda(); y = torch.randint(0, 10, (n,), generator=g).cuda()
+    eps = torch.randn(n, 128, generator=g).cuda()
+    P = R.init_params(arch, 0)
+    theta = torch.tensor(R.flatten_params(arch, P), device=eng.device)
+    grad = torch.empty_like(theta)
+    out = eng.loss_fwd_bwd(theta, x, y, eps, grad=grad)
+    assert all(torch.isfinite(out[k]).all() for k in ("z", "mu", "lv", "xh")) and torch.isfinite(grad).all()
+    perm = torch.randperm(n, generator=g).cuda()
+    g2 = torch.empty_like(theta)
+    out2 = eng.loss_fwd_bwd(theta, x[perm].contiguous(), y[perm].contiguous(), eps[perm].contiguous(), grad=g2)
+    for k in ("z", "mu", "xh"):
+        assert torch.equal(out2[k], out[k][perm]), k
+    assert rel(g2, grad.cpu().numpy()) < 2e-4
+    # losses are means of per-frame terms
+    xh, mu, lv = out["xh"].double(), out["mu"].double(), out["lv"].double()
+    c = float(np.float32(1.0) + np.float32(1e-6))
+    logp = (-0.5 * (R.LOG_2PI + (x.double() - xh) ** 2 / c)).sum(1).mean()
+    kl = (0.5 * (-lv + (lv.exp() + mu * mu) / c - 1)).sum(1).mean()
+    lo = out["losses"].double().cpu()
+    assert abs(lo[2] - logp.cpu()) < 1e-5 * abs(logp.cpu()) and abs(lo[1] - kl.cpu()) < 1e-5 * abs(kl.cpu())
+    # a slice against the oracle
+    P32 = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in P.items()}
+    sl = slice(5000, 5064)
+    ref = R.forward(arch, P32, x[sl].cpu().numpy(), y[sl].cpu().numpy(), eps[sl].cpu().numpy())
+    for k in ("z", "mu", "lv", "xh"):
+        assert rel(out[k][sl], ref[k]) <= TOL_OUT, k
+
+
+def test_tanhize_and_record_reader(eng):
+    g = torch.Generator(device="cpu").manual_seed(3)
+    xmin = torch.randn(513, generator=g) - 3; xmax = xmin + 1 + torch.rand(513, generator=g)
+    rec = torch.randn(50, 1029, generator=g); rec[:, -1] = torch.randint(0, 10, (50,), generator=g).float()
+    x, y = eng.unpack_records(rec.cuda(), 513, xmin.cuda(), xmax.cuda())
+    ref = R.tanhize_forward(rec[:, :513].double().numpy(), xmin.double().numpy(), xmax.double().numpy())
+    assert rel(x, ref) < 1e-6 and torch.equal(y.cpu(), rec[:, -1].long())
+    back = eng.tanhize_backward(x, xmin.cuda(), xmax.cuda())
+    assert rel(back, R.tanhize_backward(ref, xmin.double().numpy(), xmax.double().numpy())) < 1e-6
+    fwd = eng.tanhize_forward(rec[:, :513].contiguous().cuda(), xmin.cuda(), xmax.cuda())
+    assert torch.equal(fwd, x)
+
+
+def test_plugin_surface_trains(arch, tmp_path):
+    """main.py call shape: MODEL(arch) -> loss -> TRAINER(loss, arch, args, dirs).train(...)."""
+    from importlib import import_module
+    MODEL = getattr(import_module("model.vae"), "ConvVAE")
+    TRAINER = getattr(import_module("trainer.vae"), "VAETrainer")
+    a = dict(arch); a["training"] = dict(arch["training"], max_iter=30, lr=1e-3)
+    machine = MODEL(a)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    image = (torch.rand(64, 1, 513, 1, generator=g) * 2 - 1).cuda(); label = torch.randint(0, 10, (64,), generator=g).cuda()
+    loss = machine.loss(image, label)
+    assert set(loss.keys()) == {"G", "D_KL", "logP"}
+    g0 = float(loss["G"])
+    dirs = {"logdir": str(tmp_path / "train"), "logdir_root": str(tmp_path), "restore_from": str(tmp_path / "train")}
+    trainer = TRAINER(loss, a, None, dirs)
+    trainer.train(nIter=a["training"]["max_iter"], machine=machine)
+    g1 = float(machine.loss(image, label)["G"])
+    assert trainer.global_step == 30 and g1 < g0
+    assert os.path.exists(os.path.join(dirs["logdir"], "model.ckpt-30"))
+    z = machine.encode(image)
+    xh = machine.decode(z, label)
+    assert z.shape == (64, 128) and xh.shape == (64, 513, 1, 1) and machine.generate == machine.decode

@@ -1,0 +1,107 @@
+"""CPU tests of the host side of the product: C-ABI surface, parameter table, launch plan
+(executed by the numpy interpreter against the oracle), error behaviour without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import plan_interp as PI
+from oracle import convvae_ref as R
+from vae_npvc_b200 import lib
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(__file__)), "include", "npvc_b200.h")
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / (np.abs(np.asarray(b)).max() + 1e-300))
+
+
+def test_library_exports_every_declared_symbol():
+    src = open(HEADER).read()
+    declared = set(re.findall(r"\b(npvc_[a-z_0-9]+)\s*\(", src))
+    assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
+    dll = C.CDLL(lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(dll, name), name
+    assert b"sm_100a" in lib.load().npvc_version()
+
+
+def test_param_table_matches_reference_variable_order(arch):
+    h = lib.Handle(arch)
+    tab = h.param_table()
+    specs = R.param_specs(arch)
+    assert h.param_count() == 939162 and len(tab) == 44
+    off = 0
+    for t, (name, shape, fi, fo, kind) in zip(tab, specs):
+        assert t["name"] == name and t["shape"] == tuple(shape) and t["offset"] == off
+        assert (t["fan_in"], t["fan_out"]) == (fi, fo) and t["init"] == {"glorot": 0, "zeros": 1, "ones": 2}[kind]
+        off += t["size"]
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_plan_matches_oracle(arch, n):
+    h = lib.Handle(arch)
+    plan = h.plan()
+    tables = {k: h.plan_table(k) for k in ("pack_src", "unpack_ptr", "unpack_idx")}
+    P = R.init_params(arch, 0)
+    x, y, eps = R.make_inputs(arch, n)
+    out = PI.Interp(plan, tables, R.flatten_params(arch, P, np.float64), n, x, y, eps).loss_fwd_bwd()
+    ref = R.forward(arch, P, x, y, eps, with_grads=True)
+    for k in ("mu", "lv", "z", "xh"):
+        assert rel(out[k], ref[k]) < 1e-12, k
+    for k in ("D_KL", "logP", "G"):
+        assert rel(out[k], ref[k]) < 1e-6, k
+    gref = R.flatten_params(arch, ref["grads"], np.float64)
+    for t in h.param_table():
+        sl = slice(t["offset"], t["offset"] + t["size"])
+        assert rel(out["grad"][sl], gref[sl]) < 1e-9, t["name"]
+
+
+def test_pack_tables_are_consistent(arch):
+    h = lib.Handle(arch)
+    plan = h.plan()
+    src, ptr, idx = (h.plan_table(k) for k in ("pack_src", "unpack_ptr", "unpack_idx"))
+    assert len(src) == plan["arena_w"] and len(ptr) == plan["n_params"] + 1
+    assert src.max() < plan["n_params"] and src.min() >= -1
+    assert idx.max() < plan["arena_dw"] and (np.diff(ptr) >= 0).all() and ptr[-1] == len(idx)
+    # every conv / dense kernel element receives its gradient from the packed arena; the
+    # 1025-tap kernel gathers one full Toeplitz diagonal (513 entries) per tap and channel
+    tab = {t["name"]: t for t in h.param_table()}
+    t3 = tab["Generator/conv2d_transpose_3/kernel"]
+    cnt = np.diff(ptr)[t3["offset"]:t3["offset"] + t3["size"]].reshape(1025, 8)
+    assert cnt[512].min() == 513 and cnt[0].max() == 1 and cnt.sum() == 513 * 513 * 8
+    e0 = tab["Encoder/Conv2d-0/Conv2d-0/kernel"]
+    assert (np.diff(ptr)[e0["offset"]:e0["offset"] + e0["size"]] == 1).all()
+    lnp = tab["Encoder/Conv2d-0/layernorm.scale"]
+    assert (np.diff(ptr)[lnp["offset"]:lnp["offset"] + lnp["size"]] == 0).all()
+
+
+def test_workspace_sizes(arch):
+    h = lib.Handle(arch, 4096)
+    a, b = h.workspace_bytes(100, False), h.workspace_bytes(100, True)
+    assert 0 < a < b
+    assert h.workspace_bytes(4096, True) == h.workspace_bytes(100000, True)      # chunked above max_chunk
+    assert h.workspace_bytes(200, True) > b
+
+
+def test_bad_architecture_raises_value_error(arch):
+    bad = dict(arch); bad["encoder"] = dict(arch["encoder"]); bad["encoder"]["output"] = [16, 32, 64, 128, 255]
+    with pytest.raises(ValueError):
+        lib.Handle(bad)
+    bad2 = dict(arch); bad2["generator"] = dict(arch["generator"]); bad2["generator"]["output"] = [32, 16, 8]
+    with pytest.raises(AssertionError):          # model/vae.py:37-39 _sanity_check
+        lib.Handle(bad2)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_gpu_fails_loudly(arch):
+    from vae_npvc_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(arch)
+    h = lib.Handle(arch)
+    buf = np.zeros(1024, np.float32)
+    rc = h.lib.npvc_pack_weights(h.h, buf.ctypes.data, 256 * 1024 * 1024 * 16, 1 << 40, None)
+    assert rc != 0 and ("CUDA" in lib.last_error() or "device" in lib.last_error())

@@ -1,0 +1,102 @@
+"""``trainer.vae.VAETrainer`` -- the reference's trainer plugin surface (``trainer/vae.py:9-111``,
+ctor contract of ``trainer/gan.py:14-23``) over the B200-native engine.
+
+``VAETrainer(loss, arch, args, dirs)`` / ``.train(nIter, machine=None, summary_op=None)`` keep the
+reference signatures.  ``_optimize`` is TF-form Adam over ALL variables (one flat buffer);
+``train`` is the ``for step in range(max_iter): sess.run(opt['g'])`` hot loop with the same 60 s
+status line and 300 s checkpoint cadence.  Under ``torch.distributed`` (world_size > 1) the flat
+gradient is all-reduced once per step over NCCL before the replicated Adam step.
+"""
+import logging
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+
+class VAETrainer(object):
+    def __init__(self, loss, arch, args, dirs):
+        self.loss = loss
+        self.arch = arch
+        self.args = args
+        self.dirs = dirs
+        self.machine = getattr(loss, 'machine', None)
+        self.opt = self._optimize()
+        if dirs and dirs.get('logdir'):
+            os.makedirs(dirs['logdir'], exist_ok=True)
+            logging.basicConfig(level=logging.INFO, filename=os.path.join(dirs['logdir'], 'training.log'))
+
+    # -- optimiser (trainer/vae.py:10-28) ---------------------------------------------------
+    def _optimize(self):
+        tr = self.arch['training']
+        self.lr, self.b1, self.b2 = tr['lr'], tr['beta1'], tr['beta2']
+        self.global_step = 0
+        self._state = None
+        return {'g': self._train_step, 'global_step': lambda: self.global_step}
+
+    def _ensure_state(self, machine):
+        if self._state is None or self._state['machine'] is not machine:
+            th = machine.theta
+            self._state = dict(machine=machine, grad=torch.empty_like(th), m=torch.zeros_like(th), v=torch.zeros_like(th),
+                               losses=torch.zeros(3, device=th.device))
+            self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            if self.world > 1:      # identical replicas: broadcast rank 0's initial variables once
+                dist.broadcast(th, src=0)
+        return self._state
+
+    def _train_step(self, x=None, y=None, eps=None):
+        """One ``sess.run(opt['g'])``: fwd + bwd (+ all-reduce) + Adam on one batch of frames."""
+        machine = self.machine
+        st = self._ensure_state(machine)
+        if x is None:
+            x, y = self.loss.feed
+            if hasattr(x, 'dequeue'):
+                x, y = x.dequeue()
+        out = machine.loss_and_grad(x, y, st['grad'], eps=eps)
+        if self.world > 1:
+            dist.all_reduce(st['grad'], op=dist.ReduceOp.SUM)      # one 3.76 MB bucket over NVLink
+        self.global_step += 1
+        machine.engine.adam_step(machine.theta, st['grad'], st['m'], st['v'], self.global_step,
+                                 self.lr, self.b1, self.b2, 1e-8, 1.0 / self.world)
+        st['losses'] = out['losses']
+        return out['losses']
+
+    # -- status line (trainer/vae.py:31-52) -------------------------------------------------
+    def _refresh_status(self, sess=None):
+        losses = self._state['losses'].tolist() if self._state else [float('nan')] * 3
+        msg = 'Iter {:05d}: '.format(self.global_step)
+        msg += 'log P(x|z, y) = {:.3e} '.format(losses[2])
+        msg += 'D_KL(z) = {:.3e} '.format(losses[1])
+        print('\r{}'.format(msg), end='', flush=True)
+        logging.info(msg)
+        return msg
+
+    def save(self, path=None):
+        """Checkpoint: the variables under their TF names + Adam slots + global_step (the
+        reference's Supervisor autosave, trainer/vae.py:78-84, as one torch file)."""
+        st = self._state
+        path = path or os.path.join(self.dirs['logdir'], 'model.ckpt-{}'.format(self.global_step))
+        torch.save({'variables': {k: v.cpu() for k, v in self.machine.variables().items()},
+                    'adam_m': st['m'].cpu(), 'adam_v': st['v'].cpu(), 'global_step': self.global_step}, path)
+        return path
+
+    # -- hot loop (trainer/vae.py:73-99) ----------------------------------------------------
+    def train(self, nIter=None, machine=None, summary_op=None, status_secs=60, save_secs=300):
+        if machine is not None:
+            self.machine = machine
+        if self.machine is None:
+            raise ValueError('VAETrainer needs the machine: pass `machine=` or a loss from machine.loss()')
+        rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+        t_status = t_save = time.time()
+        for step in range(self.arch['training']['max_iter'] if nIter is None else min(nIter, self.arch['training']['max_iter'])):
+            self.opt['g']()
+            now = time.time()
+            if rank0 and now - t_status >= status_secs:
+                self._refresh_status(); t_status = now
+            if rank0 and self.dirs and self.dirs.get('logdir') and now - t_save >= save_secs:
+                self.save(); t_save = now
+        torch.cuda.synchronize()
+        if rank0 and self.dirs and self.dirs.get('logdir'):
+            self._refresh_status()
+            self.save()

@@ -1,0 +1,46 @@
+"""Architecture dictionaries (the hyper-parameter source the reference reads from
+``architecture-*.json``; consumed keys per SURVEY 2 #7).  The values below restate
+``architecture-vae-vcc2016.json:2-28`` so tests / bench do not depend on a file copied from the
+reference; a user's own JSON file is passed through ``ConvVAE(arch)`` verbatim."""
+import copy
+import json
+
+_VCC2016_VAE = {
+    "mode": "VAE",
+    "hwc": [513, 1, 1],
+    "z_dim": 128,
+    "y_dim": 10,
+    "y_emb_dim": 128,
+    "encoder": {
+        "kernel": [[7, 1]] * 5,
+        "stride": [[3, 1]] * 5,
+        "output": [16, 32, 64, 128, 256],
+        "l2-reg": 1e-6,
+    },
+    "generator": {
+        "hwc": [19, 1, 81],
+        "merge_dim": 171,
+        "kernel": [[9, 1], [7, 1], [7, 1], [1025, 1]],
+        "stride": [[3, 1], [3, 1], [3, 1], [1, 1]],
+        "output": [32, 16, 8, 1],
+        "l2-reg": 1e-6,
+    },
+    "training": {
+        "datadir": "./dataset/vcc2016/bin/Training Set/*/*.bin",
+        "batch_size": 16,
+        "epoch": 200,
+        "lr": 1e-4,
+        "beta1": 0.5,
+        "beta2": 0.999,
+        "max_iter": 60000,
+    },
+}
+
+
+def vcc2016_vae_arch():
+    return copy.deepcopy(_VCC2016_VAE)
+
+
+def write_arch_json(path, arch=None):
+    with open(path, "w") as f:
+        json.dump(arch or _VCC2016_VAE, f, indent=4)

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "kernels.cuh"
 #include "plan.h"
@@ -21,6 +22,10 @@ struct npvc_handle {
   int64_t launches = 0;
   int64_t last_chunk = 0; bool last_train = false;
   int sm_count = 148;
+  bool profiling = false;
+  struct Ev { int op; cudaEvent_t a, b; long long rows; };
+  std::vector<Ev> events;
+  std::string profile_json;
 };
 
 static thread_local std::string g_err;
@@ -193,10 +198,19 @@ int run_op(Ctx& c, const Op& o) {
 }
 
 int run_phase(Ctx& c, int phase) {
-  for (const Op& o : c.h->plan.ops) {
+  const std::vector<Op>& ops = c.h->plan.ops;
+  for (size_t i = 0; i < ops.size(); i++) {
+    const Op& o = ops[i];
     if (o.phase != phase) continue;
     if (!c.grad && (o.kind == OP_UNPACK)) continue;
+    npvc_handle::Ev ev{(int)i, nullptr, nullptr, 0};
+    if (c.h->profiling) {
+      cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+      ev.rows = (o.kind == OP_GEMM || o.kind == OP_WGRAD) ? (o.rows_fixed ? o.rows_fixed : c.n * o.A.R) : c.n;
+      cudaEventRecord(ev.a, c.st);
+    }
     int rc = run_op(c, o);
+    if (c.h->profiling) { cudaEventRecord(ev.b, c.st); c.h->events.push_back(ev); }
     if (rc) return rc;
   }
   return NPVC_OK;
@@ -293,6 +307,35 @@ int64_t npvc_plan_table(const npvc_handle* h, const char* name, int32_t* out, in
 }
 
 int64_t npvc_launch_count(const npvc_handle* h) { return h ? h->launches : 0; }
+
+int npvc_profile_enable(npvc_handle* h, int32_t enable) {
+  if (!h) return fail(NPVC_ERR_ARG, "null handle");
+  h->profiling = enable != 0;
+  return NPVC_OK;
+}
+
+const char* npvc_profile_json(npvc_handle* h) {
+  if (!h) return "[]";
+  const std::vector<Op>& ops = h->plan.ops;
+  std::vector<double> ms(ops.size(), 0.0); std::vector<long long> calls(ops.size(), 0), rows(ops.size(), 0);
+  for (auto& e : h->events) {
+    cudaEventSynchronize(e.b);
+    float t = 0.f; cudaEventElapsedTime(&t, e.a, e.b);
+    ms[e.op] += t; calls[e.op]++; rows[e.op] += e.rows;
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  h->events.clear();
+  std::string js = "["; bool first = true; char buf[512];
+  for (size_t i = 0; i < ops.size(); i++) {
+    if (!calls[i]) continue;
+    snprintf(buf, sizeof buf, "%s{\"name\":\"%s\",\"kind\":%d,\"calls\":%lld,\"ms\":%.6f,\"rows\":%lld,\"K\":%d,\"N\":%d}",
+             first ? "" : ",", ops[i].name.c_str(), ops[i].kind, calls[i], ms[i], rows[i], ops[i].K, ops[i].N);
+    js += buf; first = false;
+  }
+  js += "]";
+  h->profile_json = js;
+  return h->profile_json.c_str();
+}
 
 int npvc_pack_weights(npvc_handle* h, const float* d_theta, void* d_ws, int64_t ws_bytes, void* stream) {
   int rc = check_ws(h, 1, false, ws_bytes, d_ws); if (rc) return rc;

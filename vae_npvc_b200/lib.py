@@ -51,6 +51,8 @@ SYMBOLS = {
     "npvc_tanhize_forward": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P]),
     "npvc_tanhize_backward": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P]),
     "npvc_unpack_records": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
+    "npvc_profile_enable": (C.c_int, [_P, _I32]),
+    "npvc_profile_json": (C.c_char_p, [_P]),
     "npvc_debug_buffer": (_I64, [_P, C.c_char_p, _P, _P, _I64, _P]),
 }
 
@@ -167,3 +169,9 @@ class Handle:
 
     def launch_count(self):
         return int(self.lib.npvc_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        check(self.lib.npvc_profile_enable(self._h, 1 if on else 0))
+
+    def profile(self):
+        return json.loads(self.lib.npvc_profile_json(self._h).decode())
