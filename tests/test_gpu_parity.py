@@ -83,17 +83,24 @@ def test_golden_fixture(eng, arch):
     assert rel(grad[::int(g["stride"])], g["grad_sample"]) <= TOL_GRAD
     m = torch.zeros_like(theta); v = torch.zeros_like(theta)
     eng.adam_step(theta, grad, m, v, 1, 1e-4, 0.5, 0.999)
-    assert rel(theta[::int(g["stride"])], g["adam_theta_sample"]) <= 1e-5
+    assert rel(theta[::int(g["stride"])], g["adam_theta_sample"]) <= TOL_GRAD
 
 
 def test_adam_steps_match_tf_form(eng, arch):
+    """The Adam kernel against the TF-form closed form on IDENTICAL gradients (<= 1e-6), then the
+    end-to-end post-Adam parameters against the oracle's own gradients (<= 1e-3: Adam's m/sqrt(v)
+    normalisation turns noise-level differences of near-zero gradients into +-lr steps)."""
     theta, grad, gref, P32 = _check_against_oracle(eng, arch, 8)
+    g_gpu = grad.cpu().numpy().astype(np.float64)
     th = R.flatten_params(arch, P32, np.float64); m = np.zeros_like(th); v = np.zeros_like(th)
+    th2, m2, v2 = th.copy(), m.copy(), v.copy()
     md = torch.zeros_like(theta); vd = torch.zeros_like(theta)
     for t in (1, 2, 3):
         eng.adam_step(theta, grad, md, vd, t, 1e-4, 0.5, 0.999, 1e-8, 0.5)       # grad_scale 1/2 (two ranks)
-        th, m, v = R.adam_step(th, 0.5 * gref, m, v, t, 1e-4, 0.5, 0.999)
-    assert rel(theta, th) <= 1e-5 and rel(md, m) <= TOL_GRAD and rel(vd, v) <= 2 * TOL_GRAD
+        th, m, v = R.adam_step(th, 0.5 * g_gpu, m, v, t, 1e-4, 0.5, 0.999)
+        th2, m2, v2 = R.adam_step(th2, 0.5 * gref, m2, v2, t, 1e-4, 0.5, 0.999)
+    assert rel(theta, th) <= 1e-6 and rel(md, m) <= 1e-6 and rel(vd, v) <= 1e-6
+    assert rel(theta, th2) <= TOL_GRAD
 
 
 def test_chunked_equals_unchunked(arch, eng):
