@@ -88,9 +88,20 @@ class Interp:
                 continue
             getattr(self, "op_%d" % op["kind"])(op)
 
+    @staticmethod
+    def _tf32_rna(a):
+        # cvt.rna.tf32.f32: round the fp32 magnitude to 10 mantissa bits, ties away from zero
+        b = np.asarray(a, np.float32).view(np.uint32)
+        return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
     def op_10(self, op):   # PACK
         src = self.tables["pack_src"]
-        self.aw[:] = np.where(src >= 0, self.theta[np.maximum(src, 0)], 0.0)
+        mode = np.where(src >= 0, src >> 29, 0)
+        val = np.where(src >= 0, self.theta[np.maximum(src, 0) & ((1 << 29) - 1)], 0.0)
+        v32 = val.astype(np.float32)
+        hi = self._tf32_rna(v32)
+        lo = self._tf32_rna(v32 - hi)
+        self.aw[:] = np.where(mode == 1, hi, np.where(mode == 2, lo, val))
 
     def op_11(self, op):   # UNPACK
         ptr, idx = self.tables["unpack_ptr"], self.tables["unpack_idx"]
@@ -103,8 +114,13 @@ class Interp:
     def op_0(self, op):    # GEMM
         rows, K, N = self._rows(op), op["K"], op["N"]
         A = self.gather(op["A"], rows, K)
-        barr, boff = self.flat(op["B"])
-        Bm = barr[boff:boff + K * op["ldb"]].reshape(K, op["ldb"])[:, :N]
+        if op.get("umma"):
+            # tensor-core path: K-major [N, Kpad] tf32 hi + lo packs (3xTF32 ~ fp32 product)
+            kp = op["kpad"]
+            Bm = (self.aw[op["bu_hi"]:op["bu_hi"] + N * kp] + self.aw[op["bu_lo"]:op["bu_lo"] + N * kp]).reshape(N, kp)[:, :K].T
+        else:
+            barr, boff = self.flat(op["B"])
+            Bm = barr[boff:boff + K * op["ldb"]].reshape(K, op["ldb"])[:, :N]
         Cv = A @ Bm
         cols = np.arange(N) % op["bias_mod"]
         for key in ("bias0", "bias1", "bias2"):

@@ -99,7 +99,8 @@ def test_adam_steps_match_tf_form(eng, arch):
         eng.adam_step(theta, grad, md, vd, t, 1e-4, 0.5, 0.999, 1e-8, 0.5)       # grad_scale 1/2 (two ranks)
         th, m, v = R.adam_step(th, 0.5 * g_gpu, m, v, t, 1e-4, 0.5, 0.999)
         th2, m2, v2 = R.adam_step(th2, 0.5 * gref, m2, v2, t, 1e-4, 0.5, 0.999)
-    assert rel(theta, th) <= 1e-6 and rel(md, m) <= 1e-6 and rel(vd, v) <= 1e-6
+    # v: (1 - beta2) is formed in fp32 from fp32(0.999) exactly as TF's ApplyAdam does (1.3e-5 off the real 0.001)
+    assert rel(theta, th) <= 1e-6 and rel(md, m) <= 1e-6 and rel(vd, v) <= 5e-5
     assert rel(theta, th2) <= TOL_GRAD
 
 

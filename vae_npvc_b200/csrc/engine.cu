@@ -7,8 +7,18 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
+#include <cstdlib>
+#include <map>
+
 #include "kernels.cuh"
 #include "plan.h"
+#include "umma_gemm.cuh"
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 using namespace npvc;
 
@@ -22,6 +32,12 @@ struct npvc_handle {
   int64_t launches = 0;
   int64_t last_chunk = 0; bool last_train = false;
   int sm_count = 148;
+  bool use_umma = true;
+  std::string umma_allow;            // debug: comma-separated op names allowed on the tensor path ("" = all)
+  PFN_tmapEncodeTiled encode = nullptr;
+  struct TMaps { const void* a; const void* b; long long frames; int bn; CUtensorMap tA, tBh, tBl; };
+  std::map<int, TMaps> tmaps;        // per-op tensor-map cache
+  int64_t umma_launches = 0;
   bool profiling = false;
   struct Ev { int op; cudaEvent_t a, b; long long rows; };
   std::vector<Ev> events;
@@ -108,7 +124,128 @@ void launch_wgrad(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
   else launch_wgrad_k<16>(g, scalar, sms, st);
 }
 
-int run_op(Ctx& c, const Op& o) {
+// ---- tcgen05 path ---------------------------------------------------------------------------
+int pick_bn(int N, int* n_tiles) {
+  if (N <= 256) { *n_tiles = 1; return (N + 15) / 16 * 16; }
+  int best_bn = 256, best_t = (N + 255) / 256; long long best_cost = (long long)best_bn * best_t;
+  const int t0 = (N + 255) / 256;
+  for (int t = t0; t <= t0 + 6; t++) {
+    int bn = ((N + t - 1) / t + 15) / 16 * 16;
+    if (bn > 256) continue;
+    long long cost = (long long)bn * t;
+    if (cost < best_cost) { best_cost = cost; best_bn = bn; best_t = t; }
+  }
+  *n_tiles = best_t; return best_bn;
+}
+
+int launch_umma(Ctx& c, const Op& o, int op_index) {
+  npvc_handle* h = c.h; cudaStream_t st = c.st;
+  const int R = o.A.R;
+  const int RB = R, FB = (R == 1) ? 128 : 128 / R;
+  const long long frames = c.n;                       // rows = frames * R
+  int n_tiles = 1; const int BN = pick_bn(o.N, &n_tiles);
+  float* a_base = resolve(c, o.A.ref) + o.A.off;
+  float* b_hi = c.ws + o.bu_hi; float* b_lo = c.ws + o.bu_lo;
+  auto it = h->tmaps.find(op_index);
+  if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != frames || it->second.bn != BN) {
+    npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = frames; tm.bn = BN;
+    cuuint64_t gdA[3] = {(cuuint64_t)o.K, (cuuint64_t)R, (cuuint64_t)frames};
+    cuuint64_t gsA[2] = {(cuuint64_t)((R == 1 ? o.A.fs : o.A.rs) * 4), (cuuint64_t)(o.A.fs * 4)};
+    cuuint32_t bxA[3] = {32, (cuuint32_t)RB, (cuuint32_t)FB};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = h->encode(&tm.tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a_base, gdA, gsA, bxA, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed for " + o.name + " code " + std::to_string((int)r));
+    cuuint64_t gdB[2] = {(cuuint64_t)o.kpad, (cuuint64_t)o.N};
+    cuuint64_t gsB[1] = {(cuuint64_t)o.kpad * 4};
+    cuuint32_t bxB[2] = {32, (cuuint32_t)BN};
+    for (int w = 0; w < 2; w++) {
+      r = h->encode(w ? &tm.tBl : &tm.tBh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w ? b_lo : b_hi, gdB, gsB, bxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed for " + o.name + " code " + std::to_string((int)r));
+    }
+    h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
+  }
+  UmmaArgs g;
+  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + 31) / 32;
+  const int stage_bytes = 2 * 16384 + 2 * BN * 128;
+  int tc = 32; while (tc < 2 * BN) tc *= 2; g.tmem_cols = tc;     // main + correction accumulators
+  // short reductions are latency-bound per CTA (TMEM alloc, first TMA, epilogue): co-schedule
+  // several CTAs per SM (smem / TMEM permitting) instead of deep pipelines
+  int ctas = g.kblocks <= 8 ? 4 : (g.kblocks <= 32 ? 2 : 1);
+  if (ctas > 512 / tc) ctas = 512 / tc;
+  while (ctas > 1 && (225 * 1024) / ctas - 2048 < stage_bytes) ctas--;
+  int stages = ((225 * 1024) / ctas - 2048) / stage_bytes; if (stages > 4) stages = 4; if (stages > g.kblocks) stages = g.kblocks;
+  if (stages < 1) stages = 1;
+  g.stages = stages; g.rows_tile = RB * FB; g.FB = FB; g.rows = frames * R;
+  g.nblocks = 0; g.blocks_per_split = 0; g.out = nullptr; g.ld = 0; g.A = dview(c, o.A); g.D = g.A;
+  g.C = dview(c, o.C);
+  g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
+  g.table = resolve(c, o.table); g.labels = reinterpret_cast<const long long*>(c.y); g.table_ld = o.table_ld;
+  if (g.table && !g.labels) return fail(NPVC_ERR_ARG, "labels (y) required");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 1) + 16;
+  const long long m_tiles = (frames + FB - 1) / FB;
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
+  umma_gemm_kernel<false><<<grid, 192, smem, st>>>(it->second.tA, it->second.tBh, it->second.tBl, g);
+  h->launches++; h->umma_launches++;
+  return NPVC_OK;
+}
+
+// dB[K,N] += A_view^T . dC_view on the tensor cores: operands read straight from the activation /
+// gradient views by the producer warps (no packs, no TMA), 32-row reduction blocks split across
+// CTAs, partial tiles added with RED.ADD.
+int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
+  (void)op_index;
+  npvc_handle* h = c.h; cudaStream_t st = c.st;
+  int n_tiles = 1, BN;
+  if (o.N <= 256) BN = (o.N + 15) / 16 * 16;
+  else BN = pick_bn(o.N, &n_tiles);
+  const int m_tiles = (o.K + 127) / 128;
+  UmmaArgs g;
+  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = 0;
+  const int stage_bytes = 2 * 16384 + 2 * BN * 128;
+  int tc = 32; while (tc < 2 * BN) tc *= 2; g.tmem_cols = tc;
+  g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R;
+  g.nblocks = (g.rows + 31) / 32;
+  long long tiles = (long long)m_tiles * n_tiles;
+  int ctas = 2; if (ctas > 512 / tc) ctas = 512 / tc; if (ctas < 1) ctas = 1;
+  while (ctas > 1 && (225 * 1024) / ctas - 2048 < stage_bytes) ctas--;
+  int stages = ((225 * 1024) / ctas - 2048) / stage_bytes; if (stages > 4) stages = 4; if (stages < 1) stages = 1;
+  g.stages = stages; g.rows_tile = 32; g.FB = 0;
+  g.C = dview(c, o.C); g.bias0 = g.bias1 = g.bias2 = nullptr; g.bias_mod = 1; g.table = nullptr; g.labels = nullptr; g.table_ld = 0;
+  g.A = dview(c, o.A); g.D = dview(c, o.C);
+  long long S = ((long long)ctas * 2 * h->sm_count + tiles - 1) / tiles;
+  long long maxS = g.nblocks / 8; if (maxS < 1) maxS = 1;
+  if (S > maxS) S = maxS;
+  g.blocks_per_split = (g.nblocks + S - 1) / S;
+  S = (g.nblocks + g.blocks_per_split - 1) / g.blocks_per_split;
+  g.out = resolve(c, o.B); g.ld = o.ldb;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 1) + 16;
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)S);
+  CUtensorMap dummy; memset(&dummy, 0, sizeof dummy);
+  umma_gemm_kernel<true><<<grid, 320, smem, st>>>(dummy, dummy, dummy, g);   // 8 producer warps
+  h->launches++; h->umma_launches++;
+  return NPVC_OK;
+}
+
+bool umma_allowed(const npvc_handle* h, const Op& o) {
+  if (!o.umma || !h->encode) return false;
+  if (h->umma_allow.empty()) return true;
+  return ("," + h->umma_allow + ",").find("," + o.name + ",") != std::string::npos;
+}
+
+int run_op(Ctx& c, const Op& o, int op_index) {
   npvc_handle* h = c.h; const Plan& p = h->plan; cudaStream_t st = c.st;
   switch (o.kind) {
     case OP_PACK: {
@@ -128,6 +265,7 @@ int run_op(Ctx& c, const Op& o) {
       g.table = resolve(c, o.table); g.labels = reinterpret_cast<const long long*>(c.y); g.table_ld = o.table_ld;
       if (g.rows <= 0) break;
       if (g.table && !g.labels) return fail(NPVC_ERR_ARG, "labels (y) required");
+      if (umma_allowed(h, o)) { int rc = launch_umma(c, o, op_index); if (rc) return rc; break; }
       launch_gemm(g, !view_vec_ok(g.A), st); h->launches++; break;
     }
     case OP_WGRAD: {
@@ -135,6 +273,7 @@ int run_op(Ctx& c, const Op& o) {
       g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R; g.rows_per_split = 0; g.tiles_n = 0;
       if (g.rows <= 0) break;
       if (!view_vec_ok(g.D)) return fail(NPVC_ERR_ARG, "wgrad dC view must be 16B aligned: " + o.name);
+      if (umma_allowed(h, o)) { int rc = launch_umma_wgrad(c, o, op_index); if (rc) return rc; break; }
       launch_wgrad(g, !view_vec_ok(g.A), h->sm_count, st); h->launches++; break;
     }
     case OP_LN_FWD: {
@@ -209,7 +348,7 @@ int run_phase(Ctx& c, int phase) {
       ev.rows = (o.kind == OP_GEMM || o.kind == OP_WGRAD) ? (o.rows_fixed ? o.rows_fixed : c.n * o.A.R) : c.n;
       cudaEventRecord(ev.a, c.st);
     }
-    int rc = run_op(c, o);
+    int rc = run_op(c, o, (int)i);
     if (c.h->profiling) { cudaEventRecord(ev.b, c.st); c.h->events.push_back(ev); }
     if (rc) return rc;
   }
@@ -224,6 +363,13 @@ int ensure_tables(npvc_handle* h) {
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
   const Plan& p = h->plan;
+  if (h->use_umma) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    cudaError_t ee = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (ee != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver (needed by the tcgen05 path)");
+    h->encode = (PFN_tmapEncodeTiled)fn;
+  }
   CUDA_TRY(cudaMalloc(&h->d_pack_src, p.pack_src.size() * 4));
   CUDA_TRY(cudaMalloc(&h->d_unpack_ptr, p.unpack_ptr.size() * 4));
   CUDA_TRY(cudaMalloc(&h->d_unpack_idx, (p.unpack_idx.size() + 1) * 4));
@@ -257,7 +403,11 @@ const char* npvc_version(void) { return "npvc_b200 0.1 (sm_100a)"; }
 int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (!arch || !out) return fail(NPVC_ERR_ARG, "null argument");
   npvc_handle* h = new npvc_handle();
-  std::string err = build_plan(*arch, h->plan);
+  const char* eu = getenv("NPVC_UMMA");            // "0" = CUDA-core GEMMs only (debug / A-B comparisons)
+  h->use_umma = !(eu && eu[0] == '0');
+  const char* ea = getenv("NPVC_UMMA_OPS");
+  if (ea) h->umma_allow = ea;
+  std::string err = build_plan(*arch, h->plan, h->use_umma);
   if (!err.empty()) { delete h; return fail(NPVC_ERR_ARG, "unsupported architecture: " + err); }
   if (max_chunk > 0) h->max_chunk = max_chunk;
   *out = h;

@@ -581,7 +581,20 @@ __global__ void colsum_kernel(const float* in, float* out, int N, int rows) {
 // =============================================================================================
 __global__ void pack_kernel(const float* theta, const int* src, float* arena, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { int s = src[i]; arena[i] = (s >= 0) ? theta[s] : 0.f; }
+  if (i < n) {
+    int s = src[i];
+    float v = 0.f;
+    if (s >= 0) {
+      const int mode = s >> 29;                     // plan.h: PACK_MODE_SHIFT
+      v = theta[s & ((1 << 29) - 1)];
+      if (mode) {                                   // tf32 split for the tcgen05 operands
+        uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        if (mode == 1) v = __uint_as_float(h);
+        else { uint32_t l; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h))); v = __uint_as_float(l); }
+      }
+    }
+    arena[i] = v;
+  }
 }
 
 __global__ void unpack_kernel(const float* adw, const int* ptr, const int* idx, float* grad, long long n) {

@@ -78,7 +78,7 @@ int64_t Plan::buf_offset(int b, int64_t chunk, bool train) const {
 }
 int64_t Plan::ws_floats(int64_t chunk, bool train) const { return buf_offset((int)bufs.size(), chunk, train); }
 
-std::string build_plan(const npvc_arch& a, Plan& p) {
+std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   p = Plan();
   p.arch = a;
   Builder B(p);
@@ -507,6 +507,34 @@ std::string build_plan(const npvc_arch& a, Plan& p) {
     Op& u = B.op(OP_UNPACK, PH_FINAL, "unpack"); u.count = p.n_params;
   }
 
+  // ---------------------------------------------------------------- tcgen05 routing
+  // GEMM-shaped (F) ops go to the tensor cores: A by TMA from the strided view (whole frames per
+  // 128-row tile), B as K-major [N, Kpad] hi / lo packs derived from the CUDA-core pack.
+  if (use_umma) {
+    if (p.n_params > PACK_INDEX_MASK) return "too many parameters for the pack index encoding";
+    for (Op& o : p.ops) {
+      if (o.kind == OP_WGRAD) {
+        // (W) form on the tensor cores: operands come straight from the activation / gradient views
+        if (o.rows_fixed || o.K < 64 || o.N < 32 || o.C.pred) continue;     // tiny K/N: CUDA-core wgrad wins
+        o.umma = 1;
+        continue;
+      }
+      if (o.kind != OP_GEMM || o.rows_fixed || o.A.pred || o.a_scalar) continue;
+      if (o.A.R > 128 || o.K < 32 || o.N < 16) continue;
+      if (o.A.fs % 4 || o.A.rs % 4 || o.A.off % 4 || o.A.off < 0 || o.B.space != SP_AW) continue;
+      o.kpad = rup(o.K, 32);
+      const int64_t sz = (int64_t)o.N * o.kpad;
+      o.bu_hi = B.aw_alloc(sz); o.bu_lo = B.aw_alloc(sz);
+      for (int n = 0; n < o.N; n++) for (int k = 0; k < o.K; k++) {
+        int32_t src = p.pack_src[o.B.off + (int64_t)k * o.ldb + n];
+        if (src < 0) continue;
+        p.pack_src[o.bu_hi + (int64_t)n * o.kpad + k] = src | (1 << PACK_MODE_SHIFT);
+        p.pack_src[o.bu_lo + (int64_t)n * o.kpad + k] = src | (2 << PACK_MODE_SHIFT);
+      }
+      o.umma = 1;
+    }
+  }
+
   // ---------------------------------------------------------------- JSON
   std::ostringstream js;
   js << "{\"n_params\":" << p.n_params << ",\"arena_w\":" << p.arena_w << ",\"arena_dw\":" << p.arena_dw
@@ -532,7 +560,8 @@ std::string build_plan(const npvc_arch& a, Plan& p) {
     js << ",\"ldb\":" << o.ldb << ","; json_ref(js, "bias0", o.bias[0]); js << ","; json_ref(js, "bias1", o.bias[1]);
     js << ","; json_ref(js, "bias2", o.bias[2]); js << ",\"bias_mod\":" << o.bias_mod << ",";
     json_ref(js, "table", o.table); js << ",\"table_ld\":" << o.table_ld << ",\"rows_fixed\":" << o.rows_fixed
-       << ",\"a_scalar\":" << o.a_scalar << ",";
+       << ",\"a_scalar\":" << o.a_scalar << ",\"umma\":" << o.umma << ",\"bu_hi\":" << o.bu_hi << ",\"bu_lo\":" << o.bu_lo
+       << ",\"kpad\":" << o.kpad << ",";
     json_ref(js, "in", o.in); js << ","; json_ref(js, "xhat", o.xhat); js << ","; json_ref(js, "aout", o.aout); js << ",";
     json_ref(js, "rstd", o.rstd); js << ","; json_ref(js, "gamma", o.gamma); js << ","; json_ref(js, "beta", o.beta); js << ",";
     json_ref(js, "dgamma", o.dgamma); js << ","; json_ref(js, "dbeta", o.dbeta); js << ","; json_ref(js, "dbias", o.dbias);

@@ -60,6 +60,8 @@ struct Op {
   Ref table; int table_ld = 0;   // + labels (U_Y): C[r,:] += table[y[r], :]
   int64_t rows_fixed = 0;        // >0: row count independent of n (A is not per-frame)
   int a_scalar = 0;              // A needs the scalar (unaligned / predicated) loader
+  // tcgen05 path (OP_GEMM only): B as K-major [N, Kpad] tf32 hi / lo packs in arena_w
+  int umma = 0; int64_t bu_hi = 0, bu_lo = 0; int kpad = 0;
   // LN_FWD / LN_BWD
   Ref in, xhat, aout, rstd, gamma, beta, dgamma, dbeta, dbias;
   int L = 0, Cn = 0, out_flen = 0, out_off = 0;
@@ -95,7 +97,12 @@ struct Plan {
   int64_t buf_offset(int b, int64_t chunk, bool train) const;   // float offset inside ws
 };
 
-// Returns empty string on success, else an error message.
-std::string build_plan(const npvc_arch& a, Plan& p);
+// pack_src entries: -1 = zero; else theta index | mode << 29 (0 copy, 1 tf32 hi, 2 tf32 lo of the residual)
+constexpr int PACK_MODE_SHIFT = 29;
+constexpr int32_t PACK_INDEX_MASK = (1 << PACK_MODE_SHIFT) - 1;
+
+// Returns empty string on success, else an error message.  use_umma: route GEMM-shaped ops to the
+// tcgen05 kernel (adds their hi / lo operand packs).
+std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma);
 
 }  // namespace npvc

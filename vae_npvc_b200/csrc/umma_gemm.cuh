@@ -1,0 +1,368 @@
+// tcgen05 (5th-gen tensor core) view-GEMM for sm_100a:
+//   C[rows,N] = A_view[rows,K] . B[K,N] (+ bias + table[label])      fp32 in, fp32 out
+// computed as 3xTF32 (A = Ah + Al, B = Bh + Bl;  Ah.Bh + Al.Bh + Ah.Bl, fp32 accumulate in TMEM)
+// so that the result holds the 1e-4 fp32 parity bar of the path (single-pass TF32 does not).
+//
+//   warp 0      TMA producer: A fp32 tile [128 rows x 32 k] straight from the strided conv-window
+//               view (3-D tensor map k / row-in-frame / frame: im2col for free), B hi / lo tiles
+//               [BN x 32 k] (K-major packs written by pack_kernel), 128B swizzle, mbarrier tx.
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs / k-block), tcgen05.commit.
+//   warps 2-5   converters: split the landed A tile into tf32 hi (in place) + lo (second buffer),
+//               fence.proxy.async, hand the stage to the MMA warp; afterwards the epilogue:
+//               tcgen05.ld the 128 x BN accumulator, add bias / per-speaker table, store through
+//               the (optionally predicated) output view.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace npvc {
+
+struct UmmaArgs {
+  int K, N;              // logical GEMM sizes (wgrad: dB is [K, N])
+  int BN;                // N tile (multiple of 16, 16..256; wgrad: multiple of 32)
+  int kblocks;           // forward: ceil(K / 32) reduction blocks
+  int stages;            // smem pipeline depth
+  int rows_tile;         // forward: valid rows per 128-row M tile (whole frames); wgrad: valid rows per 32-row block
+  int FB;                // frames per tile / block
+  long long rows;        // total rows
+  int tmem_cols;         // power of two >= max(2*BN, 32): main + correction accumulators
+  DView C;               // forward: output view
+  const float* bias0; const float* bias1; const float* bias2; int bias_mod;
+  const float* table; const long long* labels; int table_ld;
+  // wgrad only: dB[K,N] += A_view^T . D_view over 32-row reduction blocks
+  DView A, D;
+  long long nblocks;     // total 32-row reduction blocks
+  long long blocks_per_split;
+  float* out; int ld;    // dB accumulated with atomics
+};
+
+namespace umma {
+
+constexpr int BM = 128, BK = 32, A_TILE_BYTES = BM * BK * 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    long long t = clock64();
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart), sm_100 descriptor
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address            bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset       bits [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version = 1   bits [46,48)
+  d |= (uint64_t)2 << 61;                         // layout = SWIZZLE_128B    bits [61,64)
+  return d;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+  uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return u;
+}
+
+}  // namespace umma
+
+template <bool WG>
+__global__ void __launch_bounds__(WG ? 320 : 192)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                 const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
+  using namespace umma;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_tile_bytes = (uint32_t)g.BN * 128u;
+  const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
+  const uint32_t bar_base = sbase + (uint32_t)g.stages * stage_bytes;
+  // barriers: full[s], ready[s], empty[s], accum ; then the TMEM base pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto ready_bar = [&](int s) { return bar_base + 8u * (uint32_t)(g.stages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * g.stages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (uint32_t)(3 * g.stages);
+  const uint32_t tmem_slot = accum_bar + 8u;
+  uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));     // generic pointer to sbase
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int n0 = tile_n * g.BN;
+  // reduction range of this CTA
+  long long kb_begin = 0, kb_end = g.kblocks;
+  if (WG) {
+    kb_begin = (long long)blockIdx.z * g.blocks_per_split;
+    kb_end = kb_begin + g.blocks_per_split; if (kb_end > g.nblocks) kb_end = g.nblocks;
+    if (kb_begin >= kb_end) return;                     // uniform per CTA
+  }
+  const int nkb = (int)(kb_end - kb_begin);
+
+  if (warp == 0 && lane == 0) {
+    if (!WG) { prefetch_tmap(&tmA); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl); }
+    for (int s = 0; s < g.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), (uint32_t)(blockDim.x / 32 - 2)); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (forward only)
+    if (!WG && lane == 0) {
+      const uint32_t tx = (uint32_t)g.rows_tile * 128u + 2u * b_tile_bytes;
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % g.stages; const uint32_t ph = (uint32_t)((kb / g.stages) & 1);
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        mbar_expect_tx(full_bar(s), tx);
+        tma_load_3d(st, &tmA, full_bar(s), kb * BK, 0, tile_m * g.FB);
+        tma_load_2d(st + 2u * A_TILE_BYTES, &tmBh, full_bar(s), kb * BK, n0);
+        tma_load_2d(st + 2u * A_TILE_BYTES + b_tile_bytes, &tmBl, full_bar(s), kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // both operands K-major (MN-major tf32 operands return zeros on this part: tools/umma_mn_probe.cu)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint64_t kstep = 2ull;                    // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (addr >> 4) field
+      const int ksteps = 4;
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
+        mbar_wait(ready_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        const uint64_t ah = make_sdesc(st), al = make_sdesc(st + A_TILE_BYTES);
+        const uint64_t bh = make_sdesc(st + 2u * A_TILE_BYTES), bl = make_sdesc(st + 2u * A_TILE_BYTES + b_tile_bytes);
+        for (int k4 = 0; k4 < ksteps; k4++) {
+          // Tensor-core fp32 accumulation truncates (measured: ~2^-24 |acc| drift per MMA), so the
+          // main products and the 2^-11-sized corrections go to SEPARATE accumulators: the big one
+          // sees K/8 adds instead of 3K/8, the small one's drift is negligible; summed in the epilogue.
+          const uint64_t o = (uint64_t)k4 * kstep;
+          const uint32_t first = (i > 0 || k4 > 0) ? 1u : 0u;
+          mma_tf32(tmem_base, ah + o, bh + o, idesc, first);
+          mma_tf32(tmem_base + (uint32_t)g.BN, al + o, bh + o, idesc, first);
+          mma_tf32(tmem_base + (uint32_t)g.BN, ah + o, bl + o, idesc, 1u);
+        }
+        umma_commit(empty_bar(s));                  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(accum_bar);                       // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ converters (4 warps = 128 threads)
+    const int ct = (threadIdx.x - 64) & 127;
+    if (!WG) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
+        mbar_wait(full_bar(s), ph);
+        float4* ahp = reinterpret_cast<float4*>(gen_base + (size_t)s * stage_bytes);
+        uint4* alp = reinterpret_cast<uint4*>(gen_base + (size_t)s * stage_bytes + A_TILE_BYTES);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int idx = ct + q * 128;
+          float4 v = ahp[idx];
+          uint4 h, l;
+          h.x = cvt_tf32(v.x); h.y = cvt_tf32(v.y); h.z = cvt_tf32(v.z); h.w = cvt_tf32(v.w);
+          l.x = cvt_tf32(v.x - __uint_as_float(h.x)); l.y = cvt_tf32(v.y - __uint_as_float(h.y));
+          l.z = cvt_tf32(v.z - __uint_as_float(h.z)); l.w = cvt_tf32(v.w - __uint_as_float(h.w));
+          reinterpret_cast<uint4*>(ahp)[idx] = h;
+          alp[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(s));
+      }
+    } else {
+      // wgrad: these warps ARE the producers.  Thread ct owns operand row ct of the K-major tiles
+      // (A: view column k = tile_m*128 + ct; D: view column n = n0 + ct [+128]) and walks the 32
+      // reduction rows of the block: coalesced global loads (a warp reads 128 contiguous bytes of
+      // one view row), tf32 hi/lo split, 16-byte stores into the 128B-swizzled K-major layout
+      // (row ct, 16B chunk c ^ (ct & 7): conflict-free, this is what the swizzle is for).
+      const int ka = tile_m * 128 + ct;
+      const bool a_col_ok = ka < g.K;
+      const int nb0 = n0 + ct, nb1 = n0 + ct + 128;
+      const bool d0_ok = (ct < g.BN) && (nb0 < g.N), d1_ok = (ct + 128 < g.BN) && (nb1 < g.N);
+      const uint32_t rowoff = (uint32_t)(ct >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
+      const uint32_t rowoff1 = (uint32_t)((ct + 128) >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
+      const int pg = (warp - 2) >> 2;                 // producer group: rows [16*pg, 16*pg + 16) of the block
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        uint8_t* stp = gen_base + (size_t)s * stage_bytes;
+        const long long r0 = (kb_begin + i) * 32 + pg * 16;
+        long long f = r0 / g.A.R; int j = (int)(r0 - f * g.A.R);
+        // all 16 rows x (A, D, D+128) loads first: memory-level parallelism hides the L2 / HBM latency
+        float va[16], v0[16], v1[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          float a = 0.f, d0 = 0.f, d1 = 0.f;
+          if (r0 + e < g.rows) {
+            if (a_col_ok) {
+              const int inf = j * g.A.rs + g.A.off + ka;
+              if (!g.A.pred || (inf >= 0 && inf < g.A.flen)) a = __ldg(g.A.p + f * g.A.fs + inf);
+            }
+            const float* dp = g.D.p + f * g.D.fs + j * g.D.rs + g.D.off;
+            if (d0_ok) d0 = __ldg(dp + nb0);
+            if (d1_ok) d1 = __ldg(dp + nb1);
+          }
+          va[e] = a; v0[e] = d0; v1[e] = d1;
+          if (++j == g.A.R) { j = 0; f++; }
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+          const int c = pg * 4 + c4;
+          const uint32_t chunk = (uint32_t)((c ^ (ct & 7)) * 16);
+          uint4 h, l;
+          h.x = cvt_tf32(va[c4 * 4 + 0]); h.y = cvt_tf32(va[c4 * 4 + 1]); h.z = cvt_tf32(va[c4 * 4 + 2]); h.w = cvt_tf32(va[c4 * 4 + 3]);
+          l.x = cvt_tf32(va[c4 * 4 + 0] - __uint_as_float(h.x)); l.y = cvt_tf32(va[c4 * 4 + 1] - __uint_as_float(h.y));
+          l.z = cvt_tf32(va[c4 * 4 + 2] - __uint_as_float(h.z)); l.w = cvt_tf32(va[c4 * 4 + 3] - __uint_as_float(h.w));
+          *reinterpret_cast<uint4*>(stp + rowoff + chunk) = h;
+          *reinterpret_cast<uint4*>(stp + A_TILE_BYTES + rowoff + chunk) = l;
+          if (ct < g.BN) {
+            h.x = cvt_tf32(v0[c4 * 4 + 0]); h.y = cvt_tf32(v0[c4 * 4 + 1]); h.z = cvt_tf32(v0[c4 * 4 + 2]); h.w = cvt_tf32(v0[c4 * 4 + 3]);
+            l.x = cvt_tf32(v0[c4 * 4 + 0] - __uint_as_float(h.x)); l.y = cvt_tf32(v0[c4 * 4 + 1] - __uint_as_float(h.y));
+            l.z = cvt_tf32(v0[c4 * 4 + 2] - __uint_as_float(h.z)); l.w = cvt_tf32(v0[c4 * 4 + 3] - __uint_as_float(h.w));
+            *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + rowoff + chunk) = h;
+            *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + b_tile_bytes + rowoff + chunk) = l;
+          }
+          if (ct + 128 < g.BN) {
+            h.x = cvt_tf32(v1[c4 * 4 + 0]); h.y = cvt_tf32(v1[c4 * 4 + 1]); h.z = cvt_tf32(v1[c4 * 4 + 2]); h.w = cvt_tf32(v1[c4 * 4 + 3]);
+            l.x = cvt_tf32(v1[c4 * 4 + 0] - __uint_as_float(h.x)); l.y = cvt_tf32(v1[c4 * 4 + 1] - __uint_as_float(h.y));
+            l.z = cvt_tf32(v1[c4 * 4 + 2] - __uint_as_float(h.z)); l.w = cvt_tf32(v1[c4 * 4 + 3] - __uint_as_float(h.w));
+            *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + rowoff1 + chunk) = h;
+            *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + b_tile_bytes + rowoff1 + chunk) = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(s));
+      }
+    }
+    if (warp >= 6) goto done;                         // second producer group has no epilogue share
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int lq = warp & 3;                        // TMEM lane quarter this warp may access
+    const int row_local = lq * 32 + lane;
+    const long long r = WG ? (long long)tile_m * 128 + row_local : (long long)tile_m * g.rows_tile + row_local;
+    const bool row_ok = WG ? (r < g.K) : ((row_local < g.rows_tile) && (r < g.rows));
+    float* cp = nullptr; int inf = 0; const float* trow = nullptr;
+    if (row_ok) {
+      if (WG) {
+        cp = g.out + r * g.ld;
+      } else {
+        const long long f = r / g.C.R; const int j = (int)(r - f * g.C.R);
+        inf = j * g.C.rs + g.C.off;
+        cp = g.C.p + f * g.C.fs + inf;
+        if (g.table) trow = g.table + (long long)g.labels[f] * g.table_ld;
+      }
+    }
+    for (int c0 = 0; c0 < g.BN; c0 += 16) {
+      uint32_t v[16], w[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr) : "memory");
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+            "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+          : "r"(taddr + (uint32_t)g.BN) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!row_ok) continue;
+      if (WG) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          const int n = n0 + c0 + e;
+          if (n < g.N) atomicAdd(cp + n, __uint_as_float(v[e]) + __uint_as_float(w[e]));
+        }
+        continue;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int nb = n0 + c0 + q * 4;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int n = nb + e;
+          float t = __uint_as_float(v[q * 4 + e]) + __uint_as_float(w[q * 4 + e]);
+          if (n < g.N) {
+            const int bi = n % g.bias_mod;
+            if (g.bias0) t += g.bias0[bi];
+            if (g.bias1) t += g.bias1[bi];
+            if (g.bias2) t += g.bias2[bi];
+            if (trow) t += trow[n];
+          }
+          o[e] = t;
+        }
+        bool full = (nb + 4 <= g.N);
+        if (g.C.pred) full = full && (inf + nb >= 0) && (inf + nb + 4 <= g.C.flen);
+        if (full && ((reinterpret_cast<uintptr_t>(cp + nb) & 15) == 0)) {
+          *reinterpret_cast<float4*>(cp + nb) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int n = nb + e;
+            bool ok = n < g.N;
+            if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
+            if (ok) cp[n] = o[e];
+          }
+        }
+      }
+    }
+  }
+done:
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace npvc
