@@ -1,0 +1,79 @@
+"""Frame reader / loader tests.  CPU: record files, shuffle-buffer semantics.  GPU: the pinned async
+loader end to end against a numpy restatement of analyzer.py:111-127."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import analyzer
+from oracle import convvae_ref as R
+
+
+def _write_bins(tmp_path, n_files=3, frames=(40, 25, 61), seed=0):
+    rs = np.random.RandomState(seed)
+    paths, allrec = [], []
+    for i in range(n_files):
+        rec = rs.randn(frames[i], analyzer.FEAT_DIM).astype(np.float32)
+        rec[:, -1] = i % 10                                    # speaker id as float (analyzer.py:62-66)
+        p = tmp_path / ("spk%d" % i); p.mkdir()
+        f = p / "utt.bin"; rec.tofile(str(f)); paths.append(str(f)); allrec.append(rec)
+    return paths, np.concatenate(allrec)
+
+
+def test_record_constants():
+    assert (analyzer.SP_DIM, analyzer.FEAT_DIM, analyzer.RECORD_BYTES) == (513, 1029, 4116)
+    assert len(analyzer.SPEAKERS) == 10
+
+
+def test_shuffle_reader_is_a_permutation_stream(tmp_path):
+    paths, allrec = _write_bins(tmp_path)
+    rf = analyzer.RecordFiles(paths)
+    assert rf.n_records() == len(allrec)
+    rd = analyzer.ShuffleReader(rf, batch_size=7, capacity=32, min_after_dequeue=16, seed=1)
+    keys = {tuple(r[:4]) for r in allrec}
+    seen = []
+    out = np.empty((7, analyzer.FEAT_DIM), np.float32)
+    for _ in range(3 * len(allrec) // 7):
+        rd.next_batch(out)
+        assert rd.fill >= rd.min_after                         # never below min_after_dequeue
+        for r in out:
+            assert tuple(r[:4]) in keys                        # every row is a real record, unmodified
+            seen.append(tuple(r[:4]))
+    # sampling without replacement from the buffer: each record appears about once per epoch
+    counts = {k: seen.count(k) for k in keys}
+    assert max(counts.values()) <= 4 and sum(counts.values()) == len(seen)
+    assert len(set(seen[:7])) == 7                             # no duplicates inside a batch
+    assert seen[:7] != [tuple(r[:4]) for r in allrec[:7]]      # and it is shuffled
+
+
+def test_whole_file_reader(tmp_path):
+    paths, allrec = _write_bins(tmp_path, 1, (33,))
+    feats = list(analyzer.read_whole_features(os.path.join(str(tmp_path), "*", "*.bin")))
+    assert len(feats) == 1 and feats[0]["sp"].shape == (33, 513) and feats[0]["speaker"].dtype == np.int64
+    assert np.array_equal(feats[0]["f0"], allrec[:, 1026]) and np.array_equal(feats[0]["en"], allrec[:, 1027])
+
+
+@pytest.mark.gpu
+def test_async_loader_matches_reference_semantics(tmp_path, arch):
+    from vae_npvc_b200.engine import Engine
+    paths, allrec = _write_bins(tmp_path)
+    rs = np.random.RandomState(3)
+    xmin = rs.randn(513) - 3; xmax = xmin + 1 + rs.rand(513)
+    eng = Engine(arch)
+    norm = analyzer.Tanhize(xmin=xmin, xmax=xmax, engine=eng)
+    image, label = analyzer.read(os.path.join(str(tmp_path), "*", "*.bin"), batch_size=16, capacity=64,
+                                 min_after_dequeue=32, normalizer=norm, engine=eng)
+    lut = {tuple(np.round(R.tanhize_forward(r[:513].astype(np.float64), xmin, xmax)[:6], 5)): r for r in allrec}
+    for _ in range(5):
+        x, y = image.dequeue()
+        assert x.shape == (16, 1, 513, 1) and y.shape == (16,) and y.dtype == torch.int64 and x.is_cuda
+        xs = x.reshape(16, 513).cpu().numpy()
+        for i in range(16):
+            r = lut[tuple(np.round(xs[i, :6].astype(np.float64), 5))]
+            assert np.abs(xs[i] - R.tanhize_forward(r[:513].astype(np.float64), xmin, xmax)).max() < 1e-5
+            assert int(y[i]) == int(r[-1])
+    xp, yp = image.dequeue(peek=True)
+    xq, yq = label.dequeue()
+    assert torch.equal(xp, xq) and torch.equal(yp, yq)          # both handles share one queue; peek does not consume
+    image.loader.close()

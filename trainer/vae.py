@@ -14,6 +14,8 @@ import time
 import torch
 import torch.distributed as dist
 
+from vae_npvc_b200.parallel import allreduce_flat_grad_, broadcast_params_, world_info
+
 
 class VAETrainer(object):
     def __init__(self, loss, arch, args, dirs):
@@ -40,9 +42,8 @@ class VAETrainer(object):
             th = machine.theta
             self._state = dict(machine=machine, grad=torch.empty_like(th), m=torch.zeros_like(th), v=torch.zeros_like(th),
                                losses=torch.zeros(3, device=th.device))
-            self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-            if self.world > 1:      # identical replicas: broadcast rank 0's initial variables once
-                dist.broadcast(th, src=0)
+            self.world = world_info()[1]
+            broadcast_params_(th, src=0)       # identical replicas: rank 0's initial variables
         return self._state
 
     def _train_step(self, x=None, y=None, eps=None):
@@ -54,11 +55,10 @@ class VAETrainer(object):
             if hasattr(x, 'dequeue'):
                 x, y = x.dequeue()
         out = machine.loss_and_grad(x, y, st['grad'], eps=eps)
-        if self.world > 1:
-            dist.all_reduce(st['grad'], op=dist.ReduceOp.SUM)      # one 3.76 MB bucket over NVLink
+        scale = allreduce_flat_grad_(st['grad'], self.world)      # one 3.76 MB bucket over NVLink
         self.global_step += 1
         machine.engine.adam_step(machine.theta, st['grad'], st['m'], st['v'], self.global_step,
-                                 self.lr, self.b1, self.b2, 1e-8, 1.0 / self.world)
+                                 self.lr, self.b1, self.b2, 1e-8, scale)
         st['losses'] = out['losses']
         return out['losses']
 

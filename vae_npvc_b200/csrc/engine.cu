@@ -214,15 +214,22 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R;
   g.nblocks = (g.rows + 31) / 32;
   long long tiles = (long long)m_tiles * n_tiles;
-  int ctas = 2; if (ctas > 512 / tc) ctas = 512 / tc; if (ctas < 1) ctas = 1;
-  while (ctas > 1 && (225 * 1024) / ctas - 2048 < stage_bytes) ctas--;
+  int ctas = 1;     // 320 threads x ~130 registers (double-buffered producer registers): one CTA per SM
   int stages = ((225 * 1024) / ctas - 2048) / stage_bytes; if (stages > 4) stages = 4; if (stages < 1) stages = 1;
   g.stages = stages; g.rows_tile = 32; g.FB = 0;
   g.C = dview(c, o.C); g.bias0 = g.bias1 = g.bias2 = nullptr; g.bias_mod = 1; g.table = nullptr; g.labels = nullptr; g.table_ld = 0;
   g.A = dview(c, o.A); g.D = dview(c, o.C);
-  long long S = ((long long)ctas * 2 * h->sm_count + tiles - 1) / tiles;
-  long long maxS = g.nblocks / 8; if (maxS < 1) maxS = 1;
-  if (S > maxS) S = maxS;
+  // split the reduction so that tiles * S fills whole waves of (ctas * SMs) resident CTAs, each
+  // CTA keeping >= 16 reduction blocks (amortises its 128 x BN atomic epilogue)
+  long long maxS = g.nblocks / 16; if (maxS < 1) maxS = 1; if (maxS > 4096) maxS = 4096;
+  const double slots = (double)ctas * h->sm_count;
+  long long S = 1; double best = 1e30;
+  for (long long cand = 1; cand <= maxS; cand++) {
+    double waves = (double)(tiles * cand) / slots;
+    if (waves > 8.0 && cand > 1) break;
+    double cost = (waves < 1.0 ? 1.0 / waves : std::ceil(waves) / waves) + 0.01 * waves;
+    if (cost < best - 1e-9) { best = cost; S = cand; }
+  }
   g.blocks_per_split = (g.nblocks + S - 1) / S;
   S = (g.nblocks + g.blocks_per_split - 1) / g.blocks_per_split;
   g.out = resolve(c, o.B); g.ld = o.ldb;

@@ -228,14 +228,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t rowoff = (uint32_t)(ct >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
       const uint32_t rowoff1 = (uint32_t)((ct + 128) >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
       const int pg = (warp - 2) >> 2;                 // producer group: rows [16*pg, 16*pg + 16) of the block
-      for (int i = 0; i < nkb; i++) {
-        const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        uint8_t* stp = gen_base + (size_t)s * stage_bytes;
-        const long long r0 = (kb_begin + i) * 32 + pg * 16;
+      // Software-pipelined producer: the global loads of block i+1 are issued BEFORE block i is
+      // converted and stored, so one full round of loads (48 per thread) is always in flight.
+      auto load_block = [&](long long blk, float (&va)[16], float (&v0)[16], float (&v1)[16]) {
+        const long long r0 = blk * 32 + pg * 16;
         long long f = r0 / g.A.R; int j = (int)(r0 - f * g.A.R);
-        // all 16 rows x (A, D, D+128) loads first: memory-level parallelism hides the L2 / HBM latency
-        float va[16], v0[16], v1[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) {
           float a = 0.f, d0 = 0.f, d1 = 0.f;
@@ -251,27 +248,31 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           va[e] = a; v0[e] = d0; v1[e] = d1;
           if (++j == g.A.R) { j = 0; f++; }
         }
+      };
+      auto split4 = [&](const float* v, uint4& h, uint4& l) {
+        h.x = cvt_tf32(v[0]); h.y = cvt_tf32(v[1]); h.z = cvt_tf32(v[2]); h.w = cvt_tf32(v[3]);
+        l.x = cvt_tf32(v[0] - __uint_as_float(h.x)); l.y = cvt_tf32(v[1] - __uint_as_float(h.y));
+        l.z = cvt_tf32(v[2] - __uint_as_float(h.z)); l.w = cvt_tf32(v[3] - __uint_as_float(h.w));
+      };
+      auto store_block = [&](int i, const float (&va)[16], const float (&v0)[16], const float (&v1)[16]) {
+        const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        uint8_t* stp = gen_base + (size_t)s * stage_bytes;
 #pragma unroll
         for (int c4 = 0; c4 < 4; c4++) {
           const int c = pg * 4 + c4;
           const uint32_t chunk = (uint32_t)((c ^ (ct & 7)) * 16);
           uint4 h, l;
-          h.x = cvt_tf32(va[c4 * 4 + 0]); h.y = cvt_tf32(va[c4 * 4 + 1]); h.z = cvt_tf32(va[c4 * 4 + 2]); h.w = cvt_tf32(va[c4 * 4 + 3]);
-          l.x = cvt_tf32(va[c4 * 4 + 0] - __uint_as_float(h.x)); l.y = cvt_tf32(va[c4 * 4 + 1] - __uint_as_float(h.y));
-          l.z = cvt_tf32(va[c4 * 4 + 2] - __uint_as_float(h.z)); l.w = cvt_tf32(va[c4 * 4 + 3] - __uint_as_float(h.w));
+          split4(&va[c4 * 4], h, l);
           *reinterpret_cast<uint4*>(stp + rowoff + chunk) = h;
           *reinterpret_cast<uint4*>(stp + A_TILE_BYTES + rowoff + chunk) = l;
           if (ct < g.BN) {
-            h.x = cvt_tf32(v0[c4 * 4 + 0]); h.y = cvt_tf32(v0[c4 * 4 + 1]); h.z = cvt_tf32(v0[c4 * 4 + 2]); h.w = cvt_tf32(v0[c4 * 4 + 3]);
-            l.x = cvt_tf32(v0[c4 * 4 + 0] - __uint_as_float(h.x)); l.y = cvt_tf32(v0[c4 * 4 + 1] - __uint_as_float(h.y));
-            l.z = cvt_tf32(v0[c4 * 4 + 2] - __uint_as_float(h.z)); l.w = cvt_tf32(v0[c4 * 4 + 3] - __uint_as_float(h.w));
+            split4(&v0[c4 * 4], h, l);
             *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + rowoff + chunk) = h;
             *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + b_tile_bytes + rowoff + chunk) = l;
           }
           if (ct + 128 < g.BN) {
-            h.x = cvt_tf32(v1[c4 * 4 + 0]); h.y = cvt_tf32(v1[c4 * 4 + 1]); h.z = cvt_tf32(v1[c4 * 4 + 2]); h.w = cvt_tf32(v1[c4 * 4 + 3]);
-            l.x = cvt_tf32(v1[c4 * 4 + 0] - __uint_as_float(h.x)); l.y = cvt_tf32(v1[c4 * 4 + 1] - __uint_as_float(h.y));
-            l.z = cvt_tf32(v1[c4 * 4 + 2] - __uint_as_float(h.z)); l.w = cvt_tf32(v1[c4 * 4 + 3] - __uint_as_float(h.w));
+            split4(&v1[c4 * 4], h, l);
             *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + rowoff1 + chunk) = h;
             *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + b_tile_bytes + rowoff1 + chunk) = l;
           }
@@ -279,6 +280,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(ready_bar(s));
+      };
+      float pa[16], p0[16], p1[16], qa[16], q0[16], q1[16];
+      load_block(kb_begin, pa, p0, p1);
+      for (int i = 0; i < nkb; i += 2) {
+        if (i + 1 < nkb) load_block(kb_begin + i + 1, qa, q0, q1);
+        store_block(i, pa, p0, p1);
+        if (i + 1 < nkb) {
+          if (i + 2 < nkb) load_block(kb_begin + i + 2, pa, p0, p1);
+          store_block(i + 1, qa, q0, q1);
+        }
       }
     }
     if (warp >= 6) goto done;                         // second producer group has no epilogue share
@@ -300,6 +311,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (g.table) trow = g.table + (long long)g.labels[f] * g.table_ld;
       }
     }
+    const bool has_add = (g.bias0 != nullptr) || (g.table != nullptr);
     for (int c0 = 0; c0 < g.BN; c0 += 16) {
       uint32_t v[16], w[16];
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
@@ -331,11 +343,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int e = 0; e < 4; e++) {
           const int n = nb + e;
           float t = __uint_as_float(v[q * 4 + e]) + __uint_as_float(w[q * 4 + e]);
-          if (n < g.N) {
-            const int bi = n % g.bias_mod;
-            if (g.bias0) t += g.bias0[bi];
-            if (g.bias1) t += g.bias1[bi];
-            if (g.bias2) t += g.bias2[bi];
+          if (has_add && n < g.N) {
+            if (g.bias0) {
+              const int bi = (g.bias_mod >= g.N) ? n : n % g.bias_mod;
+              t += g.bias0[bi];
+              if (g.bias1) t += g.bias1[bi];
+              if (g.bias2) t += g.bias2[bi];
+            }
             if (trow) t += trow[n];
           }
           o[e] = t;
