@@ -59,7 +59,7 @@ def test_async_loader_matches_reference_semantics(tmp_path, arch):
     from vae_npvc_b200.engine import Engine
     paths, allrec = _write_bins(tmp_path)
     rs = np.random.RandomState(3)
-    xmin = rs.randn(513) - 3; xmax = xmin + 1 + rs.rand(513)
+    xmin = -2.5 - rs.rand(513); xmax = 2.5 + rs.rand(513)        # a few percent of the N(0,1) data clips
     eng = Engine(arch)
     norm = analyzer.Tanhize(xmin=xmin, xmax=xmax, engine=eng)
     image, label = analyzer.read(os.path.join(str(tmp_path), "*", "*.bin"), batch_size=16, capacity=64,
@@ -71,7 +71,8 @@ def test_async_loader_matches_reference_semantics(tmp_path, arch):
         xs = x.reshape(16, 513).cpu().numpy()
         for i in range(16):
             r = lut[tuple(np.round(xs[i, :6].astype(np.float64), 5))]
-            assert np.abs(xs[i] - R.tanhize_forward(r[:513].astype(np.float64), xmin, xmax)).max() < 1e-5
+            err = np.abs(xs[i] - R.tanhize_forward(r[:513].astype(np.float64), xmin, xmax))
+            assert err.max() < 1e-5, (float(err.max()), int(err.argmax()))
             assert int(y[i]) == int(r[-1])
     xp, yp = image.dequeue(peek=True)
     xq, yq = label.dequeue()

@@ -166,17 +166,12 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
     }
     h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
   }
-  UmmaArgs g;
+  UmmaFwdArgs pa; UmmaArgs& g = pa.g;
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + 31) / 32;
   const int stage_bytes = 2 * 16384 + 2 * BN * 128;
-  int tc = 32; while (tc < 2 * BN) tc *= 2; g.tmem_cols = tc;     // main + correction accumulators
-  // short reductions are latency-bound per CTA (TMEM alloc, first TMA, epilogue): co-schedule
-  // several CTAs per SM (smem / TMEM permitting) instead of deep pipelines
-  int ctas = g.kblocks <= 8 ? 4 : (g.kblocks <= 32 ? 2 : 1);
-  if (ctas > 512 / tc) ctas = 512 / tc;
-  while (ctas > 1 && (225 * 1024) / ctas - 2048 < stage_bytes) ctas--;
-  int stages = ((225 * 1024) / ctas - 2048) / stage_bytes; if (stages > 4) stages = 4; if (stages > g.kblocks) stages = g.kblocks;
-  if (stages < 1) stages = 1;
+  pa.acc_sets = (4 * BN <= 512) ? 2 : 1;                            // double-buffered accumulators when TMEM allows
+  int tc = 32; while (tc < pa.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
+  int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 6) stages = 6; if (stages < 1) stages = 1;
   g.stages = stages; g.rows_tile = RB * FB; g.FB = FB; g.rows = frames * R;
   g.nblocks = 0; g.blocks_per_split = 0; g.out = nullptr; g.ld = 0; g.A = dview(c, o.A); g.D = g.A;
   g.C = dview(c, o.C);
@@ -185,14 +180,14 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   if (g.table && !g.labels) return fail(NPVC_ERR_ARG, "labels (y) required");
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(umma_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 1) + 16;
-  const long long m_tiles = (frames + FB - 1) / FB;
-  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
-  umma_gemm_kernel<false><<<grid, 192, smem, st>>>(it->second.tA, it->second.tBh, it->second.tBl, g);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 5) + 32 + 1024;   // + bias_s[256]
+  pa.m_tiles = (int)((frames + FB - 1) / FB); pa.n_tiles = n_tiles;
+  long long total = (long long)pa.m_tiles * pa.n_tiles;
+  unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
+  umma_fwd_persistent_kernel<<<grid, 320, smem, st>>>(it->second.tA, it->second.tBh, it->second.tBl, pa);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -214,7 +209,12 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R;
   g.nblocks = (g.rows + 31) / 32;
   long long tiles = (long long)m_tiles * n_tiles;
-  int ctas = 1;     // 320 threads x ~130 registers (double-buffered producer registers): one CTA per SM
+  // wide N tiles: software-pipelined producer (130 registers x 320 threads -> 1 CTA / SM);
+  // BN <= 128: single register set, 2 CTAs / SM (smem / TMEM permitting)
+  const bool pipelined = BN > 128;
+  int ctas = pipelined ? 1 : 2;
+  if (ctas > 512 / tc) ctas = 512 / tc; if (ctas < 1) ctas = 1;
+  while (ctas > 1 && (225 * 1024) / ctas - 2048 < stage_bytes) ctas--;
   int stages = ((225 * 1024) / ctas - 2048) / stage_bytes; if (stages > 4) stages = 4; if (stages < 1) stages = 1;
   g.stages = stages; g.rows_tile = 32; g.FB = 0;
   g.C = dview(c, o.C); g.bias0 = g.bias1 = g.bias2 = nullptr; g.bias_mod = 1; g.table = nullptr; g.labels = nullptr; g.table_ld = 0;
@@ -235,13 +235,15 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   g.out = resolve(c, o.B); g.ld = o.ldb;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 1) + 16;
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)S);
   CUtensorMap dummy; memset(&dummy, 0, sizeof dummy);
-  umma_gemm_kernel<true><<<grid, 320, smem, st>>>(dummy, dummy, dummy, g);   // 8 producer warps
+  if (pipelined) umma_gemm_kernel<1><<<grid, 320, smem, st>>>(dummy, dummy, dummy, g);   // 8 producer warps
+  else umma_gemm_kernel<2><<<grid, 320, smem, st>>>(dummy, dummy, dummy, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }

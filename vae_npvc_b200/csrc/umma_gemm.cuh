@@ -104,11 +104,14 @@ __device__ __forceinline__ uint32_t cvt_tf32(float x) {
 
 }  // namespace umma
 
-template <bool WG>
-__global__ void __launch_bounds__(WG ? 320 : 192)
+// MODE 0: forward (F) form.  MODE 1: wgrad (W) form, software-pipelined producer registers (1 CTA / SM;
+// wide N tiles).  MODE 2: wgrad, single register set, <= 102 registers so 2 CTAs co-reside (BN <= 128).
+template <int MODE>
+__global__ void __launch_bounds__(MODE ? 320 : 192, MODE == 2 ? 2 : 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                  const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
   using namespace umma;
+  constexpr bool WG = (MODE != 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = (uint32_t)g.BN * 128u;
@@ -281,15 +284,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(ready_bar(s));
       };
-      float pa[16], p0[16], p1[16], qa[16], q0[16], q1[16];
-      load_block(kb_begin, pa, p0, p1);
-      for (int i = 0; i < nkb; i += 2) {
-        if (i + 1 < nkb) load_block(kb_begin + i + 1, qa, q0, q1);
-        store_block(i, pa, p0, p1);
-        if (i + 1 < nkb) {
-          if (i + 2 < nkb) load_block(kb_begin + i + 2, pa, p0, p1);
-          store_block(i + 1, qa, q0, q1);
+      if (MODE == 1) {
+        float pa[16], p0[16], p1[16], qa[16], q0[16], q1[16];
+        load_block(kb_begin, pa, p0, p1);
+        for (int i = 0; i < nkb; i += 2) {
+          if (i + 1 < nkb) load_block(kb_begin + i + 1, qa, q0, q1);
+          store_block(i, pa, p0, p1);
+          if (i + 1 < nkb) {
+            if (i + 2 < nkb) load_block(kb_begin + i + 2, pa, p0, p1);
+            store_block(i + 1, qa, q0, q1);
+          }
         }
+      } else {
+        // BN <= 128: the second CTA on the SM covers this CTA's load latency
+        float pa[16], p0[16], p1[16];
+        for (int i = 0; i < nkb; i++) { load_block(kb_begin + i, pa, p0, p1); store_block(i, pa, p0, p1); }
       }
     }
     if (warp >= 6) goto done;                         // second producer group has no epilogue share
@@ -371,6 +380,220 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 done:
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+  }
+}
+
+
+// =============================================================================================
+// Persistent forward (F) kernel: one CTA per SM slot loops over (M, N) tiles.
+//   warp 0      TMA producer, runs ahead across tile boundaries (the smem ring never drains)
+//   warp 1      MMA issuer; accumulators double-buffered in TMEM when 4*BN <= 512 columns
+//   warps 2-5   tf32 hi/lo converters of the landed A tiles
+//   warps 6-9   epilogue (TMEM -> registers -> bias/table -> view store), overlapped with the
+//               next tile's mainloop through the accf / acce barriers
+// =============================================================================================
+struct UmmaFwdArgs {
+  UmmaArgs g;
+  int m_tiles, n_tiles, acc_sets;
+};
+
+__global__ void __launch_bounds__(320, 1)
+umma_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                           const __grid_constant__ CUtensorMap tmBl, UmmaFwdArgs pa) {
+  using namespace umma;
+  const UmmaArgs& g = pa.g;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_tile_bytes = (uint32_t)g.BN * 128u;
+  const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
+  const uint32_t bar_base = sbase + (uint32_t)g.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto ready_bar = [&](int s) { return bar_base + 8u * (uint32_t)(g.stages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * g.stages + s); };
+  auto accf_bar = [&](int b) { return bar_base + 8u * (uint32_t)(3 * g.stages + b); };
+  auto acce_bar = [&](int b) { return bar_base + 8u * (uint32_t)(3 * g.stages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(3 * g.stages + 4);
+  uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
+  float* bias_s = reinterpret_cast<float*>(gen_base + (tmem_slot - sbase) + 16);      // [256] effective bias of the current N tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = pa.m_tiles * pa.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
+    for (int s = 0; s < g.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)g.rows_tile * 128u + 2u * b_tile_bytes;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int tile_m = t / pa.n_tiles, n0 = (t % pa.n_tiles) * g.BN;
+        for (int kb = 0; kb < g.kblocks; kb++, it++) {
+          const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+          mbar_expect_tx(full_bar(s), tx);
+          tma_load_3d(st, &tmA, full_bar(s), kb * BK, 0, tile_m * g.FB);
+          tma_load_2d(st + 2u * A_TILE_BYTES, &tmBh, full_bar(s), kb * BK, n0);
+          tma_load_2d(st + 2u * A_TILE_BYTES + b_tile_bytes, &tmBl, full_bar(s), kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0; int lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
+        const int buf = lt % pa.acc_sets; const uint32_t aph = (uint32_t)((lt / pa.acc_sets) & 1);
+        mbar_wait(acce_bar(buf), aph ^ 1u);                 // epilogue has drained this accumulator set
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * g.BN);
+        for (int kb = 0; kb < g.kblocks; kb++, it++) {
+          const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
+          mbar_wait(ready_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+          const uint64_t ah = make_sdesc(st), al = make_sdesc(st + A_TILE_BYTES);
+          const uint64_t bh = make_sdesc(st + 2u * A_TILE_BYTES), bl = make_sdesc(st + 2u * A_TILE_BYTES + b_tile_bytes);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) {
+            const uint64_t o = (uint64_t)(k4 * 2);
+            const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
+            mma_tf32(acc, ah + o, bh + o, idesc, first);                       // main products
+            mma_tf32(acc + (uint32_t)g.BN, al + o, bh + o, idesc, first);      // corrections (see umma_gemm_kernel)
+            mma_tf32(acc + (uint32_t)g.BN, ah + o, bl + o, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(accf_bar(buf));
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ converters
+    const int ct = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < g.kblocks; kb++, it++) {
+        const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        float4* ahp = reinterpret_cast<float4*>(gen_base + (size_t)s * stage_bytes);
+        uint4* alp = reinterpret_cast<uint4*>(gen_base + (size_t)s * stage_bytes + A_TILE_BYTES);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int idx = ct + q * 128;
+          float4 v = ahp[idx];
+          uint4 h, l;
+          h.x = cvt_tf32(v.x); h.y = cvt_tf32(v.y); h.z = cvt_tf32(v.z); h.w = cvt_tf32(v.w);
+          l.x = cvt_tf32(v.x - __uint_as_float(h.x)); l.y = cvt_tf32(v.y - __uint_as_float(h.y));
+          l.z = cvt_tf32(v.z - __uint_as_float(h.z)); l.w = cvt_tf32(v.w - __uint_as_float(h.w));
+          reinterpret_cast<uint4*>(ahp)[idx] = h;
+          alp[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(s));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int lq = warp & 3;
+    const int row_local = lq * 32 + lane;
+    const int et = threadIdx.x - 192;               // 0..127 within the epilogue group
+    int lt = 0, n0_staged = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
+      const int tile_m = t / pa.n_tiles, n0 = (t % pa.n_tiles) * g.BN;
+      if (g.bias0 && n0 != n0_staged) {             // (bias0 + bias1 + bias2)[n % bias_mod] for this tile's columns
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's readers are done
+        for (int c = et; c < g.BN; c += 128) {
+          const int n = n0 + c; float b = 0.f;
+          if (n < g.N) {
+            const int bi = n % g.bias_mod;
+            b = g.bias0[bi]; if (g.bias1) b += g.bias1[bi]; if (g.bias2) b += g.bias2[bi];
+          }
+          bias_s[c] = b;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        n0_staged = n0;
+      }
+      const int buf = lt % pa.acc_sets; const uint32_t aph = (uint32_t)((lt / pa.acc_sets) & 1);
+      const long long r = (long long)tile_m * g.rows_tile + row_local;
+      const bool row_ok = (row_local < g.rows_tile) && (r < g.rows);
+      float* cp = nullptr; int inf = 0; const float* trow = nullptr;
+      if (row_ok) {
+        const long long f = r / g.C.R; const int j = (int)(r - f * g.C.R);
+        inf = j * g.C.rs + g.C.off;
+        cp = g.C.p + f * g.C.fs + inf;
+        if (g.table) trow = g.table + (long long)g.labels[f] * g.table_ld;
+      }
+      mbar_wait(accf_bar(buf), aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * g.BN) + ((uint32_t)(lq * 32) << 16);
+      for (int c0 = 0; c0 < g.BN; c0 += 16) {
+        uint32_t v[16], w[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(acc + (uint32_t)c0) : "memory");
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+              "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+            : "r"(acc + (uint32_t)(g.BN + c0)) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int nb = n0 + c0 + q * 4;
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int n = nb + e;
+            float tt = __uint_as_float(v[q * 4 + e]) + __uint_as_float(w[q * 4 + e]);
+            if (g.bias0) tt += bias_s[c0 + q * 4 + e];
+            if (trow && n < g.N) tt += trow[n];
+            o[e] = tt;
+          }
+          bool full = (nb + 4 <= g.N);
+          if (g.C.pred) full = full && (inf + nb >= 0) && (inf + nb + 4 <= g.C.flen);
+          if (full && ((reinterpret_cast<uintptr_t>(cp + nb) & 15) == 0)) {
+            *reinterpret_cast<float4*>(cp + nb) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int n = nb + e;
+              bool ok = n < g.N;
+              if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
+              if (ok) cp[n] = o[e];
+            }
+          }
+        }
+      }
+      // this accumulator set may be overwritten by the MMA warp now
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar(buf));
+    }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
