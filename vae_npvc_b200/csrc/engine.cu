@@ -275,6 +275,26 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       if (g.rows <= 0) break;
       if (g.table && !g.labels) return fail(NPVC_ERR_ARG, "labels (y) required");
       if (umma_allowed(h, o)) { int rc = launch_umma(c, o, op_index); if (rc) return rc; break; }
+      if (o.rows_fixed && o.rows_fixed <= 16 && !g.bias0 && !g.table && o.C.ref.space == SP_GRAD && !g.A.pred && g.A.R == 1 && g.C.R == 1 && o.K >= 256) {
+        // few-row GEMM accumulated into the (zero-initialised) gradient buffer
+        const int kchunk = 128, ks = (o.K + kchunk - 1) / kchunk;
+        dim3 grid((unsigned)((o.N + 127) / 128), (unsigned)ks);
+        fewrows_gemm_kernel<<<grid, 128, (size_t)o.rows_fixed * kchunk * sizeof(float), st>>>(
+            g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, kchunk);
+        h->launches++; break;
+      }
+      if (!g.table && !g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && g.rows >= 65536) {
+        RowGemmArgs rg; rg.A = g.A; rg.K = o.K; rg.B = g.B; rg.ldb = o.ldb; rg.N = o.N; rg.C = g.C; rg.rows = g.rows;
+        rg.bias0 = g.bias0; rg.bias_mod = o.bias_mod;
+        const bool sc = !view_vec_ok(g.A) || (o.K % 4 != 0);
+        const unsigned blocks = (unsigned)((g.rows + 255) / 256);
+        if (sc && o.K <= 8 && o.N <= 16) rowgemm_kernel<8, 16, true><<<blocks, 256, 0, st>>>(rg);
+        else if (!sc && o.K <= 48 && o.N <= 24) rowgemm_kernel<48, 24, false><<<blocks, 256, 0, st>>>(rg);
+        else if (!sc && o.K <= 56 && o.N <= 16) rowgemm_kernel<56, 16, false><<<blocks, 256, 0, st>>>(rg);
+        else if (!sc) rowgemm_kernel<64, 32, false><<<blocks, 256, 0, st>>>(rg);
+        else rowgemm_kernel<64, 32, true><<<blocks, 256, 0, st>>>(rg);
+        h->launches++; break;
+      }
       launch_gemm(g, !view_vec_ok(g.A), st); h->launches++; break;
     }
     case OP_WGRAD: {

@@ -319,6 +319,110 @@ __global__ void __launch_bounds__(256) wgrad_view_kernel(WgradArgs g) {
 }
 
 // =============================================================================================
+// (F) for small K, N and millions of rows (E0, G2 fwd / dgrad): one output row per thread.
+// The row's K-float window is loaded once into registers (coalesced across the warp: consecutive
+// rows are consecutive / overlapping windows), weights are broadcast from shared memory as float4,
+// the N outputs leave as one contiguous run.  Bandwidth-shaped: ~0.4 KB per row.
+// =============================================================================================
+struct RowGemmArgs {
+  DView A; int K; const float* B; int ldb; int N; DView C; long long rows;
+  const float* bias0; int bias_mod;
+};
+
+template <int KMAX, int NMAX, bool ASCALAR>
+__global__ void __launch_bounds__(256) rowgemm_kernel(RowGemmArgs g) {
+  __shared__ __align__(16) float Ws[KMAX * NMAX];
+  __shared__ float bs[NMAX];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < KMAX * NMAX; i += 256) {
+    const int k = i / NMAX, n = i % NMAX;
+    Ws[i] = (k < g.K && n < g.N) ? g.B[(long long)k * g.ldb + n] : 0.f;
+  }
+  if (tid < NMAX) bs[tid] = (g.bias0 && tid < g.N) ? g.bias0[tid % g.bias_mod] : 0.f;
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * 256 + tid;
+  if (r >= g.rows) return;
+  float x[KMAX];
+  {
+    const long long f = r / g.A.R; const int j = (int)(r - f * g.A.R);
+    const int inf = j * g.A.rs + g.A.off;
+    const float* ap = g.A.p + f * g.A.fs + inf;
+    if (!ASCALAR) {
+#pragma unroll
+      for (int k4 = 0; k4 < KMAX / 4; k4++) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k4 * 4 < g.K) v = *reinterpret_cast<const float4*>(ap + k4 * 4);
+        x[k4 * 4 + 0] = v.x; x[k4 * 4 + 1] = v.y; x[k4 * 4 + 2] = v.z; x[k4 * 4 + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KMAX; k++) {
+        bool ok = k < g.K;
+        if (g.A.pred) { const int q = inf + k; ok = ok && q >= 0 && q < g.A.flen; }
+        x[k] = ok ? ap[k] : 0.f;
+      }
+    }
+  }
+  float acc[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; n++) acc[n] = bs[n];
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) {
+    if (k < g.K) {
+      const float xv = x[k];
+#pragma unroll
+      for (int n4 = 0; n4 < NMAX / 4; n4++) {
+        const float4 w = *reinterpret_cast<const float4*>(&Ws[k * NMAX + n4 * 4]);
+        acc[n4 * 4 + 0] = fmaf(xv, w.x, acc[n4 * 4 + 0]); acc[n4 * 4 + 1] = fmaf(xv, w.y, acc[n4 * 4 + 1]);
+        acc[n4 * 4 + 2] = fmaf(xv, w.z, acc[n4 * 4 + 2]); acc[n4 * 4 + 3] = fmaf(xv, w.w, acc[n4 * 4 + 3]);
+      }
+    }
+  }
+  const long long f = r / g.C.R; const int j = (int)(r - f * g.C.R);
+  const int inf = j * g.C.rs + g.C.off;
+  float* cp = g.C.p + f * g.C.fs + inf;
+  const bool vec = !g.C.pred && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) && (g.N % 4 == 0);
+  if (vec) {
+#pragma unroll
+    for (int n4 = 0; n4 < NMAX / 4; n4++)
+      if (n4 * 4 < g.N) *reinterpret_cast<float4*>(cp + n4 * 4) = make_float4(acc[n4 * 4], acc[n4 * 4 + 1], acc[n4 * 4 + 2], acc[n4 * 4 + 3]);
+  } else {
+#pragma unroll
+    for (int n = 0; n < NMAX; n++) {
+      bool ok = n < g.N;
+      if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
+      if (ok) cp[n] = acc[n];
+    }
+  }
+}
+
+// C[R,N] += A[R,K] . B[K,N] for a handful of rows (R <= 16): K split across blocks, atomics out
+// (the per-speaker embedding gradient: 10 x 1596 x 128).
+__global__ void __launch_bounds__(128) fewrows_gemm_kernel(const float* A, int lda, int R, int K, const float* B, int ldb, int N,
+                                                           float* C, int ldc, int kchunk) {
+  extern __shared__ float As[];                    // [R][kchunk]
+  const int k0 = blockIdx.y * kchunk;
+  const int kn = min(kchunk, K - k0);
+  for (int i = threadIdx.x; i < R * kchunk; i += blockDim.x) {
+    const int r = i / kchunk, k = i % kchunk;
+    As[i] = (k < kn) ? A[(long long)r * lda + k0 + k] : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) acc[r] = 0.f;
+  for (int k = 0; k < kn; k++) {
+    const float b = B[(long long)(k0 + k) * ldb + n];
+#pragma unroll
+    for (int r = 0; r < 16; r++) if (r < R) acc[r] = fmaf(As[r * kchunk + k], b, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 16; r++) if (r < R) atomicAdd(&C[(long long)r * ldc + n], acc[r]);
+}
+
+// =============================================================================================
 // block reductions
 // =============================================================================================
 __device__ __forceinline__ float warp_sum(float v) {
