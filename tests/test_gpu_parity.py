@@ -170,6 +170,28 @@ def test_full_size_properties(eng, arch):
         assert rel(out[k][sl], ref[k]) <= TOL_OUT, k
 
 
+def test_cfg3_inference_size(eng, arch):
+    """cfg3 (convert.py path): encode -> mu -> decode at N = 256*512 = 131,072 frames, processed in
+    16,384-frame chunks inside the library; chunk boundaries must be invisible and a slice that
+    straddles one must match the oracle."""
+    n = 131072
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = (torch.rand(n, 513, generator=g) * 2 - 1).cuda(); y = torch.randint(0, 10, (n,), generator=g).cuda()
+    P = R.init_params(arch, 0)
+    theta = torch.tensor(R.flatten_params(arch, P), device=eng.device)
+    mu, lv = eng.encode(theta, x)
+    xh = eng.decode(theta, mu, y)
+    assert mu.shape == (n, 128) and xh.shape == (n, 513) and torch.isfinite(xh).all() and torch.isfinite(mu).all()
+    sl = slice(16384 - 20, 16384 + 20)                      # straddles the first chunk boundary
+    mu2, _ = eng.encode(theta, x[sl].contiguous())
+    xh2 = eng.decode(theta, mu2, y[sl].contiguous())
+    assert torch.equal(mu2, mu[sl]) and torch.equal(xh2, xh[sl])
+    P32 = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in P.items()}
+    mu_ref, _ = R.encode(arch, P32, x[sl].cpu().numpy())
+    xh_ref = R.decode(arch, P32, mu_ref, y[sl].cpu().numpy()).reshape(40, -1)
+    assert rel(mu[sl], mu_ref) <= TOL_OUT and rel(xh[sl], xh_ref) <= TOL_OUT
+
+
 def test_tanhize_and_record_reader(eng):
     g = torch.Generator(device="cpu").manual_seed(3)
     xmin = torch.randn(513, generator=g) - 3; xmax = xmin + 1 + torch.rand(513, generator=g)

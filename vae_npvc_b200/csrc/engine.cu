@@ -198,9 +198,17 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
 int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   (void)op_index;
   npvc_handle* h = c.h; cudaStream_t st = c.st;
+  // N tile: multiple of 32 (the producer's column-quad permutation needs BN/4 % 8 == 0)
   int n_tiles = 1, BN;
-  if (o.N <= 256) BN = (o.N + 15) / 16 * 16;
-  else BN = pick_bn(o.N, &n_tiles);
+  if (o.N <= 256) BN = (o.N + 31) / 32 * 32;
+  else {
+    long long best = -1; BN = 256; n_tiles = (o.N + 255) / 256;
+    for (int t = (o.N + 255) / 256; t <= (o.N + 255) / 256 + 6; t++) {
+      int bn = ((o.N + t - 1) / t + 31) / 32 * 32; if (bn > 256) continue;
+      long long cost = (long long)bn * t;
+      if (best < 0 || cost < best) { best = cost; BN = bn; n_tiles = t; }
+    }
+  }
   const int m_tiles = (o.K + 127) / 128;
   UmmaArgs g;
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = 0;
@@ -283,7 +291,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
             g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, kchunk);
         h->launches++; break;
       }
-      if (!g.table && !g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && g.rows >= 65536) {
+      if (!g.table && !g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && !o.rows_fixed) {     // (independent of n: per-frame results must not depend on the batch size)
         RowGemmArgs rg; rg.A = g.A; rg.K = o.K; rg.B = g.B; rg.ldb = o.ldb; rg.N = o.N; rg.C = g.C; rg.rows = g.rows;
         rg.bias0 = g.bias0; rg.bias_mod = o.bias_mod;
         const bool sc = !view_vec_ok(g.A) || (o.K % 4 != 0);

@@ -219,65 +219,76 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(ready_bar(s));
       }
     } else {
-      // wgrad: these warps ARE the producers.  Thread ct owns operand row ct of the K-major tiles
-      // (A: view column k = tile_m*128 + ct; D: view column n = n0 + ct [+128]) and walks the 32
-      // reduction rows of the block: coalesced global loads (a warp reads 128 contiguous bytes of
-      // one view row), tf32 hi/lo split, 16-byte stores into the 128B-swizzled K-major layout
-      // (row ct, 16B chunk c ^ (ct & 7): conflict-free, this is what the swizzle is for).
-      const int ka = tile_m * 128 + ct;
-      const bool a_col_ok = ka < g.K;
-      const int nb0 = n0 + ct, nb1 = n0 + ct + 128;
-      const bool d0_ok = (ct < g.BN) && (nb0 < g.N), d1_ok = (ct + 128 < g.BN) && (nb1 < g.N);
-      const uint32_t rowoff = (uint32_t)(ct >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
-      const uint32_t rowoff1 = (uint32_t)((ct + 128) >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
-      const int pg = (warp - 2) >> 2;                 // producer group: rows [16*pg, 16*pg + 16) of the block
-      // Software-pipelined producer: the global loads of block i+1 are issued BEFORE block i is
-      // converted and stored, so one full round of loads (48 per thread) is always in flight.
-      auto load_block = [&](long long blk, float (&va)[16], float (&v0)[16], float (&v1)[16]) {
-        const long long r0 = blk * 32 + pg * 16;
-        long long f = r0 / g.A.R; int j = (int)(r0 - f * g.A.R);
+      // wgrad: these warps ARE the producers.  A task = a 4-row x 4-column patch of a view: four
+      // coalesced LDG.128 (a warp reads 512 contiguous bytes of one view row), tf32 hi/lo split,
+      // and one 16-byte store per column into the K-major 128B-swizzled operand tile.  The operand
+      // row of view column (4*q + i) is PERMUTED to (i * quads + q): consecutive lanes then write
+      // consecutive operand rows, whose (row & 7) swizzle phases differ -> conflict-free stores with
+      // no register shuffling.  The epilogue applies the inverse permutation.
+      const int pw = warp - 2;                        // 0..7: row-quad of this warp's A task
+      const int pt = threadIdx.x - 64;                // 0..255 within the producer group
+      const int NQ = g.BN >> 2;                       // column quads of the dC tile (multiple of 8)
+      constexpr int DT = (MODE == 1) ? 2 : 1;         // dC tasks per thread
+      const int ka = tile_m * 128 + 4 * lane;
+      const bool a_ok = ka < g.K;
+      auto load_block = [&](long long blk, float4 (&va)[4], float4 (&vd)[DT][4]) {
+        const long long rb = blk * 32;
+        {   // A task: rows rb + 4*pw + e, columns ka..ka+3
+          const long long r0 = rb + 4 * pw;
+          long long f = r0 / g.A.R; int j = (int)(r0 - f * g.A.R);
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-          float a = 0.f, d0 = 0.f, d1 = 0.f;
-          if (r0 + e < g.rows) {
-            if (a_col_ok) {
-              const int inf = j * g.A.rs + g.A.off + ka;
-              if (!g.A.pred || (inf >= 0 && inf < g.A.flen)) a = __ldg(g.A.p + f * g.A.fs + inf);
-            }
-            const float* dp = g.D.p + f * g.D.fs + j * g.D.rs + g.D.off;
-            if (d0_ok) d0 = __ldg(dp + nb0);
-            if (d1_ok) d1 = __ldg(dp + nb1);
+          for (int e = 0; e < 4; e++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a_ok && r0 + e < g.rows) v = __ldg(reinterpret_cast<const float4*>(g.A.p + f * g.A.fs + (long long)j * g.A.rs + g.A.off + ka));
+            va[e] = v;
+            if (++j == g.A.R) { j = 0; f++; }
           }
-          va[e] = a; v0[e] = d0; v1[e] = d1;
-          if (++j == g.A.R) { j = 0; f++; }
+        }
+#pragma unroll
+        for (int d = 0; d < DT; d++) {
+          const int tsk = pt + d * 256;
+          const int rq = tsk / NQ, nq = tsk - rq * NQ;
+          const int nn = n0 + 4 * nq;
+          const bool ok = (tsk < 8 * NQ) && (nn < g.N);
+          const long long r0 = rb + 4 * rq;
+          long long f = r0 / g.D.R; int j = (int)(r0 - f * g.D.R);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && r0 + e < g.rows) v = __ldg(reinterpret_cast<const float4*>(g.D.p + f * g.D.fs + (long long)j * g.D.rs + g.D.off + nn));
+            vd[d][e] = v;
+            if (++j == g.D.R) { j = 0; f++; }
+          }
         }
       };
-      auto split4 = [&](const float* v, uint4& h, uint4& l) {
-        h.x = cvt_tf32(v[0]); h.y = cvt_tf32(v[1]); h.z = cvt_tf32(v[2]); h.w = cvt_tf32(v[3]);
-        l.x = cvt_tf32(v[0] - __uint_as_float(h.x)); l.y = cvt_tf32(v[1] - __uint_as_float(h.y));
-        l.z = cvt_tf32(v[2] - __uint_as_float(h.z)); l.w = cvt_tf32(v[3] - __uint_as_float(h.w));
+      auto split_store = [&](uint8_t* hi_base, uint8_t* lo_base, int rho, int chunk, float x0, float x1, float x2, float x3) {
+        const uint32_t off = (uint32_t)(rho >> 3) * 1024u + (uint32_t)(rho & 7) * 128u + (uint32_t)((chunk ^ (rho & 7)) * 16);
+        uint4 h, l;
+        h.x = cvt_tf32(x0); h.y = cvt_tf32(x1); h.z = cvt_tf32(x2); h.w = cvt_tf32(x3);
+        l.x = cvt_tf32(x0 - __uint_as_float(h.x)); l.y = cvt_tf32(x1 - __uint_as_float(h.y));
+        l.z = cvt_tf32(x2 - __uint_as_float(h.z)); l.w = cvt_tf32(x3 - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(hi_base + off) = h;
+        *reinterpret_cast<uint4*>(lo_base + off) = l;
       };
-      auto store_block = [&](int i, const float (&va)[16], const float (&v0)[16], const float (&v1)[16]) {
+      auto store_block = [&](int i, const float4 (&va)[4], const float4 (&vd)[DT][4]) {
         const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
         mbar_wait(empty_bar(s), ph ^ 1u);
         uint8_t* stp = gen_base + (size_t)s * stage_bytes;
+        // A: operand row of view column 4*lane + c is 32*c + lane; 16-byte chunk = row-quad pw
+        split_store(stp, stp + A_TILE_BYTES, 0 * 32 + lane, pw, va[0].x, va[1].x, va[2].x, va[3].x);
+        split_store(stp, stp + A_TILE_BYTES, 1 * 32 + lane, pw, va[0].y, va[1].y, va[2].y, va[3].y);
+        split_store(stp, stp + A_TILE_BYTES, 2 * 32 + lane, pw, va[0].z, va[1].z, va[2].z, va[3].z);
+        split_store(stp, stp + A_TILE_BYTES, 3 * 32 + lane, pw, va[0].w, va[1].w, va[2].w, va[3].w);
 #pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-          const int c = pg * 4 + c4;
-          const uint32_t chunk = (uint32_t)((c ^ (ct & 7)) * 16);
-          uint4 h, l;
-          split4(&va[c4 * 4], h, l);
-          *reinterpret_cast<uint4*>(stp + rowoff + chunk) = h;
-          *reinterpret_cast<uint4*>(stp + A_TILE_BYTES + rowoff + chunk) = l;
-          if (ct < g.BN) {
-            split4(&v0[c4 * 4], h, l);
-            *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + rowoff + chunk) = h;
-            *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + b_tile_bytes + rowoff + chunk) = l;
-          }
-          if (ct + 128 < g.BN) {
-            split4(&v1[c4 * 4], h, l);
-            *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + rowoff1 + chunk) = h;
-            *reinterpret_cast<uint4*>(stp + 2 * A_TILE_BYTES + b_tile_bytes + rowoff1 + chunk) = l;
+        for (int d = 0; d < DT; d++) {
+          const int tsk = pt + d * 256;
+          if (tsk < 8 * NQ) {
+            const int rq = tsk / NQ, nq = tsk - rq * NQ;
+            uint8_t* bh = stp + 2 * A_TILE_BYTES; uint8_t* bl = bh + b_tile_bytes;
+            split_store(bh, bl, 0 * NQ + nq, rq, vd[d][0].x, vd[d][1].x, vd[d][2].x, vd[d][3].x);
+            split_store(bh, bl, 1 * NQ + nq, rq, vd[d][0].y, vd[d][1].y, vd[d][2].y, vd[d][3].y);
+            split_store(bh, bl, 2 * NQ + nq, rq, vd[d][0].z, vd[d][1].z, vd[d][2].z, vd[d][3].z);
+            split_store(bh, bl, 3 * NQ + nq, rq, vd[d][0].w, vd[d][1].w, vd[d][2].w, vd[d][3].w);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -285,20 +296,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(ready_bar(s));
       };
       if (MODE == 1) {
-        float pa[16], p0[16], p1[16], qa[16], q0[16], q1[16];
-        load_block(kb_begin, pa, p0, p1);
+        // software-pipelined: block i+1's loads are in flight while block i is split and stored
+        float4 pa[4], pd[DT][4], qa[4], qd[DT][4];
+        load_block(kb_begin, pa, pd);
         for (int i = 0; i < nkb; i += 2) {
-          if (i + 1 < nkb) load_block(kb_begin + i + 1, qa, q0, q1);
-          store_block(i, pa, p0, p1);
+          if (i + 1 < nkb) load_block(kb_begin + i + 1, qa, qd);
+          store_block(i, pa, pd);
           if (i + 1 < nkb) {
-            if (i + 2 < nkb) load_block(kb_begin + i + 2, pa, p0, p1);
-            store_block(i + 1, qa, q0, q1);
+            if (i + 2 < nkb) load_block(kb_begin + i + 2, pa, pd);
+            store_block(i + 1, qa, qd);
           }
         }
       } else {
         // BN <= 128: the second CTA on the SM covers this CTA's load latency
-        float pa[16], p0[16], p1[16];
-        for (int i = 0; i < nkb; i++) { load_block(kb_begin + i, pa, p0, p1); store_block(i, pa, p0, p1); }
+        float4 pa[4], pd[DT][4];
+        for (int i = 0; i < nkb; i++) { load_block(kb_begin + i, pa, pd); store_block(i, pa, pd); }
       }
     }
     if (warp >= 6) goto done;                         // second producer group has no epilogue share
@@ -307,7 +319,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int lq = warp & 3;                        // TMEM lane quarter this warp may access
     const int row_local = lq * 32 + lane;
-    const long long r = WG ? (long long)tile_m * 128 + row_local : (long long)tile_m * g.rows_tile + row_local;
+    // wgrad: accumulator row rho holds view column 4*(rho % 32) + rho / 32 (see the producer)
+    const long long r = WG ? (long long)tile_m * 128 + 4 * (row_local & 31) + (row_local >> 5) : (long long)tile_m * g.rows_tile + row_local;
     const bool row_ok = WG ? (r < g.K) : ((row_local < g.rows_tile) && (r < g.rows));
     float* cp = nullptr; int inf = 0; const float* trow = nullptr;
     if (row_ok) {
@@ -337,9 +350,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (!row_ok) continue;
       if (WG) {
+        const int NQe = g.BN >> 2;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-          const int n = n0 + c0 + e;
+          const int chi = c0 + e;                     // accumulator column chi holds view column 4*(chi % NQ) + chi / NQ
+          const int n = n0 + 4 * (chi % NQe) + chi / NQe;
           if (n < g.N) atomicAdd(cp + n, __uint_as_float(v[e]) + __uint_as_float(w[e]));
         }
         continue;
