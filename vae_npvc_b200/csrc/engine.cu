@@ -311,6 +311,12 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       if (g.rows <= 0) break;
       if (!view_vec_ok(g.D)) return fail(NPVC_ERR_ARG, "wgrad dC view must be 16B aligned: " + o.name);
       if (umma_allowed(h, o)) { int rc = launch_umma_wgrad(c, o, op_index); if (rc) return rc; break; }
+      if (o.K <= 8 && o.N <= 16 && g.rows >= 4096) {
+        const long long blocks = (long long)h->sm_count * 4;
+        long long rpb = (g.rows + blocks - 1) / blocks; rpb = (rpb + 255) / 256 * 256;
+        wgrad_tiny_kernel<8, 16><<<(unsigned)((g.rows + rpb - 1) / rpb), 256, 0, st>>>(g, rpb);
+        h->launches++; break;
+      }
       launch_wgrad(g, !view_vec_ok(g.A), h->sm_count, st); h->launches++; break;
     }
     case OP_LN_FWD: {

@@ -423,6 +423,67 @@ __global__ void __launch_bounds__(128) fewrows_gemm_kernel(const float* A, int l
 }
 
 // =============================================================================================
+// (W) for tiny K x N (first layer: 7 taps x 16 channels) and millions of rows: every thread keeps
+// the whole K x N gradient in registers over its rows, one block reduction + K*N atomics per block.
+// =============================================================================================
+template <int KMAX, int NMAX>
+__global__ void __launch_bounds__(256) wgrad_tiny_kernel(WgradArgs g, long long rows_per_block) {
+  __shared__ float red[8][KMAX * NMAX];
+  float acc[KMAX][NMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; k++)
+#pragma unroll
+    for (int n = 0; n < NMAX; n++) acc[k][n] = 0.f;
+  const long long rb = (long long)blockIdx.x * rows_per_block;
+  long long re = rb + rows_per_block; if (re > g.rows) re = g.rows;
+  for (long long r = rb + threadIdx.x; r < re; r += 256) {
+    const long long fa = r / g.A.R; const int ja = (int)(r - fa * g.A.R);
+    const int inf = ja * g.A.rs + g.A.off;
+    const float* ap = g.A.p + fa * g.A.fs + inf;
+    float x[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+      bool ok = k < g.K;
+      if (g.A.pred) { const int q = inf + k; ok = ok && q >= 0 && q < g.A.flen; }
+      x[k] = ok ? ap[k] : 0.f;
+    }
+    const long long fd = r / g.D.R; const int jd = (int)(r - fd * g.D.R);
+    const float* dp = g.D.p + fd * g.D.fs + jd * g.D.rs + g.D.off;
+    float d[NMAX];
+#pragma unroll
+    for (int n4 = 0; n4 < NMAX / 4; n4++) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n4 * 4 < g.N) v = *reinterpret_cast<const float4*>(dp + n4 * 4);
+      d[n4 * 4] = v.x; d[n4 * 4 + 1] = v.y; d[n4 * 4 + 2] = v.z; d[n4 * 4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; k++)
+#pragma unroll
+      for (int n = 0; n < NMAX; n++) acc[k][n] = fmaf(x[k], d[n], acc[k][n]);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KMAX; k++)
+#pragma unroll
+    for (int n = 0; n < NMAX; n++) {
+      float v = acc[k][n];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[w][k * NMAX + n] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < KMAX * NMAX; i += 256) {
+    const int k = i / NMAX, n = i % NMAX;
+    if (k < g.K && n < g.N) {
+      float v = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ww++) v += red[ww][i];
+      atomicAdd(g.out + (long long)k * g.ld + n, v);
+    }
+  }
+}
+
+// =============================================================================================
 // block reductions
 // =============================================================================================
 __device__ __forceinline__ float warp_sum(float v) {

@@ -515,7 +515,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     for (Op& o : p.ops) {
       if (o.kind == OP_WGRAD) {
         // (W) form on the tensor cores: operands come straight from the activation / gradient views
-        if (o.rows_fixed || o.K < 64 || o.N < 32 || o.C.pred || o.A.pred) continue;     // tiny K/N: CUDA-core wgrad wins
+        if (o.rows_fixed || o.K < 64 || o.N < 32 || o.C.pred || o.A.pred) continue;     // tiny K/N (E0, G2): CUDA-core wgrads measured faster
         // producers read 4x4 patches with 16-byte loads
         if (o.A.fs % 4 || o.A.rs % 4 || o.A.off % 4 || o.C.fs % 4 || o.C.rs % 4 || o.C.off % 4) continue;
         o.umma = 1;
