@@ -295,12 +295,13 @@ int run_op(Ctx& c, const Op& o, int op_index) {
         RowGemmArgs rg; rg.A = g.A; rg.K = o.K; rg.B = g.B; rg.ldb = o.ldb; rg.N = o.N; rg.C = g.C; rg.rows = g.rows;
         rg.bias0 = g.bias0; rg.bias_mod = o.bias_mod;
         const bool sc = !view_vec_ok(g.A) || (o.K % 4 != 0);
-        const unsigned blocks = (unsigned)((g.rows + 255) / 256);
-        if (sc && o.K <= 8 && o.N <= 16) rowgemm_kernel<8, 16, true><<<blocks, 256, 0, st>>>(rg);
-        else if (!sc && o.K <= 48 && o.N <= 24) rowgemm_kernel<48, 24, false><<<blocks, 256, 0, st>>>(rg);
-        else if (!sc && o.K <= 56 && o.N <= 16) rowgemm_kernel<56, 16, false><<<blocks, 256, 0, st>>>(rg);
-        else if (!sc) rowgemm_kernel<64, 32, false><<<blocks, 256, 0, st>>>(rg);
-        else rowgemm_kernel<64, 32, true><<<blocks, 256, 0, st>>>(rg);
+        const unsigned b1 = (unsigned)((g.rows + 255) / 256), b2 = (unsigned)((g.rows + 511) / 512);
+        (void)b2;   // 2 rows / thread measured slower for the 48x24 / 56x16 shapes (170 registers)
+        if (sc && o.K <= 8 && o.N <= 16) rowgemm_kernel<8, 16, true, 2><<<b2, 256, 0, st>>>(rg);
+        else if (!sc && o.K <= 48 && o.N <= 24) rowgemm_kernel<48, 24, false, 1><<<b1, 256, 0, st>>>(rg);
+        else if (!sc && o.K <= 56 && o.N <= 16) rowgemm_kernel<56, 16, false, 1><<<b1, 256, 0, st>>>(rg);
+        else if (!sc) rowgemm_kernel<64, 32, false, 1><<<b1, 256, 0, st>>>(rg);
+        else rowgemm_kernel<64, 32, true, 1><<<b1, 256, 0, st>>>(rg);
         h->launches++; break;
       }
       launch_gemm(g, !view_vec_ok(g.A), st); h->launches++; break;
@@ -331,7 +332,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       g.dgamma = resolve(c, o.dgamma); g.dbeta = resolve(c, o.dbeta); g.dbias = resolve(c, o.dbias);
       g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
       long long blocks = (long long)h->sm_count * 8; if (blocks > c.n) blocks = c.n;
-      ln_bwd_kernel<<<(unsigned)blocks, 256, (size_t)3 * o.Cn * sizeof(float), st>>>(g); h->launches++; break;
+      ln_bwd_kernel<<<(unsigned)blocks, 256, (size_t)(2 * o.L + 3 * o.Cn) * sizeof(float), st>>>(g); h->launches++; break;
     }
     case OP_SAMPLE: {
       const int z = o.i0, fpb = 8;
@@ -355,12 +356,18 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       h->launches++; break;
     }
     case OP_SEGSUM: {
-      const int fpb = 64; size_t sm = (size_t)o.i0 * o.i1 * sizeof(float);
-      static bool attr_set = false;
-      if (!attr_set) { cudaFuncSetAttribute(segsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-      if (sm > 200 * 1024) return fail(NPVC_ERR_ARG, "y_dim * merge width too large for segsum shared memory");
-      segsum_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 256, sm, st>>>(
-          resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb);
+      if (o.i1 <= 16) {
+        const int fpb = 256;
+        dim3 grid((unsigned)((o.i0 + 127) / 128), (unsigned)((c.n + fpb - 1) / fpb));
+        segsum_kernel<<<grid, 128, 0, st>>>(resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb);
+      } else {
+        const int fpb = 64; size_t sm = (size_t)o.i0 * o.i1 * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(segsum_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+        if (sm > 200 * 1024) return fail(NPVC_ERR_ARG, "y_dim * merge width too large for segsum shared memory");
+        segsum_smem_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 256, sm, st>>>(
+            resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb);
+      }
       h->launches++; break;
     }
     case OP_COLSUM: {
@@ -453,6 +460,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   std::string err = build_plan(*arch, h->plan, h->use_umma);
   if (!err.empty()) { delete h; return fail(NPVC_ERR_ARG, "unsupported architecture: " + err); }
   if (max_chunk > 0) h->max_chunk = max_chunk;
+  else if (const char* mc = getenv("NPVC_MAX_CHUNK")) { long v = atol(mc); if (v > 0) h->max_chunk = v; }
   *out = h;
   return NPVC_OK;
 }

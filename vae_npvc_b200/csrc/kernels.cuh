@@ -329,8 +329,10 @@ struct RowGemmArgs {
   const float* bias0; int bias_mod;
 };
 
-template <int KMAX, int NMAX, bool ASCALAR>
+template <int KMAX, int NMAX, bool ASCALAR, int ROWS>
 __global__ void __launch_bounds__(256) rowgemm_kernel(RowGemmArgs g) {
+  // ROWS output rows per thread (rows r, r + 256, ... of the block's slab): every weight fetched
+  // from shared memory feeds ROWS FMAs, which moves the kernel from LDS-issue-bound to FMA-bound
   __shared__ __align__(16) float Ws[KMAX * NMAX];
   __shared__ float bs[NMAX];
   const int tid = threadIdx.x;
@@ -340,58 +342,71 @@ __global__ void __launch_bounds__(256) rowgemm_kernel(RowGemmArgs g) {
   }
   if (tid < NMAX) bs[tid] = (g.bias0 && tid < g.N) ? g.bias0[tid % g.bias_mod] : 0.f;
   __syncthreads();
-  const long long r = (long long)blockIdx.x * 256 + tid;
-  if (r >= g.rows) return;
-  float x[KMAX];
-  {
-    const long long f = r / g.A.R; const int j = (int)(r - f * g.A.R);
+  const long long rbase = (long long)blockIdx.x * (256 * ROWS) + tid;
+  float x[ROWS][KMAX];
+#pragma unroll
+  for (int q = 0; q < ROWS; q++) {
+    const long long r = rbase + q * 256;
+    const bool rok = r < g.rows;
+    const long long rr = rok ? r : 0;
+    const long long f = rr / g.A.R; const int j = (int)(rr - f * g.A.R);
     const int inf = j * g.A.rs + g.A.off;
     const float* ap = g.A.p + f * g.A.fs + inf;
     if (!ASCALAR) {
 #pragma unroll
       for (int k4 = 0; k4 < KMAX / 4; k4++) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k4 * 4 < g.K) v = *reinterpret_cast<const float4*>(ap + k4 * 4);
-        x[k4 * 4 + 0] = v.x; x[k4 * 4 + 1] = v.y; x[k4 * 4 + 2] = v.z; x[k4 * 4 + 3] = v.w;
+        if (rok && k4 * 4 < g.K) v = *reinterpret_cast<const float4*>(ap + k4 * 4);
+        x[q][k4 * 4 + 0] = v.x; x[q][k4 * 4 + 1] = v.y; x[q][k4 * 4 + 2] = v.z; x[q][k4 * 4 + 3] = v.w;
       }
     } else {
 #pragma unroll
       for (int k = 0; k < KMAX; k++) {
-        bool ok = k < g.K;
-        if (g.A.pred) { const int q = inf + k; ok = ok && q >= 0 && q < g.A.flen; }
-        x[k] = ok ? ap[k] : 0.f;
+        bool ok = rok && k < g.K;
+        if (g.A.pred) { const int qq = inf + k; ok = ok && qq >= 0 && qq < g.A.flen; }
+        x[q][k] = ok ? ap[k] : 0.f;
       }
     }
   }
-  float acc[NMAX];
+  float acc[ROWS][NMAX];
 #pragma unroll
-  for (int n = 0; n < NMAX; n++) acc[n] = bs[n];
+  for (int q = 0; q < ROWS; q++)
+#pragma unroll
+    for (int n = 0; n < NMAX; n++) acc[q][n] = bs[n];
 #pragma unroll
   for (int k = 0; k < KMAX; k++) {
     if (k < g.K) {
-      const float xv = x[k];
 #pragma unroll
       for (int n4 = 0; n4 < NMAX / 4; n4++) {
         const float4 w = *reinterpret_cast<const float4*>(&Ws[k * NMAX + n4 * 4]);
-        acc[n4 * 4 + 0] = fmaf(xv, w.x, acc[n4 * 4 + 0]); acc[n4 * 4 + 1] = fmaf(xv, w.y, acc[n4 * 4 + 1]);
-        acc[n4 * 4 + 2] = fmaf(xv, w.z, acc[n4 * 4 + 2]); acc[n4 * 4 + 3] = fmaf(xv, w.w, acc[n4 * 4 + 3]);
+#pragma unroll
+        for (int q = 0; q < ROWS; q++) {
+          const float xv = x[q][k];
+          acc[q][n4 * 4 + 0] = fmaf(xv, w.x, acc[q][n4 * 4 + 0]); acc[q][n4 * 4 + 1] = fmaf(xv, w.y, acc[q][n4 * 4 + 1]);
+          acc[q][n4 * 4 + 2] = fmaf(xv, w.z, acc[q][n4 * 4 + 2]); acc[q][n4 * 4 + 3] = fmaf(xv, w.w, acc[q][n4 * 4 + 3]);
+        }
       }
     }
   }
-  const long long f = r / g.C.R; const int j = (int)(r - f * g.C.R);
-  const int inf = j * g.C.rs + g.C.off;
-  float* cp = g.C.p + f * g.C.fs + inf;
-  const bool vec = !g.C.pred && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) && (g.N % 4 == 0);
-  if (vec) {
 #pragma unroll
-    for (int n4 = 0; n4 < NMAX / 4; n4++)
-      if (n4 * 4 < g.N) *reinterpret_cast<float4*>(cp + n4 * 4) = make_float4(acc[n4 * 4], acc[n4 * 4 + 1], acc[n4 * 4 + 2], acc[n4 * 4 + 3]);
-  } else {
+  for (int q = 0; q < ROWS; q++) {
+    const long long r = rbase + q * 256;
+    if (r >= g.rows) continue;
+    const long long f = r / g.C.R; const int j = (int)(r - f * g.C.R);
+    const int inf = j * g.C.rs + g.C.off;
+    float* cp = g.C.p + f * g.C.fs + inf;
+    const bool vec = !g.C.pred && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0) && (g.N % 4 == 0);
+    if (vec) {
 #pragma unroll
-    for (int n = 0; n < NMAX; n++) {
-      bool ok = n < g.N;
-      if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
-      if (ok) cp[n] = acc[n];
+      for (int n4 = 0; n4 < NMAX / 4; n4++)
+        if (n4 * 4 < g.N) *reinterpret_cast<float4*>(cp + n4 * 4) = make_float4(acc[q][n4 * 4], acc[q][n4 * 4 + 1], acc[q][n4 * 4 + 2], acc[q][n4 * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int n = 0; n < NMAX; n++) {
+        bool ok = n < g.N;
+        if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
+        if (ok) cp[n] = acc[q][n];
+      }
     }
   }
 }
@@ -564,8 +579,9 @@ struct LnBwdArgs {
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
-  extern __shared__ float chs[];                  // 3 * Cn
+  extern __shared__ __align__(16) float lsm[];    // [L] dxhat | [L] xhat | [3*Cn] channel sums
   __shared__ float red[40];
+  float* sdx = lsm; float* sxh = lsm + g.L; float* chs = lsm + 2 * g.L;
   for (int i = threadIdx.x; i < 3 * g.Cn; i += blockDim.x) chs[i] = 0.f;
   const int L4 = g.L >> 2;
   const bool fixed = ((blockDim.x * 4) % g.Cn) == 0;   // thread -> channel mapping constant across i
@@ -577,52 +593,55 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
     const float4* dy4 = reinterpret_cast<const float4*>(g.dy + f * g.L);
     const float4* xh4 = reinterpret_cast<const float4*>(g.xhat + f * g.L);
     float s1 = 0.f, s2 = 0.f;
+    // pass 1 (global -> smem): dxhat = dy * lrelu'(u) * gamma, partial sums, dgamma / dbeta
     for (int i = threadIdx.x; i < L4; i += blockDim.x) {
       float4 d = dy4[i], h = xh4[i];
       const int c = (i * 4) % g.Cn;
-      float dv[4] = {d.x, d.y, d.z, d.w}, hv[4] = {h.x, h.y, h.z, h.w};
+      float dv[4] = {d.x, d.y, d.z, d.w}, hv[4] = {h.x, h.y, h.z, h.w}, ox[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         float gm = g.gamma[c + e];
         float u = fmaf(hv[e], gm, g.beta[c + e]);
         float du = dv[e] * (u >= 0.f ? 1.0f : 0.02f);
-        float dxh = du * gm;
-        s1 += dxh; s2 += dxh * hv[e];
+        ox[e] = du * gm;
+        s1 += ox[e]; s2 += ox[e] * hv[e];
+        if (fixed) { adg[e] += du * hv[e]; adb[e] += du; }
+        else { atomicAdd(&chs[c + e], du * hv[e]); atomicAdd(&chs[g.Cn + c + e], du); }
       }
+      reinterpret_cast<float4*>(sdx)[i] = make_float4(ox[0], ox[1], ox[2], ox[3]);
+      reinterpret_cast<float4*>(sxh)[i] = h;
     }
     s1 = block_sum(s1, red) * invL;
     s2 = block_sum(s2, red) * invL;
     const float rs = g.rstd[f];
     float4* dc4 = reinterpret_cast<float4*>(g.dc + f * g.out_flen);
+    // pass 2 (smem -> global): dc = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), zero pads
     for (int i = threadIdx.x; i < F4; i += blockDim.x) {
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       const int ii = i - off4;
       if (ii >= 0 && ii < L4) {
-        float4 d = dy4[ii], h = xh4[ii];
-        const int c = (ii * 4) % g.Cn;
-        float dv[4] = {d.x, d.y, d.z, d.w}, hv[4] = {h.x, h.y, h.z, h.w}, ov[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          float gm = g.gamma[c + e];
-          float u = fmaf(hv[e], gm, g.beta[c + e]);
-          float du = dv[e] * (u >= 0.f ? 1.0f : 0.02f);
-          float dxh = du * gm;
-          ov[e] = rs * (dxh - s1 - hv[e] * s2);
-          if (fixed) { adg[e] += du * hv[e]; adb[e] += du; adc[e] += ov[e]; }
-          else { atomicAdd(&chs[c + e], du * hv[e]); atomicAdd(&chs[g.Cn + c + e], du); atomicAdd(&chs[2 * g.Cn + c + e], ov[e]); }
+        float4 d = reinterpret_cast<const float4*>(sdx)[ii], h = reinterpret_cast<const float4*>(sxh)[ii];
+        o.x = rs * (d.x - s1 - h.x * s2); o.y = rs * (d.y - s1 - h.y * s2);
+        o.z = rs * (d.z - s1 - h.z * s2); o.w = rs * (d.w - s1 - h.w * s2);
+        if (fixed) { adc[0] += o.x; adc[1] += o.y; adc[2] += o.z; adc[3] += o.w; }
+        else {
+          const int c = (ii * 4) % g.Cn;
+          atomicAdd(&chs[2 * g.Cn + c], o.x); atomicAdd(&chs[2 * g.Cn + c + 1], o.y);
+          atomicAdd(&chs[2 * g.Cn + c + 2], o.z); atomicAdd(&chs[2 * g.Cn + c + 3], o.w);
         }
-        o = make_float4(ov[0], ov[1], ov[2], ov[3]);
       }
       dc4[i] = o;
     }
+    __syncthreads();                               // smem frame buffers are reused by the next frame
   }
   if (fixed) {
-    // thread t handles float4 index ii = t + it*blockDim - off4, so its channels are
-    // (4t - out_off) mod Cn + {0..3} for every it when blockDim*4 % Cn == 0
-    const int c = (int)(((long long)threadIdx.x * 4 - g.out_off) % g.Cn + g.Cn) % g.Cn;
+    // pass 1: thread t handles float4 index t + it*blockDim -> channels (4t) mod Cn + {0..3};
+    // pass 2: index ii = t + it*blockDim - off4    -> channels (4t - out_off) mod Cn + {0..3}
+    const int c1 = (threadIdx.x * 4) % g.Cn;
+    const int c2 = (int)(((long long)threadIdx.x * 4 - g.out_off) % g.Cn + g.Cn) % g.Cn;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      atomicAdd(&chs[c + e], adg[e]); atomicAdd(&chs[g.Cn + c + e], adb[e]); atomicAdd(&chs[2 * g.Cn + c + e], adc[e]);
+      atomicAdd(&chs[c1 + e], adg[e]); atomicAdd(&chs[g.Cn + c1 + e], adb[e]); atomicAdd(&chs[2 * g.Cn + c2 + e], adc[e]);
     }
   }
   __syncthreads();
@@ -717,8 +736,36 @@ __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float*
 // =============================================================================================
 // per-speaker row sums: out[y[f], :] += in[f, :]   (dynamic smem: ny * N floats)
 // =============================================================================================
-__global__ void segsum_kernel(const float* in, const long long* y, float* out, int N, int ny,
-                              long long frames, int frames_per_block) {
+__global__ void __launch_bounds__(128) segsum_kernel(const float* in, const long long* y, float* out, int N, int ny,
+                                                     long long frames, int frames_per_block) {
+  // thread = column, block = (column tile, frame chunk); the speaker id is uniform across the block,
+  // so "acc[s] += v" is a uniform switch over register accumulators: no shared memory, ny atomics per thread
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long f0 = (long long)blockIdx.y * frames_per_block;
+  float acc[16];
+#pragma unroll
+  for (int s = 0; s < 16; s++) acc[s] = 0.f;
+  for (int i = 0; i < frames_per_block; i++) {
+    const long long f = f0 + i; if (f >= frames) break;
+    const int s = (int)y[f];
+    const float v = (col < N) ? in[f * N + col] : 0.f;
+    switch (s) {
+      case 0: acc[0] += v; break; case 1: acc[1] += v; break; case 2: acc[2] += v; break; case 3: acc[3] += v; break;
+      case 4: acc[4] += v; break; case 5: acc[5] += v; break; case 6: acc[6] += v; break; case 7: acc[7] += v; break;
+      case 8: acc[8] += v; break; case 9: acc[9] += v; break; case 10: acc[10] += v; break; case 11: acc[11] += v; break;
+      case 12: acc[12] += v; break; case 13: acc[13] += v; break; case 14: acc[14] += v; break; case 15: acc[15] += v; break;
+      default: break;
+    }
+  }
+  if (col < N) {
+#pragma unroll
+    for (int s = 0; s < 16; s++) if (s < ny && acc[s] != 0.f) atomicAdd(&out[(long long)s * N + col], acc[s]);
+  }
+}
+
+// fallback for more than 16 classes: shared-memory accumulators (dynamic smem: ny * N floats)
+__global__ void segsum_smem_kernel(const float* in, const long long* y, float* out, int N, int ny,
+                                   long long frames, int frames_per_block) {
   extern __shared__ float acc[];
   for (int i = threadIdx.x; i < ny * N; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
