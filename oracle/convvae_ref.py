@@ -225,8 +225,10 @@ def generator(P, arch, z, y, acts=None):
             out = torch.einsum("nci,ipoc->nop", xin, T)            # [N, Cout, H]
             x = out.unsqueeze(-1) + b.reshape(1, -1, 1, 1)
         else:
-            x = F.conv_transpose2d(x, W.permute(3, 2, 0, 1), b, stride=(s, 1),
-                                   padding=((k - s) // 2, 0))
+            # SAME transposed conv = full transposed conv cropped to s*H from crop_left = (k-s)//2
+            # (== padding=(k-s)//2 when k-s is even, as in the reference architecture)
+            full = F.conv_transpose2d(x, W.permute(3, 2, 0, 1), None, stride=(s, 1))
+            x = full[:, :, cl:cl + s * H, :] + b.reshape(1, -1, 1, 1)
         if i < len(gg) - 1:
             x = _layernorm(x, P["Generator/ConvT-LN%d.scale" % i], P["Generator/ConvT-LN%d.offset" % i])
             x = _lrelu(x)

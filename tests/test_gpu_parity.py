@@ -192,6 +192,13 @@ def test_cfg3_inference_size(eng, arch):
     assert rel(mu[sl], mu_ref) <= TOL_OUT and rel(xh[sl], xh_ref) <= TOL_OUT
 
 
+def test_alternative_architectures_on_gpu(alt_arch):
+    """The CUDA path on architectures other than VCC2016 (different tile / routing decisions)."""
+    from vae_npvc_b200.engine import Engine
+    e2 = Engine(alt_arch, "cuda:0")
+    _check_against_oracle(e2, alt_arch, 29)
+
+
 def test_tanhize_and_record_reader(eng):
     g = torch.Generator(device="cpu").manual_seed(3)
     xmin = torch.randn(513, generator=g) - 3; xmax = xmin + 1 + torch.rand(513, generator=g)

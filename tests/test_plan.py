@@ -111,3 +111,24 @@ def test_no_gpu_fails_loudly(arch):
     buf = np.zeros(1024, np.float32)
     rc = h.lib.npvc_pack_weights(h.h, buf.ctypes.data, 256 * 1024 * 1024 * 16, 1 << 40, None)
     assert rc != 0 and ("CUDA" in lib.last_error() or "device" in lib.last_error())
+
+
+@pytest.mark.parametrize("umma", [0, 1])
+def test_alternative_architectures(alt_arch, umma, monkeypatch):
+    """Generic plan: other kernel sizes / strides / asymmetric pads / padded channel counts."""
+    monkeypatch.setenv("NPVC_UMMA", str(umma))
+    tol = 1e-10 if not umma else 1e-5
+    from oracle import convvae_loops as L
+    h = lib.Handle(alt_arch)
+    plan = h.plan()
+    tables = {k: h.plan_table(k) for k in ("pack_src", "unpack_ptr", "unpack_idx")}
+    P = R.init_params(alt_arch, 0)
+    x, y, eps = R.make_inputs(alt_arch, 3)
+    ref = R.forward(alt_arch, P, x, y, eps, with_grads=True)
+    lo = L.forward(alt_arch, P, x, y, eps)
+    assert rel(ref["xh"], lo["xh"]) < 1e-12 and rel(ref["mu"], lo["mu"]) < 1e-12          # both oracle formulations
+    out = PI.Interp(plan, tables, R.flatten_params(alt_arch, P, np.float64), 3, x, y, eps).loss_fwd_bwd()
+    for k in ("mu", "lv", "z", "xh"):
+        assert rel(out[k], ref[k]) < tol, k
+    assert rel(out["grad"], R.flatten_params(alt_arch, ref["grads"], np.float64)) < tol
+    assert h.param_count() == R.n_params(alt_arch)

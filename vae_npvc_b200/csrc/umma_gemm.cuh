@@ -78,6 +78,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// L2 prefetch of a tile (no shared memory, no barrier): shortens the latency of the later TMA load
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -459,10 +463,22 @@ umma_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     if (lane == 0) {
       const uint32_t tx = (uint32_t)g.rows_tile * 128u + 2u * b_tile_bytes;
       uint32_t it = 0;
+      // look-ahead iterator: the A tile of the k-block PF steps ahead is prefetched into L2 (A is
+      // the operand that comes from DRAM; the weight tiles stay L2-resident)
+      constexpr int PF = 6;
+      int pt = blockIdx.x, pkb = 0;
+      auto pf_step = [&]() {
+        if (pt < total_tiles) {
+          tma_prefetch_3d(&tmA, pkb * BK, 0, (pt / pa.n_tiles) * g.FB);
+          if (++pkb == g.kblocks) { pkb = 0; pt += gridDim.x; }
+        }
+      };
+      for (int i = 0; i < PF; i++) pf_step();
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int tile_m = t / pa.n_tiles, n0 = (t % pa.n_tiles) * g.BN;
         for (int kb = 0; kb < g.kblocks; kb++, it++) {
           const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
+          pf_step();
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t st = sbase + (uint32_t)s * stage_bytes;
           mbar_expect_tx(full_bar(s), tx);
