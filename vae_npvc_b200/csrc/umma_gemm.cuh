@@ -235,34 +235,49 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr int DT = (MODE == 1) ? 2 : 1;         // dC tasks per thread
       const int ka = tile_m * 128 + 4 * lane;
       const bool a_ok = ka < g.K;
-      auto load_block = [&](long long blk, float4 (&va)[4], float4 (&vd)[DT][4]) {
-        const long long rb = blk * 32;
-        {   // A task: rows rb + 4*pw + e, columns ka..ka+3
-          const long long r0 = rb + 4 * pw;
-          long long f = r0 / g.A.R; int j = (int)(r0 - f * g.A.R);
+      // Row addressing is incremental (adds only): a task tracks (row, j = row % R, element offset
+      // f*fs + j*rs) of its first row; blocks are visited in order, each 32 rows further on.
+      const int q32 = 32 / g.A.R, r32 = 32 % g.A.R;                 // A and D views share R
+      const long long a_wrap = g.A.fs - (long long)g.A.R * g.A.rs, d_wrap = g.D.fs - (long long)g.D.R * g.D.rs;
+      const long long a_blk = (long long)q32 * g.A.fs + (long long)r32 * g.A.rs, d_blk = (long long)q32 * g.D.fs + (long long)r32 * g.D.rs;
+      const float* a_base = g.A.p + g.A.off + ka;
+      long long a_row = kb_begin * 32 + 4 * pw; int a_j; long long a_off;
+      { const long long f = a_row / g.A.R; a_j = (int)(a_row - f * g.A.R); a_off = f * g.A.fs + (long long)a_j * g.A.rs; }
+      const float* d_base[DT]; long long d_row[DT], d_off[DT]; int d_j[DT]; bool d_ok[DT];
+#pragma unroll
+      for (int d = 0; d < DT; d++) {
+        const int tsk = pt + d * 256;
+        const int rq = tsk / NQ, nq = tsk - rq * NQ;
+        const int nn = n0 + 4 * nq;
+        d_ok[d] = (tsk < 8 * NQ) && (nn < g.N);
+        d_base[d] = g.D.p + g.D.off + nn;
+        d_row[d] = kb_begin * 32 + 4 * rq;
+        const long long f = d_row[d] / g.D.R; d_j[d] = (int)(d_row[d] - f * g.D.R);
+        d_off[d] = f * g.D.fs + (long long)d_j[d] * g.D.rs;
+      }
+      auto load_block = [&](float4 (&va)[4], float4 (&vd)[DT][4]) {
+        {
+          long long off = a_off; int j = a_j;
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a_ok && r0 + e < g.rows) v = __ldg(reinterpret_cast<const float4*>(g.A.p + f * g.A.fs + (long long)j * g.A.rs + g.A.off + ka));
+            if (a_ok && a_row + e < g.rows) v = __ldg(reinterpret_cast<const float4*>(a_base + off));
             va[e] = v;
-            if (++j == g.A.R) { j = 0; f++; }
+            off += g.A.rs; if (++j == g.A.R) { j = 0; off += a_wrap; }
           }
+          a_row += 32; a_off += a_blk; a_j += r32; if (a_j >= g.A.R) { a_j -= g.A.R; a_off += a_wrap; }
         }
 #pragma unroll
         for (int d = 0; d < DT; d++) {
-          const int tsk = pt + d * 256;
-          const int rq = tsk / NQ, nq = tsk - rq * NQ;
-          const int nn = n0 + 4 * nq;
-          const bool ok = (tsk < 8 * NQ) && (nn < g.N);
-          const long long r0 = rb + 4 * rq;
-          long long f = r0 / g.D.R; int j = (int)(r0 - f * g.D.R);
+          long long off = d_off[d]; int j = d_j[d];
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok && r0 + e < g.rows) v = __ldg(reinterpret_cast<const float4*>(g.D.p + f * g.D.fs + (long long)j * g.D.rs + g.D.off + nn));
+            if (d_ok[d] && d_row[d] + e < g.rows) v = __ldg(reinterpret_cast<const float4*>(d_base[d] + off));
             vd[d][e] = v;
-            if (++j == g.D.R) { j = 0; f++; }
+            off += g.D.rs; if (++j == g.D.R) { j = 0; off += d_wrap; }
           }
+          d_row[d] += 32; d_off[d] += d_blk; d_j[d] += r32; if (d_j[d] >= g.D.R) { d_j[d] -= g.D.R; d_off[d] += d_wrap; }
         }
       };
       auto split_store = [&](uint8_t* hi_base, uint8_t* lo_base, int rho, int chunk, float x0, float x1, float x2, float x3) {
@@ -302,19 +317,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (MODE == 1) {
         // software-pipelined: block i+1's loads are in flight while block i is split and stored
         float4 pa[4], pd[DT][4], qa[4], qd[DT][4];
-        load_block(kb_begin, pa, pd);
+        load_block(pa, pd);
         for (int i = 0; i < nkb; i += 2) {
-          if (i + 1 < nkb) load_block(kb_begin + i + 1, qa, qd);
+          if (i + 1 < nkb) load_block(qa, qd);
           store_block(i, pa, pd);
           if (i + 1 < nkb) {
-            if (i + 2 < nkb) load_block(kb_begin + i + 2, pa, pd);
+            if (i + 2 < nkb) load_block(pa, pd);
             store_block(i + 1, qa, qd);
           }
         }
       } else {
         // BN <= 128: the second CTA on the SM covers this CTA's load latency
         float4 pa[4], pd[DT][4];
-        for (int i = 0; i < nkb; i++) { load_block(kb_begin + i, pa, pd); store_block(i, pa, pd); }
+        for (int i = 0; i < nkb; i++) { load_block(pa, pd); store_block(i, pa, pd); }
       }
     }
     if (warp >= 6) goto done;                         // second producer group has no epilogue share
