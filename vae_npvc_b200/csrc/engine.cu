@@ -318,6 +318,12 @@ int run_op(Ctx& c, const Op& o, int op_index) {
         wgrad_tiny_kernel<8, 16><<<(unsigned)((g.rows + rpb - 1) / rpb), 256, 0, st>>>(g, rpb);
         h->launches++; break;
       }
+      if (o.K > 8 && o.K <= 48 && o.N <= 24 && o.K % 4 == 0 && o.N % 4 == 0 && view_vec_ok(g.A) && g.rows >= 4096) {
+        const long long blocks = (long long)h->sm_count * 8;
+        long long rpb = (g.rows + blocks - 1) / blocks; rpb = (rpb + 63) / 64 * 64;
+        wgrad_small_kernel<48, 24><<<(unsigned)((g.rows + rpb - 1) / rpb), 192, 0, st>>>(g, rpb);
+        h->launches++; break;
+      }
       launch_wgrad(g, !view_vec_ok(g.A), h->sm_count, st); h->launches++; break;
     }
     case OP_LN_FWD: {

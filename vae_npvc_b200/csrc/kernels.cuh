@@ -499,6 +499,75 @@ __global__ void __launch_bounds__(256) wgrad_tiny_kernel(WgradArgs g, long long 
 }
 
 // =============================================================================================
+// (W) for small K x N (<= 48 x 24: the last stride-3 transposed conv) and millions of rows:
+// 6 x 4 register blocks (24 FMAs per 4 shared-memory loads), 4 row-slices per block, rows staged
+// through shared memory with coalesced 16-byte loads, one reduction + K*N atomics per block.
+// =============================================================================================
+template <int KT, int NT>
+__global__ void __launch_bounds__(192) wgrad_small_kernel(WgradArgs g, long long rows_per_block) {
+  constexpr int RB = 64, TG = (KT / 6) * (NT / 4), SL = 4;
+  static_assert(TG * SL == 192, "thread layout");
+  __shared__ __align__(16) float As[RB][KT];
+  __shared__ __align__(16) float Ds[RB][NT];
+  __shared__ float red[SL][KT * NT];
+  const int tid = threadIdx.x, sl = tid / TG, tg = tid % TG;
+  const int tk = tg / (NT / 4), tn = tg % (NT / 4);
+  float acc[6][4];
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  const long long rb = (long long)blockIdx.x * rows_per_block;
+  long long re = rb + rows_per_block; if (re > g.rows) re = g.rows;
+  for (long long r0 = rb; r0 < re; r0 += RB) {
+    for (int i = tid; i < RB * (KT / 4); i += 192) {
+      const int rr = i / (KT / 4), q = i % (KT / 4);
+      const long long r = r0 + rr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < re && q * 4 < g.K) {
+        const long long f = r / g.A.R; const int j = (int)(r - f * g.A.R);
+        v = *reinterpret_cast<const float4*>(g.A.p + f * g.A.fs + (long long)j * g.A.rs + g.A.off + q * 4);
+      }
+      *reinterpret_cast<float4*>(&As[rr][q * 4]) = v;
+    }
+    for (int i = tid; i < RB * (NT / 4); i += 192) {
+      const int rr = i / (NT / 4), q = i % (NT / 4);
+      const long long r = r0 + rr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < re && q * 4 < g.N) {
+        const long long f = r / g.D.R; const int j = (int)(r - f * g.D.R);
+        v = *reinterpret_cast<const float4*>(g.D.p + f * g.D.fs + (long long)j * g.D.rs + g.D.off + q * 4);
+      }
+      *reinterpret_cast<float4*>(&Ds[rr][q * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = sl; rr < RB; rr += SL) {
+      const float2 a0 = *reinterpret_cast<const float2*>(&As[rr][tk * 6]);
+      const float2 a1 = *reinterpret_cast<const float2*>(&As[rr][tk * 6 + 2]);
+      const float2 a2 = *reinterpret_cast<const float2*>(&As[rr][tk * 6 + 4]);
+      const float4 d = *reinterpret_cast<const float4*>(&Ds[rr][tn * 4]);
+      const float a[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        acc[i][0] = fmaf(a[i], d.x, acc[i][0]); acc[i][1] = fmaf(a[i], d.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], d.z, acc[i][2]); acc[i][3] = fmaf(a[i], d.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) red[sl][(tk * 6 + i) * NT + tn * 4 + j] = acc[i][j];
+  __syncthreads();
+  for (int i = tid; i < KT * NT; i += 192) {
+    const int k = i / NT, n = i % NT;
+    if (k < g.K && n < g.N) atomicAdd(g.out + (long long)k * g.ld + n, red[0][i] + red[1][i] + red[2][i] + red[3][i]);
+  }
+}
+
+// =============================================================================================
 // block reductions
 // =============================================================================================
 __device__ __forceinline__ float warp_sum(float v) {
