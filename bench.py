@@ -267,9 +267,13 @@ def main():
     top_ms = top["ms"] / top["calls"]
     top_flops = 2.0 * (top["rows"] / top["calls"]) * top["K"] * top["N"] if top["kind"] in (0, 1) else 0.0
     achieved_tf = top_flops / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))["bytes_per_launch"].get(top["name"])
     roofline = {
         "bound": "tensor", "kernel": top["name"], "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
-        "frac": achieved_tf / pk["tf"], "traffic": None, "peak_source": pk["source"] + " bf16 dense (sustained)",
+        "frac": achieved_tf / pk["tf"], "traffic": traffic, "peak_source": pk["source"] + " bf16 dense (sustained)",
         "share_of_step": top["ms"] / tot_ms if tot_ms else None,
         "note": "fp32 path: algorithmic FLOPs (2*rows*K*N of the dense contraction) / CUDA-event time of that op; "
                 "3xTF32 on tcgen05 caps this fraction at 1/6 of the bf16 peak",
