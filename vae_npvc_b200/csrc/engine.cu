@@ -243,15 +243,14 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   g.out = resolve(c, o.B); g.ld = o.ldb;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(umma_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(umma_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(umma_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 1) + 16;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 1) + 16;
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)S);
-  CUtensorMap dummy; memset(&dummy, 0, sizeof dummy);
-  if (pipelined) umma_gemm_kernel<1><<<grid, 320, smem, st>>>(dummy, dummy, dummy, g);   // 8 producer warps
-  else umma_gemm_kernel<2><<<grid, 320, smem, st>>>(dummy, dummy, dummy, g);
+  if (pipelined) umma_wgrad_kernel<1><<<grid, 320, smem, st>>>(g);   // 8 producer warps
+  else umma_wgrad_kernel<2><<<grid, 320, smem, st>>>(g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
