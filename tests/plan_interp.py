@@ -154,7 +154,7 @@ class Interp:
         c = np.arange(L) % Cn
         u = xh * gamma[c] + beta[c]
         a = np.maximum(u, 0.02 * u)
-        self.flat(op["xhat"])[0][:n * L] = xh.reshape(-1)
+        self.flat(op["r0"])[0][:n] = m[:, 0]            # (mean, rstd) kept; backward recomputes xhat from c
         self.flat(op["rstd"])[0][:n] = rs[:, 0]
         out = self.flat(op["aout"])[0].reshape(n, op["out_flen"])
         out[:] = 0.0
@@ -163,8 +163,8 @@ class Interp:
     def op_3(self, op):    # LN_BWD
         L, Cn, n = op["L"], op["Cn"], self.n
         dy = self.flat(op["in"])[0][:n * L].reshape(n, L)
-        xh = self.flat(op["xhat"])[0][:n * L].reshape(n, L)
         rs = self.flat(op["rstd"])[0][:n][:, None]
+        xh = (self.flat(op["xhat"])[0][:n * L].reshape(n, L) - self.flat(op["r0"])[0][:n][:, None]) * rs   # "xhat" ref = raw conv output
         garr, goff = self.flat(op["gamma"]); barr, boff = self.flat(op["beta"])
         gamma, beta = garr[goff:goff + Cn], barr[boff:boff + Cn]
         assert not np.isnan(dy).any() and not np.isnan(xh).any()

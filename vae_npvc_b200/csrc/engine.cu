@@ -326,13 +326,13 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       launch_wgrad(g, !view_vec_ok(g.A), h->sm_count, st); h->launches++; break;
     }
     case OP_LN_FWD: {
-      LnFwdArgs g; g.in = resolve(c, o.in); g.xhat = c.train ? resolve(c, o.xhat) : nullptr; g.aout = resolve(c, o.aout);
+      LnFwdArgs g; g.in = resolve(c, o.in); g.mean = resolve(c, o.r0); g.aout = resolve(c, o.aout);
       g.rstd = resolve(c, o.rstd); g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta);
       g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
       ln_fwd_kernel<<<(unsigned)c.n, 256, (size_t)o.L * sizeof(float), st>>>(g); h->launches++; break;
     }
     case OP_LN_BWD: {
-      LnBwdArgs g; g.dy = resolve(c, o.in); g.xhat = resolve(c, o.xhat); g.rstd = resolve(c, o.rstd);
+      LnBwdArgs g; g.dy = resolve(c, o.in); g.cin = resolve(c, o.xhat); g.mean = resolve(c, o.r0); g.rstd = resolve(c, o.rstd);
       g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta); g.dc = resolve(c, o.aout);
       g.dgamma = resolve(c, o.dgamma); g.dbeta = resolve(c, o.dbeta); g.dbias = resolve(c, o.dbias);
       g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;

@@ -591,7 +591,7 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats *
 // Layernorm + lrelu forward  (util/layers.py:10-44,147-149): one block per frame
 // =============================================================================================
 struct LnFwdArgs {
-  const float* in; float* xhat; float* aout; float* rstd; const float* gamma; const float* beta;
+  const float* in; float* mean; float* aout; float* rstd; const float* gamma; const float* beta;
   int L, Cn, out_flen, out_off; long long frames;
 };
 
@@ -616,8 +616,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs g) {
   }
   const float var = block_sum(q, red) / (float)g.L;
   const float rs = rsqrtf(var + NPVC_LN_EPS);
-  if (threadIdx.x == 0) g.rstd[f] = rs;
-  float* xo = g.xhat ? g.xhat + f * g.L : nullptr;
+  if (threadIdx.x == 0) { g.rstd[f] = rs; g.mean[f] = mean; }
   float* ao = g.aout + f * g.out_flen;
   const int off4 = g.out_off >> 2, F4 = g.out_flen >> 2;
   for (int i = threadIdx.x; i < F4; i += blockDim.x) {
@@ -627,7 +626,6 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs g) {
       float4 v = reinterpret_cast<const float4*>(sm)[ii];
       const int c = (ii * 4) % g.Cn;
       float4 h = make_float4((v.x - mean) * rs, (v.y - mean) * rs, (v.z - mean) * rs, (v.w - mean) * rs);
-      if (xo) reinterpret_cast<float4*>(xo)[ii] = h;
       o.x = lrelu_f(fmaf(h.x, g.gamma[c], g.beta[c]));
       o.y = lrelu_f(fmaf(h.y, g.gamma[c + 1], g.beta[c + 1]));
       o.z = lrelu_f(fmaf(h.z, g.gamma[c + 2], g.beta[c + 2]));
@@ -642,7 +640,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs g) {
 // into a zero-padded frame), dgamma, dbeta, dbias.  Persistent blocks, grid-stride over frames.
 // =============================================================================================
 struct LnBwdArgs {
-  const float* dy; const float* xhat; const float* rstd; const float* gamma; const float* beta;
+  const float* dy; const float* cin; const float* mean; const float* rstd; const float* gamma; const float* beta;   // cin = raw conv output
   float* dc; float* dgamma; float* dbeta; float* dbias;
   int L, Cn, out_flen, out_off; long long frames;
 };
@@ -660,11 +658,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
   __syncthreads();
   for (long long f = blockIdx.x; f < g.frames; f += gridDim.x) {
     const float4* dy4 = reinterpret_cast<const float4*>(g.dy + f * g.L);
-    const float4* xh4 = reinterpret_cast<const float4*>(g.xhat + f * g.L);
+    const float4* xh4 = reinterpret_cast<const float4*>(g.cin + f * g.L);
+    const float rs = g.rstd[f], mu = g.mean[f];
     float s1 = 0.f, s2 = 0.f;
     // pass 1 (global -> smem): dxhat = dy * lrelu'(u) * gamma, partial sums, dgamma / dbeta
     for (int i = threadIdx.x; i < L4; i += blockDim.x) {
       float4 d = dy4[i], h = xh4[i];
+      h.x = (h.x - mu) * rs; h.y = (h.y - mu) * rs; h.z = (h.z - mu) * rs; h.w = (h.w - mu) * rs;   // xhat, as the forward formed it
       const int c = (i * 4) % g.Cn;
       float dv[4] = {d.x, d.y, d.z, d.w}, hv[4] = {h.x, h.y, h.z, h.w}, ox[4];
 #pragma unroll
@@ -682,7 +682,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
     }
     s1 = block_sum(s1, red) * invL;
     s2 = block_sum(s2, red) * invL;
-    const float rs = g.rstd[f];
     float4* dc4 = reinterpret_cast<float4*>(g.dc + f * g.out_flen);
     // pass 2 (smem -> global): dc = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), zero pads
     for (int i = threadIdx.x; i < F4; i += blockDim.x) {

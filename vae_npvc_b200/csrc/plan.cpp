@@ -312,12 +312,12 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   p.buf_adw = B.add_buf("arena_dw", 0, p.arena_dw, true);
   int b_dptab = B.add_buf("dptab", 0, (int64_t)a.y_dim * Nm, true);
   p.buf_dptab = b_dptab;
-  std::vector<int> b_ce(nE), b_xe(nE), b_ae(nE), b_re(nE), b_dce(nE), b_dae(nE);
+  std::vector<int> b_ce(nE), b_me(nE), b_ae(nE), b_re(nE), b_dce(nE), b_dae(nE);
   std::vector<int> ae_flen(nE), ae_off(nE), dce_flen(nE), dce_off(nE);
   for (int e = 0; e < nE; e++) {
     char nm[32]; const EncL& l = E[e]; int L = l.Ho * l.Co;
     snprintf(nm, sizeof nm, "c_e%d", e);    b_ce[e] = B.add_buf(nm, L, 0, false);
-    snprintf(nm, sizeof nm, "xhat_e%d", e); b_xe[e] = B.add_buf(nm, L, 0, true);
+    snprintf(nm, sizeof nm, "mean_e%d", e); b_me[e] = B.add_buf(nm, 1, 0, false);
     if (e < nE - 1) { ae_flen[e] = (E[e + 1].pl + l.Ho + E[e + 1].pr) * l.Co; ae_off[e] = E[e + 1].pl * l.Co; }
     else { ae_flen[e] = L; ae_off[e] = 0; }
     snprintf(nm, sizeof nm, "a_e%d", e);    b_ae[e] = B.add_buf(nm, ae_flen[e], 0, false);
@@ -334,12 +334,12 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   const int hm_flen = (-G[0].lo + gh + G[0].hi) * gcp, hm_off = -G[0].lo * gcp;
   int b_hm = B.add_buf("hm", hm_flen, 0, false);
   int b_dhm = B.add_buf("dhm", Nm, 0, true);
-  std::vector<int> b_cg(nG, -1), b_xg(nG, -1), b_ag(nG, -1), b_rg(nG, -1), b_dcg(nG, -1), b_dag(nG, -1);
+  std::vector<int> b_cg(nG, -1), b_mg(nG, -1), b_ag(nG, -1), b_rg(nG, -1), b_dcg(nG, -1), b_dag(nG, -1);
   std::vector<int> ag_flen(nG), ag_off(nG), dcg_flen(nG), dcg_off(nG);
   for (int g = 0; g < nG - 1; g++) {
     char nm[32]; const GenL& l = G[g]; int L = l.Ho * l.Co;
     snprintf(nm, sizeof nm, "c_g%d", g);    b_cg[g] = B.add_buf(nm, L, 0, false);
-    snprintf(nm, sizeof nm, "xhat_g%d", g); b_xg[g] = B.add_buf(nm, L, 0, true);
+    snprintf(nm, sizeof nm, "mean_g%d", g); b_mg[g] = B.add_buf(nm, 1, 0, false);
     const GenL& nx = G[g + 1];
     if (!nx.dense) { ag_flen[g] = (-nx.lo + l.Ho + nx.hi) * l.Co; ag_off[g] = -nx.lo * l.Co; }
     else { ag_flen[g] = L; ag_off[g] = 0; }
@@ -362,6 +362,8 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     o.bias_mod = Nm; o.a_scalar = 1;   // theta offsets are not 16B aligned in general
   }
   // encoder: conv (F) + Layernorm + lrelu   (util/layers.py:47-66, model/vae.py:74-78)
+  // LN forward keeps (mean, rstd) per frame; backward recomputes xhat = (c - mean) * rstd from the raw conv
+  // output c_l (LN_BWD: `xhat` = c_l, r0 = mean) instead of storing a second activation-sized tensor
   std::vector<View> VA_e(nE);
   for (int e = 0; e < nE; e++) {
     const EncL& l = E[e]; char nm[32];
@@ -374,7 +376,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     o.bias[0] = B.th(poff(P_eb[e])); o.bias_mod = l.Co;
     snprintf(nm, sizeof nm, "ln_e%d", e);
     Op& q = B.op(OP_LN_FWD, PH_ENC, nm);
-    q.in = B.ws(b_ce[e]); q.xhat = B.ws(b_xe[e]); q.aout = B.ws(b_ae[e]); q.rstd = B.ws(b_re[e]);
+    q.in = B.ws(b_ce[e]); q.r0 = B.ws(b_me[e]); q.aout = B.ws(b_ae[e]); q.rstd = B.ws(b_re[e]);
     q.gamma = B.th(poff(P_es[e])); q.beta = B.th(poff(P_eo[e]));
     q.L = l.Ho * l.Co; q.Cn = l.Co; q.out_flen = ae_flen[e]; q.out_off = ae_off[e];
   }
@@ -411,7 +413,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
       o.bias[0] = B.th(poff(P_gb[g])); o.bias_mod = l.Co;
       snprintf(nm, sizeof nm, "ln_g%d", g);
       Op& q = B.op(OP_LN_FWD, PH_DEC, nm);
-      q.in = B.ws(b_cg[g]); q.xhat = B.ws(b_xg[g]); q.aout = B.ws(b_ag[g]); q.rstd = B.ws(b_rg[g]);
+      q.in = B.ws(b_cg[g]); q.r0 = B.ws(b_mg[g]); q.aout = B.ws(b_ag[g]); q.rstd = B.ws(b_rg[g]);
       q.gamma = B.th(poff(P_gs[g])); q.beta = B.th(poff(P_go[g]));
       q.L = l.Ho * l.Co; q.Cn = l.Co; q.out_flen = ag_flen[g]; q.out_off = ag_off[g];
     } else {
@@ -441,7 +443,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     const GenL& l = G[g]; char nm[32];
     snprintf(nm, sizeof nm, "ln_bwd_g%d", g);
     Op& q = B.op(OP_LN_BWD, PH_BWD, nm);
-    q.in = B.ws(b_dag[g]); q.xhat = B.ws(b_xg[g]); q.rstd = B.ws(b_rg[g]); q.aout = B.ws(b_dcg[g]);
+    q.in = B.ws(b_dag[g]); q.xhat = B.ws(b_cg[g]); q.r0 = B.ws(b_mg[g]); q.rstd = B.ws(b_rg[g]); q.aout = B.ws(b_dcg[g]);
     q.gamma = B.th(poff(P_gs[g])); q.beta = B.th(poff(P_go[g]));
     q.dgamma = B.gr(poff(P_gs[g])); q.dbeta = B.gr(poff(P_go[g])); q.dbias = B.gr(poff(P_gb[g]));
     q.L = l.Ho * l.Co; q.Cn = l.Co; q.out_flen = dcg_flen[g]; q.out_off = dcg_off[g];
@@ -478,7 +480,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     const EncL& l = E[e]; char nm[32];
     snprintf(nm, sizeof nm, "ln_bwd_e%d", e);
     Op& q = B.op(OP_LN_BWD, PH_BWD, nm);
-    q.in = B.ws(b_dae[e]); q.xhat = B.ws(b_xe[e]); q.rstd = B.ws(b_re[e]); q.aout = B.ws(b_dce[e]);
+    q.in = B.ws(b_dae[e]); q.xhat = B.ws(b_ce[e]); q.r0 = B.ws(b_me[e]); q.rstd = B.ws(b_re[e]); q.aout = B.ws(b_dce[e]);
     q.gamma = B.th(poff(P_es[e])); q.beta = B.th(poff(P_eo[e]));
     q.dgamma = B.gr(poff(P_es[e])); q.dbeta = B.gr(poff(P_eo[e])); q.dbias = B.gr(poff(P_eb[e]));
     q.L = l.Ho * l.Co; q.Cn = l.Co; q.out_flen = dce_flen[e]; q.out_off = dce_off[e];
