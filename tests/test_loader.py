@@ -78,3 +78,41 @@ def test_async_loader_matches_reference_semantics(tmp_path, arch):
     xq, yq = label.dequeue()
     assert torch.equal(xp, xq) and torch.equal(yp, yq)          # both handles share one queue; peek does not consume
     image.loader.close()
+
+
+@pytest.mark.gpu
+def test_main_and_convert_drivers_end_to_end(tmp_path, arch, monkeypatch):
+    """README command lines of the reference, on synthetic VCC2016-shaped data:
+    python main.py --model ConvVAE --trainer VAETrainer --architecture <json>   (main.py:45-74)
+    python convert.py --src SF1 --trg TM3 --model ConvVAE --checkpoint <ckpt>  (convert.py:66-116)"""
+    import json
+    import main as main_driver
+    import convert as convert_driver
+    monkeypatch.chdir(tmp_path)
+    rs = np.random.RandomState(0)
+    (tmp_path / "etc").mkdir()
+    xmin = (-3 - rs.rand(513)); xmax = (3 + rs.rand(513))
+    xmin.astype(np.float64).tofile("etc/xmin.npf"); xmax.astype(np.float64).tofile("etc/xmax.npf")   # float64 (SURVEY 5 dtype trap)
+    for spk in ("SF1", "TM3"):
+        np.array([5.0, 0.3], np.float32).tofile("etc/%s.npf" % spk)
+    for split in ("Training Set", "Testing Set"):
+        for si, spk in enumerate(("SF1", "TM3")):
+            d = tmp_path / "dataset" / "vcc2016" / "bin" / split / spk; d.mkdir(parents=True)
+            rec = rs.randn(90, analyzer.FEAT_DIM).astype(np.float32)
+            rec[:, 1026] = np.abs(rec[:, 1026]) * 100 + 80          # f0 > 1
+            rec[:, -1] = analyzer.SPEAKERS.index(spk)
+            rec.tofile(str(d / "100001.bin"))
+    a = dict(arch); a["training"] = dict(arch["training"], max_iter=12, batch_size=32)
+    json.dump(a, open("architecture-vae-test.json", "w"))
+    main_driver.main(["--model", "ConvVAE", "--trainer", "VAETrainer", "--architecture", "architecture-vae-test.json"])
+    runs = sorted((tmp_path / "logdir" / "train").iterdir())
+    assert len(runs) == 1 and (runs[0] / "architecture-vae-test.json").exists() and (runs[0] / "training.log").exists()
+    ckpt = runs[0] / "model.ckpt-12"
+    assert ckpt.exists()
+    convert_driver.main(["--src", "SF1", "--trg", "TM3", "--model", "ConvVAE", "--checkpoint", str(ckpt)])
+    outs = list((tmp_path / "logdir" / "output").glob("*/SF1-TM3-100001.bin"))
+    assert len(outs) == 1
+    conv = np.fromfile(str(outs[0]), np.float32).reshape(-1, analyzer.FEAT_DIM)
+    assert conv.shape == (90, analyzer.FEAT_DIM) and np.isfinite(conv).all() and (conv[:, -1] == analyzer.SPEAKERS.index("TM3")).all()
+    src = np.fromfile(str(tmp_path / 'dataset' / 'vcc2016' / 'bin' / 'Testing Set' / 'SF1' / '100001.bin'), np.float32).reshape(-1, analyzer.FEAT_DIM)
+    assert np.array_equal(conv[:, 513:1026], src[:, 513:1026]) and np.array_equal(conv[:, 1027], src[:, 1027])     # ap, en pass through

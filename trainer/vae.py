@@ -25,9 +25,13 @@ class VAETrainer(object):
         self.dirs = dirs
         self.machine = getattr(loss, 'machine', None)
         self.opt = self._optimize()
+        # training.log in the logdir (trainer/gan.py:20-23); an explicit handler, because
+        # logging.basicConfig is a no-op once the host application has configured logging
+        self.logger = logging.getLogger('vae_npvc_b200.training.%x' % id(self))
+        self.logger.setLevel(logging.INFO)
         if dirs and dirs.get('logdir'):
             os.makedirs(dirs['logdir'], exist_ok=True)
-            logging.basicConfig(level=logging.INFO, filename=os.path.join(dirs['logdir'], 'training.log'))
+            self.logger.addHandler(logging.FileHandler(os.path.join(dirs['logdir'], 'training.log')))
 
     # -- optimiser (trainer/vae.py:10-28) ---------------------------------------------------
     def _optimize(self):
@@ -69,7 +73,9 @@ class VAETrainer(object):
         msg += 'log P(x|z, y) = {:.3e} '.format(losses[2])
         msg += 'D_KL(z) = {:.3e} '.format(losses[1])
         print('\r{}'.format(msg), end='', flush=True)
-        logging.info(msg)
+        self.logger.info(msg)
+        for hd in self.logger.handlers:
+            hd.flush()
         return msg
 
     def save(self, path=None):
