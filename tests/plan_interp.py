@@ -9,7 +9,7 @@ import numpy as np
 SP_WS, SP_THETA, SP_GRAD, SP_AW, SP_ADW, SP_USER = 1, 2, 3, 4, 5, 6
 U_X, U_Y, U_EPS = 0, 1, 2
 (OP_GEMM, OP_WGRAD, OP_LN_FWD, OP_LN_BWD, OP_SAMPLE, OP_SAMPLE_BWD, OP_RECON, OP_SEGSUM, OP_COLSUM,
- OP_ZERO, OP_PACK, OP_UNPACK) = range(12)
+ OP_ZERO, OP_PACK, OP_UNPACK, OP_PACK16, OP_SPLIT) = range(14)
 PH_PACK, PH_ENC, PH_SAMPLE, PH_DEC, PH_LOSS, PH_BWD, PH_FINAL = range(7)
 
 LN_EPS = 1e-5
@@ -24,6 +24,7 @@ class Interp:
         self.theta = np.asarray(theta, np.float64)
         self.grad = np.zeros_like(self.theta)
         self.aw = np.zeros(plan["arena_w"], np.float64)
+        self.aw16 = np.zeros(plan["aw16_count"], np.float64)     # bf16 operand packs (values held as float64)
         self.adw = np.zeros(plan["arena_dw"], np.float64)
         self.tables = tables
         self.x = None if x is None else np.asarray(x, np.float64).reshape(-1)
@@ -54,6 +55,27 @@ class Interp:
     def buf(self, name):
         return self.bufs[self.buf_index[name]]
 
+    # ---- bf16 hi / lo planes (plan.h Buf::split): a split buffer holds hi + lo of the fp32 value ----
+    @staticmethod
+    def _bf16(a):
+        b = np.asarray(a, np.float32).view(np.uint32)
+        r = (b + np.uint32(0x7FFF) + ((b >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)
+        return r.view(np.float32).astype(np.float64)
+
+    @classmethod
+    def split(cls, a):
+        a32 = np.asarray(a, np.float64).astype(np.float32).astype(np.float64)
+        hi = cls._bf16(a32)
+        return hi, cls._bf16(a32 - hi)
+
+    @classmethod
+    def q(cls, a):
+        hi, lo = cls.split(a)
+        return hi + lo
+
+    def is_split(self, ref):
+        return ref["space"] == SP_WS and bool(self.plan["bufs"][ref["buf"]].get("split"))
+
     def view_index(self, v, rows, width):
         r = np.arange(rows)
         f, j = r // v["R"], r % v["R"]
@@ -77,6 +99,8 @@ class Interp:
         arr, base = self.flat(v["ref"])
         idx, valid, _ = self.view_index(v, rows, vals.shape[1])
         assert idx[valid].min() + base >= 0 and idx[valid].max() + base < arr.size
+        if self.is_split(v["ref"]):
+            vals = self.q(vals)
         arr[idx[valid] + base] = vals[valid]
 
     # ---- ops ----------------------------------------------------------------------------
@@ -88,20 +112,21 @@ class Interp:
                 continue
             getattr(self, "op_%d" % op["kind"])(op)
 
-    @staticmethod
-    def _tf32_rna(a):
-        # cvt.rna.tf32.f32: round the fp32 magnitude to 10 mantissa bits, ties away from zero
-        b = np.asarray(a, np.float32).view(np.uint32)
-        return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
-
-    def op_10(self, op):   # PACK
+    def op_10(self, op):   # PACK (fp32 operand packs)
         src = self.tables["pack_src"]
+        n = self.plan["aw16_off"]
+        self.aw[:n] = np.where(src >= 0, self.theta[np.maximum(src, 0)], 0.0)
+
+    def op_12(self, op):   # PACK16 (bf16 hi / lo operand packs of the tensor path)
+        src = self.tables["pack16_src"]
         mode = np.where(src >= 0, src >> 29, 0)
         val = np.where(src >= 0, self.theta[np.maximum(src, 0) & ((1 << 29) - 1)], 0.0)
-        v32 = val.astype(np.float32)
-        hi = self._tf32_rna(v32)
-        lo = self._tf32_rna(v32 - hi)
-        self.aw[:] = np.where(mode == 1, hi, np.where(mode == 2, lo, val))
+        hi, lo = self.split(val)
+        self.aw16[:] = np.where(mode == 1, hi, np.where(mode == 2, lo, 0.0))
+
+    def op_13(self, op):   # SPLIT: fp32 rows -> planes
+        L, n = op["i0"], self.n
+        self.flat(op["r1"])[0][:n * L] = self.q(self.flat(op["r0"])[0][:n * L])
 
     def op_11(self, op):   # UNPACK
         ptr, idx = self.tables["unpack_ptr"], self.tables["unpack_idx"]
@@ -115,13 +140,16 @@ class Interp:
         rows, K, N = self._rows(op), op["K"], op["N"]
         A = self.gather(op["A"], rows, K)
         if op.get("umma"):
-            # tensor-core path: K-major [N, Kpad] tf32 hi + lo packs (3xTF32 ~ fp32 product)
+            # tensor-core path, bf16x3: A planes x K-major [N, kpad] bf16 hi / lo packs, the lo.lo term dropped
             kp = op["kpad"]
-            Bm = (self.aw[op["bu_hi"]:op["bu_hi"] + N * kp] + self.aw[op["bu_lo"]:op["bu_lo"] + N * kp]).reshape(N, kp)[:, :K].T
+            Bh = self.aw16[op["bu_hi"]:op["bu_hi"] + N * kp].reshape(N, kp)[:, :K].T
+            Bl = self.aw16[op["bu_lo"]:op["bu_lo"] + N * kp].reshape(N, kp)[:, :K].T
+            Ah, Al = self.split(A)
+            Cv = Ah @ Bh + (Al @ Bh + Ah @ Bl)
         else:
             barr, boff = self.flat(op["B"])
             Bm = barr[boff:boff + K * op["ldb"]].reshape(K, op["ldb"])[:, :N]
-        Cv = A @ Bm
+            Cv = A @ Bm
         cols = np.arange(N) % op["bias_mod"]
         for key in ("bias0", "bias1", "bias2"):
             if op[key]["space"]:
@@ -140,7 +168,12 @@ class Interp:
         D = self.gather(op["C"], rows, N)
         arr, off = self.flat(op["B"])
         out = arr[off:off + K * op["ldb"]].reshape(K, op["ldb"])
-        out[:, :N] += A.T @ D
+        if op.get("umma"):
+            Ah, Al = self.split(A)
+            Dh, Dl = self.split(D)
+            out[:, :N] += Ah.T @ Dh + (Al.T @ Dh + Ah.T @ Dl)
+        else:
+            out[:, :N] += A.T @ D
 
     def op_2(self, op):    # LN_FWD
         L, Cn, n = op["L"], op["Cn"], self.n
@@ -158,7 +191,7 @@ class Interp:
         self.flat(op["rstd"])[0][:n] = rs[:, 0]
         out = self.flat(op["aout"])[0].reshape(n, op["out_flen"])
         out[:] = 0.0
-        out[:, op["out_off"]:op["out_off"] + L] = a
+        out[:, op["out_off"]:op["out_off"] + L] = self.q(a) if self.is_split(op["aout"]) else a
 
     def op_3(self, op):    # LN_BWD
         L, Cn, n = op["L"], op["Cn"], self.n
@@ -177,7 +210,7 @@ class Interp:
         dc = rs * (dxh - s1 - xh * s2)
         out = self.flat(op["aout"])[0].reshape(n, op["out_flen"])
         out[:] = 0.0
-        out[:, op["out_off"]:op["out_off"] + L] = dc
+        out[:, op["out_off"]:op["out_off"] + L] = self.q(dc) if self.is_split(op["aout"]) else dc
         for key, val in (("dgamma", du * xh), ("dbeta", du), ("dbias", dc)):
             arr, off = self.flat(op[key])
             arr[off:off + Cn] += val.reshape(n, L // Cn, Cn).sum((0, 1))
@@ -202,7 +235,7 @@ class Interp:
         dmu = dz + mu / ONE_PLUS_EPS * inv_n
         dlv = dz * self.eps * 0.5 * np.sqrt(np.exp(lv)) + 0.5 * (np.exp(lv) / ONE_PLUS_EPS - 1.0) * inv_n
         dhz = np.concatenate([dmu, dlv], 1)
-        self.flat(op["r2"])[0][:n * 2 * z] = dhz.reshape(-1)
+        self.flat(op["r2"])[0][:n * 2 * z] = (self.q(dhz) if self.is_split(op["r2"]) else dhz).reshape(-1)
         arr, off = self.flat(op["r3"])
         arr[off:off + 2 * z] += dhz.sum(0)
 
@@ -216,7 +249,7 @@ class Interp:
         g = d / ONE_PLUS_EPS / self.n_total
         dxh = self.flat(op["r2"])[0].reshape(n, ld)
         dxh[:] = 0.0
-        dxh[:, :H] = g
+        dxh[:, :H] = self.q(g) if self.is_split(op["r2"]) else g
         arr, off = self.flat(op["r3"])
         arr[off] += g.sum()
 

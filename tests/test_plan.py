@@ -44,12 +44,12 @@ def test_param_table_matches_reference_variable_order(arch):
 @pytest.mark.parametrize("n,umma", [(1, 0), (3, 0), (3, 1)])
 def test_plan_matches_oracle(arch, n, umma, monkeypatch):
     """umma=0: CUDA-core plan, exact in fp64.  umma=1: the tcgen05 routing with tf32 hi+lo operand
-    packs (hi + lo reproduces the fp32 weight to ~2^-22, so fp64 agreement drops to ~1e-6)."""
+    planes and packs (bf16x3: hi.hi + hi.lo + lo.hi, ~2^-17 per product, so fp64 agreement drops to ~1e-5)."""
     monkeypatch.setenv("NPVC_UMMA", str(umma))
-    tol_out, tol_g = (1e-12, 1e-9) if not umma else (1e-5, 1e-5)
+    tol_out, tol_g = (1e-12, 1e-9) if not umma else (3e-5, 5e-5)
     h = lib.Handle(arch)
     plan = h.plan()
-    tables = {k: h.plan_table(k) for k in ("pack_src", "unpack_ptr", "unpack_idx")}
+    tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx")}
     P = R.init_params(arch, 0)
     x, y, eps = R.make_inputs(arch, n)
     out = PI.Interp(plan, tables, R.flatten_params(arch, P, np.float64), n, x, y, eps).loss_fwd_bwd()
@@ -58,7 +58,7 @@ def test_plan_matches_oracle(arch, n, umma, monkeypatch):
     for k in ("mu", "lv", "z", "xh"):
         assert rel(out[k], ref[k]) < tol_out, k
     for k in ("D_KL", "logP", "G"):
-        assert rel(out[k], ref[k]) < 1e-6, k
+        assert rel(out[k], ref[k]) < (1e-6 if not umma else 1e-5), k
     gref = R.flatten_params(arch, ref["grads"], np.float64)
     for t in h.param_table():
         sl = slice(t["offset"], t["offset"] + t["size"])
@@ -117,11 +117,11 @@ def test_no_gpu_fails_loudly(arch):
 def test_alternative_architectures(alt_arch, umma, monkeypatch):
     """Generic plan: other kernel sizes / strides / asymmetric pads / padded channel counts."""
     monkeypatch.setenv("NPVC_UMMA", str(umma))
-    tol = 1e-10 if not umma else 1e-5
+    tol = 1e-10 if not umma else 5e-5          # bf16x3 planes: ~2^-17 per product, amplified by Layernorm over few elements
     from oracle import convvae_loops as L
     h = lib.Handle(alt_arch)
     plan = h.plan()
-    tables = {k: h.plan_table(k) for k in ("pack_src", "unpack_ptr", "unpack_idx")}
+    tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx")}
     P = R.init_params(alt_arch, 0)
     x, y, eps = R.make_inputs(alt_arch, 3)
     ref = R.forward(alt_arch, P, x, y, eps, with_grads=True)

@@ -17,7 +17,7 @@ P = R.init_params(arch, 0)
 theta64 = R.flatten_params(arch, P, np.float64)
 x, y, eps = R.make_inputs(arch, n)
 plan = eng.handle.plan()
-tables = {k: eng.handle.plan_table(k) for k in ("pack_src", "unpack_ptr", "unpack_idx")}
+tables = {k: eng.handle.plan_table(k) for k in ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx")}
 it = PI.Interp(plan, tables, theta64.astype(np.float32).astype(np.float64), n, x.astype(np.float32), y, eps.astype(np.float32))
 ref = it.loss_fwd_bwd()
 dev = eng.device
@@ -31,11 +31,22 @@ def rel(a, b):
     b = np.nan_to_num(b); a = np.nan_to_num(a)
     return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
 aw = eng.debug_buffer("arena_w", n).cpu().numpy()
-print("%-12s rel %.3e" % ("arena_w", rel(aw, it.aw)))
+n32 = plan["aw16_off"]
+print("%-12s rel %.3e" % ("arena_w", rel(aw[:n32], it.aw[:n32])))
+def bf16_to_f64(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+if plan["aw16_count"]:
+    a16 = bf16_to_f64(aw[n32:].view(np.uint16)[:plan["aw16_count"]])
+    print("%-12s rel %.3e" % ("arena16", rel(a16, it.aw16)))
 for b in plan["bufs"]:
     if b["name"] == "acc": continue
-    g = eng.debug_buffer(b["name"], n).cpu().numpy().astype(np.float64)
+    g = eng.debug_buffer(b["name"], n).cpu().numpy()
     r = it.bufs[it.buf_index[b["name"]]]
+    if b.get("split"):
+        pf = b["per_frame"]
+        u = g.view(np.uint16).reshape(-1, 2 * pf)
+        g = (bf16_to_f64(u[:, :pf]) + bf16_to_f64(u[:, pf:])).reshape(-1)
+    g = g.astype(np.float64)
     print("%-12s rel %.3e   |ref| %.3e" % (b["name"], rel(g, r), np.nanmax(np.abs(r))))
 gg = grad.cpu().numpy().astype(np.float64)
 for t in eng.table:

@@ -26,6 +26,7 @@ struct npvc_handle {
   Plan plan;
   int64_t max_chunk = 16384;
   int32_t* d_pack_src = nullptr;
+  int32_t* d_pack16_src = nullptr;
   int32_t* d_unpack_ptr = nullptr;
   int32_t* d_unpack_idx = nullptr;
   bool tables_on_device = false;
@@ -35,7 +36,7 @@ struct npvc_handle {
   bool use_umma = true;
   std::string umma_allow;            // debug: comma-separated op names allowed on the tensor path ("" = all)
   PFN_tmapEncodeTiled encode = nullptr;
-  struct TMaps { const void* a; const void* b; long long frames; int bn; CUtensorMap tA, tBh, tBl; };
+  struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile; CUtensorMap tAh, tAl, tBh, tBl; };
   std::map<int, TMaps> tmaps;        // per-op tensor-map cache
   int64_t umma_launches = 0;
   bool profiling = false;
@@ -75,6 +76,7 @@ float* resolve(const Ctx& c, const Ref& r) {
 }
 DView dview(const Ctx& c, const View& v) {
   DView d; d.p = resolve(c, v.ref); d.fs = v.fs; d.R = v.R; d.rs = v.rs; d.off = v.off; d.flen = v.flen; d.pred = v.pred;
+  d.split = v.split;
   return d;
 }
 bool view_vec_ok(const DView& d) {
@@ -138,99 +140,128 @@ int pick_bn(int N, int* n_tiles) {
   *n_tiles = best_t; return best_bn;
 }
 
+// rows of a view -> tiles of whole (frame, row-group) TMA boxes, <= row_target (<= 128) rows each
+RowTiling make_tiling(int R, long long frames, int row_target) {
+  RowTiling t;
+  t.Rb = umma_row_tile(R); t.Ra = R / t.Rb;
+  if (t.Ra == 1) { t.FB = row_target / t.Rb; if (t.FB < 1) t.FB = 1; t.Ab = 1; }
+  else { t.FB = 1; t.Ab = row_target / t.Rb; if (t.Ab < 1) t.Ab = 1; if (t.Ab > t.Ra) t.Ab = t.Ra; }
+  t.TA = (t.Ra + t.Ab - 1) / t.Ab;
+  t.rows_tile = t.Rb * t.Ab * t.FB;
+  t.frames = frames; t.m_tiles = ((frames + t.FB - 1) / t.FB) * t.TA;
+  return t;
+}
+
+// 4-D tensor maps (k, row-in-group, row-group, frame) over the hi / lo planes of a split view
+int make_view_maps(npvc_handle* h, const Ctx& c, const View& v, int extent, const RowTiling& rt, int box_inner, int sw_bytes,
+                   CUtensorMap* hi, CUtensorMap* lo, const std::string& name) {
+  uint16_t* base = reinterpret_cast<uint16_t*>(resolve(c, v.ref)) + v.off;
+  const cuuint64_t fsb = (cuuint64_t)v.fs * 4;                     // frame stride in bytes (2 planes of fs bf16)
+  cuuint64_t gd[4] = {(cuuint64_t)extent, (cuuint64_t)rt.Rb, (cuuint64_t)rt.Ra, (cuuint64_t)rt.frames};
+  cuuint64_t gs[3] = {v.R == 1 ? fsb : (cuuint64_t)v.rs * 2, rt.Ra == 1 ? fsb : (cuuint64_t)rt.Rb * v.rs * 2, fsb};
+  cuuint32_t bx[4] = {(cuuint32_t)box_inner, (cuuint32_t)rt.Rb, (cuuint32_t)rt.Ab, (cuuint32_t)rt.FB};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = sw_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (sw_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  for (int w = 0; w < 2; w++) {
+    CUresult r = h->encode(w ? lo : hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base + (w ? v.fs : 0), gd, gs, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(view) failed for " + name + " code " + std::to_string((int)r));
+  }
+  return NPVC_OK;
+}
+
 int launch_umma(Ctx& c, const Op& o, int op_index) {
   npvc_handle* h = c.h; cudaStream_t st = c.st;
-  const int R = o.A.R;
-  const int RB = R, FB = (R == 1) ? 128 : 128 / R;
-  const long long frames = c.n;                       // rows = frames * R
+  const long long frames = c.n;
   int n_tiles = 1; const int BN = pick_bn(o.N, &n_tiles);
-  float* a_base = resolve(c, o.A.ref) + o.A.off;
-  float* b_hi = c.ws + o.bu_hi; float* b_lo = c.ws + o.bu_lo;
+  const RowTiling rt = make_tiling(o.A.R, frames, 128);
+  const void* a_base = resolve(c, o.A.ref);
+  uint16_t* arena16 = reinterpret_cast<uint16_t*>(c.ws + h->plan.aw16_off);
+  uint16_t* b_hi = arena16 + o.bu_hi; uint16_t* b_lo = arena16 + o.bu_lo;
   auto it = h->tmaps.find(op_index);
   if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != frames || it->second.bn != BN) {
-    npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = frames; tm.bn = BN;
-    cuuint64_t gdA[3] = {(cuuint64_t)o.K, (cuuint64_t)R, (cuuint64_t)frames};
-    cuuint64_t gsA[2] = {(cuuint64_t)((R == 1 ? o.A.fs : o.A.rs) * 4), (cuuint64_t)(o.A.fs * 4)};
-    cuuint32_t bxA[3] = {32, (cuuint32_t)RB, (cuuint32_t)FB};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = h->encode(&tm.tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a_base, gdA, gsA, bxA, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed for " + o.name + " code " + std::to_string((int)r));
+    npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile;
+    int rc = make_view_maps(h, c, o.A, o.K, rt, 64, 128, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
     cuuint64_t gdB[2] = {(cuuint64_t)o.kpad, (cuuint64_t)o.N};
-    cuuint64_t gsB[1] = {(cuuint64_t)o.kpad * 4};
-    cuuint32_t bxB[2] = {32, (cuuint32_t)BN};
+    cuuint64_t gsB[1] = {(cuuint64_t)o.kpad * 2};
+    cuuint32_t bxB[2] = {64, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
     for (int w = 0; w < 2; w++) {
-      r = h->encode(w ? &tm.tBl : &tm.tBh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w ? b_lo : b_hi, gdB, gsB, bxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CUresult r = h->encode(w ? &tm.tBl : &tm.tBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w ? b_lo : b_hi, gdB, gsB, bxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed for " + o.name + " code " + std::to_string((int)r));
     }
     h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
   }
-  UmmaFwdArgs pa; UmmaArgs& g = pa.g;
-  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + 31) / 32;
+  UmmaArgs g; memset(&g, 0, sizeof g);
+  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + 63) / 64; g.rt = rt; g.n_tiles = n_tiles;
   const int stage_bytes = 2 * 16384 + 2 * BN * 128;
-  pa.acc_sets = (4 * BN <= 512) ? 2 : 1;                            // double-buffered accumulators when TMEM allows
-  int tc = 32; while (tc < pa.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
-  int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 6) stages = 6; if (stages < 1) stages = 1;
-  g.stages = stages; g.rows_tile = RB * FB; g.FB = FB; g.rows = frames * R;
-  g.nblocks = 0; g.blocks_per_split = 0; g.out = nullptr; g.ld = 0; g.A = dview(c, o.A); g.D = g.A;
+  g.acc_sets = (4 * BN <= 512) ? 2 : 1;                            // double-buffered accumulators when TMEM allows
+  int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
+  int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 8) stages = 8; if (stages < 1) stages = 1;
+  g.stages = stages;
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
   g.table = resolve(c, o.table); g.labels = reinterpret_cast<const long long*>(c.y); g.table_ld = o.table_ld;
   if (g.table && !g.labels) return fail(NPVC_ERR_ARG, "labels (y) required");
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(umma_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (3 * stages + 5) + 32 + 1024;   // + bias_s[256]
-  pa.m_tiles = (int)((frames + FB - 1) / FB); pa.n_tiles = n_tiles;
-  long long total = (long long)pa.m_tiles * pa.n_tiles;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 5) + 32 + 1024;   // + bias_s[256]
+  long long total = rt.m_tiles * n_tiles;
   unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
-  umma_fwd_persistent_kernel<<<grid, 320, smem, st>>>(it->second.tA, it->second.tBh, it->second.tBl, pa);
+  umma_fwd_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
 
-// dB[K,N] += A_view^T . dC_view on the tensor cores: operands read straight from the activation /
-// gradient views by the producer warps (no packs, no TMA), 32-row reduction blocks split across
-// CTAs, partial tiles added with RED.ADD.
+// dB[K,N] += A_view^T . dC_view on the tensor cores: both operands are the TMA boxes of the split views,
+// consumed MN-major; the reduction over row tiles is split across CTAs, partial tiles added with RED.ADD.
 int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
-  (void)op_index;
   npvc_handle* h = c.h; cudaStream_t st = c.st;
-  // N tile: multiple of 32 (the producer's column-quad permutation needs BN/4 % 8 == 0)
-  int n_tiles = 1, BN;
-  if (o.N <= 256) BN = (o.N + 31) / 32 * 32;
+  const long long frames = c.n;
+  // N tile: 16 / 32 columns in one 32B / 64B-swizzled box, else 64-column boxes (128B swizzle)
+  int BN, n_tiles = 1, d_sw;
+  if (o.N <= 16) { BN = 16; d_sw = 32; }
+  else if (o.N <= 32) { BN = 32; d_sw = 64; }
   else {
-    long long best = -1; BN = 256; n_tiles = (o.N + 255) / 256;
-    for (int t = (o.N + 255) / 256; t <= (o.N + 255) / 256 + 6; t++) {
-      int bn = ((o.N + t - 1) / t + 31) / 32 * 32; if (bn > 256) continue;
-      long long cost = (long long)bn * t;
-      if (best < 0 || cost < best) { best = cost; BN = bn; n_tiles = t; }
+    d_sw = 128; BN = 64; long long best = -1;
+    for (int bn = 64; bn <= 256; bn += 64) {
+      int t = (o.N + bn - 1) / bn; long long cost = (long long)bn * t;
+      if (best < 0 || cost * 100 <= best * 103) { if (best < 0 || cost < best) best = cost; BN = bn; n_tiles = t; }
     }
   }
-  const int m_tiles = (o.K + 127) / 128;
-  UmmaArgs g;
-  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = 0;
-  const int stage_bytes = 2 * 16384 + 2 * BN * 128;
+  const int m_tiles_k = (o.K + 127) / 128;
+  // rows per stage: keep >= 3 stages in shared memory
+  const int per_row = 512 + 4 * BN;
+  int row_target = (220 * 1024 / 3 / per_row) / 16 * 16; if (row_target > 128) row_target = 128; if (row_target < 16) row_target = 16;
+  const RowTiling rt = make_tiling(o.A.R, frames, row_target);
+  const void* a_base = resolve(c, o.A.ref); const void* d_base = resolve(c, o.C.ref);
+  auto it = h->tmaps.find(op_index);
+  if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != d_base || it->second.frames != frames || it->second.bn != BN ||
+      it->second.rows_tile != rt.rows_tile) {
+    npvc_handle::TMaps tm; tm.a = a_base; tm.b = d_base; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile;
+    int rc = make_view_maps(h, c, o.A, o.K, rt, 64, 128, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
+    rc = make_view_maps(h, c, o.C, o.N, rt, d_sw / 2, d_sw, &tm.tBh, &tm.tBl, o.name); if (rc) return rc;
+    h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
+  }
+  UmmaArgs g; memset(&g, 0, sizeof g);
+  g.K = o.K; g.N = o.N; g.BN = BN; g.rt = rt; g.n_tiles = n_tiles; g.d_sw = d_sw;
+  g.rows_al = (rt.rows_tile + 15) / 16 * 16;
+  const int d_boxes = (BN + d_sw / 2 - 1) / (d_sw / 2);
+  const int d_region = (g.rows_al * d_sw + 1023) / 1024 * 1024;
+  const int stage_bytes = 2 * (2 * g.rows_al * 128) + 2 * d_boxes * d_region;
   int tc = 32; while (tc < 2 * BN) tc *= 2; g.tmem_cols = tc;
-  g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R;
-  g.nblocks = (g.rows + 31) / 32;
-  long long tiles = (long long)m_tiles * n_tiles;
-  // wide N tiles: software-pipelined producer (130 registers x 320 threads -> 1 CTA / SM);
-  // BN <= 128: single register set, 2 CTAs / SM (smem / TMEM permitting)
-  const bool pipelined = BN > 128;
-  int ctas = pipelined ? 1 : 2;
-  if (ctas > 512 / tc) ctas = 512 / tc; if (ctas < 1) ctas = 1;
-  while (ctas > 1 && (225 * 1024) / ctas - 2048 < stage_bytes) ctas--;
-  int stages = ((225 * 1024) / ctas - 2048) / stage_bytes; if (stages > 4) stages = 4; if (stages < 1) stages = 1;
-  g.stages = stages; g.rows_tile = 32; g.FB = 0;
-  g.C = dview(c, o.C); g.bias0 = g.bias1 = g.bias2 = nullptr; g.bias_mod = 1; g.table = nullptr; g.labels = nullptr; g.table_ld = 0;
-  g.A = dview(c, o.A); g.D = dview(c, o.C);
-  // split the reduction so that tiles * S fills whole waves of (ctas * SMs) resident CTAs, each
-  // CTA keeping >= 16 reduction blocks (amortises its 128 x BN atomic epilogue)
-  long long maxS = g.nblocks / 16; if (maxS < 1) maxS = 1; if (maxS > 4096) maxS = 4096;
-  const double slots = (double)ctas * h->sm_count;
+  int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 8) stages = 8; if (stages < 1) stages = 1;
+  g.stages = stages;
+  // split the reduction so that tiles * S fills whole waves of SMs, each CTA keeping enough row
+  // tiles to amortise its 128 x BN atomic epilogue
+  const long long tiles = (long long)m_tiles_k * n_tiles;
+  const long long min_tiles = (512 + rt.rows_tile - 1) / rt.rows_tile;     // >= 512 rows per CTA
+  long long maxS = rt.m_tiles / min_tiles; if (maxS < 1) maxS = 1; if (maxS > 4096) maxS = 4096;
+  const double slots = (double)h->sm_count;
   long long S = 1; double best = 1e30;
   for (long long cand = 1; cand <= maxS; cand++) {
     double waves = (double)(tiles * cand) / slots;
@@ -238,19 +269,17 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
     double cost = (waves < 1.0 ? 1.0 / waves : std::ceil(waves) / waves) + 0.01 * waves;
     if (cost < best - 1e-9) { best = cost; S = cand; }
   }
-  g.blocks_per_split = (g.nblocks + S - 1) / S;
-  S = (g.nblocks + g.blocks_per_split - 1) / g.blocks_per_split;
+  g.tiles_per_split = (rt.m_tiles + S - 1) / S;
+  S = (rt.m_tiles + g.tiles_per_split - 1) / g.tiles_per_split;
   g.out = resolve(c, o.B); g.ld = o.ldb;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(umma_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(umma_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 1) + 16;
-  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)S);
-  if (pipelined) umma_wgrad_kernel<1><<<grid, 320, smem, st>>>(g);   // 8 producer warps
-  else umma_wgrad_kernel<2><<<grid, 320, smem, st>>>(g);
+  dim3 grid((unsigned)m_tiles_k, (unsigned)n_tiles, (unsigned)S);
+  umma_wgrad_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -265,9 +294,22 @@ int run_op(Ctx& c, const Op& o, int op_index) {
   npvc_handle* h = c.h; const Plan& p = h->plan; cudaStream_t st = c.st;
   switch (o.kind) {
     case OP_PACK: {
-      long long n = p.arena_w;
+      long long n = p.aw16_off;
       pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.theta, h->d_pack_src, c.ws, n);
       h->launches++; break;
+    }
+    case OP_PACK16: {
+      long long n = p.aw16_count;
+      if (n > 0) {
+        pack16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.theta, h->d_pack16_src, reinterpret_cast<uint16_t*>(c.ws + p.aw16_off), n);
+        h->launches++;
+      }
+      break;
+    }
+    case OP_SPLIT: {
+      long long n4 = c.n * (o.i0 / 4);
+      if (n4 > 0) { split_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(resolve(c, o.r0), resolve(c, o.r1), o.i0, c.n); h->launches++; }
+      break;
     }
     case OP_UNPACK: {
       long long n = p.n_params;
@@ -290,7 +332,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
             g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, kchunk);
         h->launches++; break;
       }
-      if (!g.table && !g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && !o.rows_fixed) {     // (independent of n: per-frame results must not depend on the batch size)
+      if (!g.table && !g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && !o.rows_fixed && !g.A.split && !g.C.split) {     // (independent of n: per-frame results must not depend on the batch size)
         RowGemmArgs rg; rg.A = g.A; rg.K = o.K; rg.B = g.B; rg.ldb = o.ldb; rg.N = o.N; rg.C = g.C; rg.rows = g.rows;
         rg.bias0 = g.bias0; rg.bias_mod = o.bias_mod;
         const bool sc = !view_vec_ok(g.A) || (o.K % 4 != 0);
@@ -317,7 +359,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
         wgrad_tiny_kernel<8, 16><<<(unsigned)((g.rows + rpb - 1) / rpb), 256, 0, st>>>(g, rpb);
         h->launches++; break;
       }
-      if (o.K > 8 && o.K <= 48 && o.N <= 24 && o.K % 4 == 0 && o.N % 4 == 0 && view_vec_ok(g.A) && g.rows >= 4096) {
+      if (o.K > 8 && o.K <= 48 && o.N <= 24 && o.K % 4 == 0 && o.N % 4 == 0 && view_vec_ok(g.A) && g.rows >= 4096 && !g.A.split && !g.D.split) {
         const long long blocks = (long long)h->sm_count * 8;
         long long rpb = (g.rows + blocks - 1) / blocks; rpb = (rpb + 63) / 64 * 64;
         wgrad_small_kernel<48, 24><<<(unsigned)((g.rows + rpb - 1) / rpb), 192, 0, st>>>(g, rpb);
@@ -329,6 +371,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       LnFwdArgs g; g.in = resolve(c, o.in); g.mean = resolve(c, o.r0); g.aout = resolve(c, o.aout);
       g.rstd = resolve(c, o.rstd); g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta);
       g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
+      g.out_split = p.bufs[o.aout.buf].split;
       ln_fwd_kernel<<<(unsigned)c.n, 256, (size_t)o.L * sizeof(float), st>>>(g); h->launches++; break;
     }
     case OP_LN_BWD: {
@@ -336,6 +379,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta); g.dc = resolve(c, o.aout);
       g.dgamma = resolve(c, o.dgamma); g.dbeta = resolve(c, o.dbeta); g.dbias = resolve(c, o.dbias);
       g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
+      g.out_split = p.bufs[o.aout.buf].split;
       long long blocks = (long long)h->sm_count * 8; if (blocks > c.n) blocks = c.n;
       ln_bwd_kernel<<<(unsigned)blocks, 256, (size_t)(2 * o.L + 3 * o.Cn) * sizeof(float), st>>>(g); h->launches++; break;
     }
@@ -349,7 +393,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
     case OP_SAMPLE_BWD: {
       const int z = o.i0, fpb = 16;
       sample_bwd_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 2 * z, 0, st>>>(
-          resolve(c, o.r0), c.eps, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), z, c.n, fpb, 1.0f / (float)c.n_total);
+          resolve(c, o.r0), c.eps, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), z, c.n, fpb, 1.0f / (float)c.n_total, p.bufs[o.r2.buf].split);
       h->launches++; break;
     }
     case OP_RECON: {
@@ -357,21 +401,21 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       const int wpb = 8;
       recon_kernel<<<(unsigned)((c.n + wpb - 1) / wpb), wpb * 32, 0, st>>>(
           c.x, resolve(c, o.r1), c.grad ? resolve(c, o.r2) : nullptr, c.grad ? resolve(c, o.r3) : nullptr, acc,
-          o.i0, o.i1, 1, c.n, 1.0f / (float)c.n_total);
+          o.i0, o.i1, 1, c.n, 1.0f / (float)c.n_total, p.bufs[o.r2.buf].split);
       h->launches++; break;
     }
     case OP_SEGSUM: {
       if (o.i1 <= 16) {
         const int fpb = 256;
         dim3 grid((unsigned)((o.i0 + 127) / 128), (unsigned)((c.n + fpb - 1) / fpb));
-        segsum_kernel<<<grid, 128, 0, st>>>(resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb);
+        segsum_kernel<<<grid, 128, 0, st>>>(resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb, p.bufs[o.r0.buf].split);
       } else {
         const int fpb = 64; size_t sm = (size_t)o.i0 * o.i1 * sizeof(float);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(segsum_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
         if (sm > 200 * 1024) return fail(NPVC_ERR_ARG, "y_dim * merge width too large for segsum shared memory");
         segsum_smem_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 256, sm, st>>>(
-            resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb);
+            resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb, p.bufs[o.r0.buf].split);
       }
       h->launches++; break;
     }
@@ -425,7 +469,9 @@ int ensure_tables(npvc_handle* h) {
       return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver (needed by the tcgen05 path)");
     h->encode = (PFN_tmapEncodeTiled)fn;
   }
-  CUDA_TRY(cudaMalloc(&h->d_pack_src, p.pack_src.size() * 4));
+  CUDA_TRY(cudaMalloc(&h->d_pack_src, (p.pack_src.size() + 1) * 4));
+  CUDA_TRY(cudaMalloc(&h->d_pack16_src, (p.pack16_src.size() + 1) * 4));
+  CUDA_TRY(cudaMemcpy(h->d_pack16_src, p.pack16_src.data(), p.pack16_src.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&h->d_unpack_ptr, p.unpack_ptr.size() * 4));
   CUDA_TRY(cudaMalloc(&h->d_unpack_idx, (p.unpack_idx.size() + 1) * 4));
   CUDA_TRY(cudaMemcpy(h->d_pack_src, p.pack_src.data(), p.pack_src.size() * 4, cudaMemcpyHostToDevice));
@@ -472,7 +518,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
 
 void npvc_destroy(npvc_handle* h) {
   if (!h) return;
-  if (h->tables_on_device) { cudaFree(h->d_pack_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); }
+  if (h->tables_on_device) { cudaFree(h->d_pack_src); cudaFree(h->d_pack16_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); }
   delete h;
 }
 
@@ -507,6 +553,7 @@ int64_t npvc_plan_table(const npvc_handle* h, const char* name, int32_t* out, in
   if (!strcmp(name, "pack_src")) v = &h->plan.pack_src;
   else if (!strcmp(name, "unpack_ptr")) v = &h->plan.unpack_ptr;
   else if (!strcmp(name, "unpack_idx")) v = &h->plan.unpack_idx;
+  else if (!strcmp(name, "pack16_src")) v = &h->plan.pack16_src;
   if (!v) return -1;
   if (out) { int64_t n = (int64_t)v->size() < max ? (int64_t)v->size() : max; memcpy(out, v->data(), n * 4); }
   return (int64_t)v->size();

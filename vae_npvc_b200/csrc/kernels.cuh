@@ -1,6 +1,7 @@
 // CUDA-core kernels of the ConvVAE hot path (sm_100a).  The tensor-core (tcgen05) GEMM lives in
 // umma_gemm.cuh; everything here is fp32 FFMA / bandwidth-shaped work.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -8,9 +9,51 @@ namespace npvc {
 
 // Strided row view (see plan.h): element (row, k) lives at
 //   p + (row / R) * fs + (row % R) * rs + off + k,  valid (when pred) iff 0 <= (row%R)*rs+off+k < flen
+// split != 0 (plan.h, Buf::split): the buffer holds bf16 hi / lo planes per frame -- element e of frame f
+// is  hi[f*2*fs + e] + lo[f*2*fs + fs + e]  (bf16 units from p), the tensor-core operand format.
 struct DView {
-  float* p; long long fs; int R, rs, off, flen, pred;
+  float* p; long long fs; int R, rs, off, flen, pred, split;
 };
+
+// ---- bf16 hi / lo planes ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t split_pack2(float a, float b, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// 4 consecutive elements (8-byte aligned) of a split frame: hi at `hi`, lo `lo_delta` bf16 further on
+__device__ __forceinline__ float4 split_ld4(const uint16_t* hi, long long lo_delta) {
+  const uint2 h = *reinterpret_cast<const uint2*>(hi), l = *reinterpret_cast<const uint2*>(hi + lo_delta);
+  float4 v;
+  v.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+  v.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+  v.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+  v.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+  return v;
+}
+__device__ __forceinline__ float split_ld1(const uint16_t* hi, long long lo_delta) {
+  return __uint_as_float((uint32_t)hi[0] << 16) + __uint_as_float((uint32_t)hi[lo_delta] << 16);
+}
+__device__ __forceinline__ void split_st4(uint16_t* hi, long long lo_delta, float4 v) {
+  uint2 h, l;
+  h.x = split_pack2(v.x, v.y, l.x); h.y = split_pack2(v.z, v.w, l.y);
+  *reinterpret_cast<uint2*>(hi) = h; *reinterpret_cast<uint2*>(hi + lo_delta) = l;
+}
+__device__ __forceinline__ void split_st1(uint16_t* hi, long long lo_delta, float v) {
+  uint32_t l; const uint32_t h = split_pack2(v, 0.f, l);
+  hi[0] = (uint16_t)(h & 0xffffu); hi[lo_delta] = (uint16_t)(l & 0xffffu);
+}
+// 4 consecutive elements of a view row starting at in-frame element index e (fp32 or split storage)
+__device__ __forceinline__ float4 view_ld4(const DView& v, long long f, int e) {
+  if (!v.split) return *reinterpret_cast<const float4*>(v.p + f * v.fs + e);
+  return split_ld4(reinterpret_cast<const uint16_t*>(v.p) + f * 2 * v.fs + e, v.fs);
+}
+__device__ __forceinline__ float view_ld1(const DView& v, long long f, int e) {
+  if (!v.split) return v.p[f * v.fs + e];
+  return split_ld1(reinterpret_cast<const uint16_t*>(v.p) + f * 2 * v.fs + e, v.fs);
+}
 
 __device__ __forceinline__ float lrelu_f(float x) { return fmaxf(x, 0.02f * x); }
 
@@ -40,15 +83,15 @@ __global__ void __launch_bounds__(256) gemm_view_kernel(GemmArgs g) {
 
   // A loader: thread -> rows (lrow, lrow+64), k-quad kq
   const int lrow = tid >> 2, kq = tid & 3;
-  const float* aptr[2]; int ainf[2];
+  const float* aptr[2]; int ainf[2]; long long afr[2];
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     long long r = m0 + lrow + 64 * h;
     if (r < g.rows) {
       long long f = r / g.A.R; int j = (int)(r - f * g.A.R);
-      ainf[h] = j * g.A.rs + g.A.off;
+      ainf[h] = j * g.A.rs + g.A.off; afr[h] = f;
       aptr[h] = g.A.p + f * g.A.fs + ainf[h];
-    } else { aptr[h] = nullptr; ainf[h] = 0; }
+    } else { aptr[h] = nullptr; ainf[h] = 0; afr[h] = 0; }
   }
   float4 ra[2]; float4 rb[NB4];
   auto load_tiles = [&](int k0) {
@@ -59,7 +102,7 @@ __global__ void __launch_bounds__(256) gemm_view_kernel(GemmArgs g) {
       if (aptr[h] != nullptr) {
         if (!ASCALAR) {
           if (k < g.K) {
-            v = *reinterpret_cast<const float4*>(aptr[h] + k);
+            v = view_ld4(g.A, afr[h], ainf[h] + k);
             if (k + 3 >= g.K) { if (k + 1 >= g.K) v.y = 0.f; if (k + 2 >= g.K) v.z = 0.f; v.w = 0.f; }
           }
         } else {
@@ -68,7 +111,7 @@ __global__ void __launch_bounds__(256) gemm_view_kernel(GemmArgs g) {
           for (int i = 0; i < 4; i++) {
             int kk = k + i; bool ok = kk < g.K;
             if (g.A.pred) { int q = ainf[h] + kk; ok = ok && q >= 0 && q < g.A.flen; }
-            t[i] = ok ? aptr[h][kk] : 0.f;
+            t[i] = ok ? view_ld1(g.A, afr[h], ainf[h] + kk) : 0.f;
           }
           v = make_float4(t[0], t[1], t[2], t[3]);
         }
@@ -169,7 +212,16 @@ __global__ void __launch_bounds__(256) gemm_view_kernel(GemmArgs g) {
       }
       bool full = (cbase + GW <= g.N);
       if (g.C.pred) full = full && (inf + cbase >= 0) && (inf + cbase + GW <= g.C.flen);
-      if (GW == 4 && full && ((reinterpret_cast<uintptr_t>(cp + cbase) & 15) == 0)) {
+      if (g.C.split) {
+        uint16_t* hp = reinterpret_cast<uint16_t*>(g.C.p) + f * 2 * g.C.fs + inf;
+#pragma unroll
+        for (int j2 = 0; j2 < GW; j2++) {
+          const int n = cbase + j2;
+          bool ok = n < g.N;
+          if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
+          if (ok) split_st1(hp + n, g.C.fs, v[j2]);
+        }
+      } else if (GW == 4 && full && ((reinterpret_cast<uintptr_t>(cp + cbase) & 15) == 0)) {
         *reinterpret_cast<float4*>(cp + cbase) = make_float4(v[0], v[1 % GW], v[2 % GW], v[3 % GW]);
       } else {
 #pragma unroll
@@ -216,16 +268,15 @@ __global__ void __launch_bounds__(256) wgrad_view_kernel(WgradArgs g) {
         if (r < rend && k < g.K) {
           long long f = r / g.A.R; int j = (int)(r - f * g.A.R);
           int inf = j * g.A.rs + g.A.off;
-          const float* ap = g.A.p + f * g.A.fs + inf;
           if (!ASCALAR) {
-            v = *reinterpret_cast<const float4*>(ap + k);
+            v = view_ld4(g.A, f, inf + k);
           } else {
             float t[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
               int kk = k + e; bool ok = kk < g.K;
               if (g.A.pred) { int qq = inf + kk; ok = ok && qq >= 0 && qq < g.A.flen; }
-              t[e] = ok ? ap[kk] : 0.f;
+              t[e] = ok ? view_ld1(g.A, f, inf + kk) : 0.f;
             }
             v = make_float4(t[0], t[1], t[2], t[3]);
           }
@@ -242,7 +293,7 @@ __global__ void __launch_bounds__(256) wgrad_view_kernel(WgradArgs g) {
         long long r = r0 + rr; int n = nt0 + q * 4;
         if (r < rend && n < g.N) {
           long long f = r / g.D.R; int j = (int)(r - f * g.D.R);
-          v = *reinterpret_cast<const float4*>(g.D.p + f * g.D.fs + j * g.D.rs + g.D.off + n);
+          v = view_ld4(g.D, f, j * g.D.rs + g.D.off + n);
         }
       }
       rd[it] = v;
@@ -463,12 +514,12 @@ __global__ void __launch_bounds__(256) wgrad_tiny_kernel(WgradArgs g, long long 
       x[k] = ok ? ap[k] : 0.f;
     }
     const long long fd = r / g.D.R; const int jd = (int)(r - fd * g.D.R);
-    const float* dp = g.D.p + fd * g.D.fs + jd * g.D.rs + g.D.off;
+    const int dinf = jd * g.D.rs + g.D.off;
     float d[NMAX];
 #pragma unroll
     for (int n4 = 0; n4 < NMAX / 4; n4++) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n4 * 4 < g.N) v = *reinterpret_cast<const float4*>(dp + n4 * 4);
+      if (n4 * 4 < g.N) v = view_ld4(g.D, fd, dinf + n4 * 4);
       d[n4 * 4] = v.x; d[n4 * 4 + 1] = v.y; d[n4 * 4 + 2] = v.z; d[n4 * 4 + 3] = v.w;
     }
 #pragma unroll
@@ -593,6 +644,7 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats *
 struct LnFwdArgs {
   const float* in; float* mean; float* aout; float* rstd; const float* gamma; const float* beta;
   int L, Cn, out_flen, out_off; long long frames;
+  int out_split;      // aout is a split (bf16 hi / lo) buffer
 };
 
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs g) {
@@ -618,6 +670,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs g) {
   const float rs = rsqrtf(var + NPVC_LN_EPS);
   if (threadIdx.x == 0) { g.rstd[f] = rs; g.mean[f] = mean; }
   float* ao = g.aout + f * g.out_flen;
+  uint16_t* ah = reinterpret_cast<uint16_t*>(g.aout) + f * 2 * g.out_flen;
   const int off4 = g.out_off >> 2, F4 = g.out_flen >> 2;
   for (int i = threadIdx.x; i < F4; i += blockDim.x) {
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -631,7 +684,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs g) {
       o.z = lrelu_f(fmaf(h.z, g.gamma[c + 2], g.beta[c + 2]));
       o.w = lrelu_f(fmaf(h.w, g.gamma[c + 3], g.beta[c + 3]));
     }
-    reinterpret_cast<float4*>(ao)[i] = o;
+    if (g.out_split) split_st4(ah + 4 * i, g.out_flen, o);
+    else reinterpret_cast<float4*>(ao)[i] = o;
   }
 }
 
@@ -643,6 +697,7 @@ struct LnBwdArgs {
   const float* dy; const float* cin; const float* mean; const float* rstd; const float* gamma; const float* beta;   // cin = raw conv output
   float* dc; float* dgamma; float* dbeta; float* dbias;
   int L, Cn, out_flen, out_off; long long frames;
+  int out_split;      // dc is a split (bf16 hi / lo) buffer
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
@@ -683,6 +738,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
     s1 = block_sum(s1, red) * invL;
     s2 = block_sum(s2, red) * invL;
     float4* dc4 = reinterpret_cast<float4*>(g.dc + f * g.out_flen);
+    uint16_t* dch = reinterpret_cast<uint16_t*>(g.dc) + f * 2 * g.out_flen;
     // pass 2 (smem -> global): dc = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), zero pads
     for (int i = threadIdx.x; i < F4; i += blockDim.x) {
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -698,7 +754,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
           atomicAdd(&chs[2 * g.Cn + c + 2], o.z); atomicAdd(&chs[2 * g.Cn + c + 3], o.w);
         }
       }
-      dc4[i] = o;
+      if (g.out_split) split_st4(dch + 4 * i, g.out_flen, o);
+      else dc4[i] = o;
     }
     __syncthreads();                               // smem frame buffers are reused by the next frame
   }
@@ -751,7 +808,7 @@ __global__ void sample_only_kernel(const float* mu, const float* lv, const float
 
 // dz, eps, (mu|lv) -> (dmu|dlv); column sums -> head-bias grads.  inv_n = 1 / (frames the means span)
 __global__ void sample_bwd_kernel(const float* dz, const float* eps, const float* hz, float* dhz, float* dbh,
-                                  int z, long long frames, int frames_per_block, float inv_n) {
+                                  int z, long long frames, int frames_per_block, float inv_n, int out_split) {
   const int col = threadIdx.x;
   const long long f0 = (long long)blockIdx.x * frames_per_block;
   float cs = 0.f;
@@ -767,7 +824,9 @@ __global__ void sample_bwd_kernel(const float* dz, const float* eps, const float
       float ev = expf(l);
       o = dz[f * z + d] * eps[f * z + d] * 0.5f * sqrtf(ev) + 0.5f * (ev / NPVC_ONE_PLUS_EPS - 1.0f) * inv_n;
     }
-    dhz[f * 2 * z + col] = o; cs += o;
+    if (out_split) split_st1(reinterpret_cast<uint16_t*>(dhz) + f * 4 * z + col, 2 * z, o);
+    else dhz[f * 2 * z + col] = o;
+    cs += o;
   }
   atomicAdd(&dbh[col], cs);
 }
@@ -776,7 +835,7 @@ __global__ void sample_bwd_kernel(const float* dz, const float* eps, const float
 // Gaussian log-density + d/dxh  (util/layers.py:159-167): one warp per frame
 // =============================================================================================
 __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float* dbias, double* acc_logp,
-                             int H, int ld, int Co, long long frames, float inv_n) {
+                             int H, int ld, int Co, long long frames, float inv_n, int out_split) {
   __shared__ float red[40];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long f = (long long)blockIdx.x * nw + w;
@@ -790,7 +849,10 @@ __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float*
         g = d / NPVC_ONE_PLUS_EPS * inv_n;
         db += g;
       }
-      if (dxh) dxh[f * ld + i] = g;
+      if (dxh) {
+        if (out_split) split_st1(reinterpret_cast<uint16_t*>(dxh) + f * 2 * ld + i, ld, g);
+        else dxh[f * ld + i] = g;
+      }
     }
   }
   float t = block_sum(lp, red);
@@ -805,7 +867,7 @@ __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float*
 // per-speaker row sums: out[y[f], :] += in[f, :]   (dynamic smem: ny * N floats)
 // =============================================================================================
 __global__ void __launch_bounds__(128) segsum_kernel(const float* in, const long long* y, float* out, int N, int ny,
-                                                     long long frames, int frames_per_block) {
+                                                     long long frames, int frames_per_block, int in_split) {
   // thread = column, block = (column tile, frame chunk); the speaker id is uniform across the block,
   // so "acc[s] += v" is a uniform switch over register accumulators: no shared memory, ny atomics per thread
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -816,7 +878,8 @@ __global__ void __launch_bounds__(128) segsum_kernel(const float* in, const long
   for (int i = 0; i < frames_per_block; i++) {
     const long long f = f0 + i; if (f >= frames) break;
     const int s = (int)y[f];
-    const float v = (col < N) ? in[f * N + col] : 0.f;
+    float v = 0.f;
+    if (col < N) v = in_split ? split_ld1(reinterpret_cast<const uint16_t*>(in) + f * 2 * N + col, N) : in[f * N + col];
     switch (s) {
       case 0: acc[0] += v; break; case 1: acc[1] += v; break; case 2: acc[2] += v; break; case 3: acc[3] += v; break;
       case 4: acc[4] += v; break; case 5: acc[5] += v; break; case 6: acc[6] += v; break; case 7: acc[7] += v; break;
@@ -833,7 +896,7 @@ __global__ void __launch_bounds__(128) segsum_kernel(const float* in, const long
 
 // fallback for more than 16 classes: shared-memory accumulators (dynamic smem: ny * N floats)
 __global__ void segsum_smem_kernel(const float* in, const long long* y, float* out, int N, int ny,
-                                   long long frames, int frames_per_block) {
+                                   long long frames, int frames_per_block, int in_split) {
   extern __shared__ float acc[];
   for (int i = threadIdx.x; i < ny * N; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
@@ -842,7 +905,8 @@ __global__ void segsum_smem_kernel(const float* in, const long long* y, float* o
     long long f = f0 + i; if (f >= frames) break;
     int s = (int)y[f];
     if (s < 0 || s >= ny) continue;
-    for (int c = threadIdx.x; c < N; c += blockDim.x) acc[s * N + c] += in[f * N + c];
+    for (int c = threadIdx.x; c < N; c += blockDim.x)
+      acc[s * N + c] += in_split ? split_ld1(reinterpret_cast<const uint16_t*>(in) + f * 2 * N + c, N) : in[f * N + c];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ny * N; i += blockDim.x) { float v = acc[i]; if (v != 0.f) atomicAdd(&out[i], v); }
@@ -861,20 +925,32 @@ __global__ void colsum_kernel(const float* in, float* out, int N, int rows) {
 // =============================================================================================
 __global__ void pack_kernel(const float* theta, const int* src, float* arena, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int s = src[i]; arena[i] = (s >= 0) ? theta[s] : 0.f; }
+}
+
+// bf16 operand packs of the tensor path: src = theta index | mode << 29 (plan.h), mode 1 = bf16(v),
+// mode 2 = bf16(v - bf16(v))
+__global__ void pack16_kernel(const float* theta, const int* src, uint16_t* arena16, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    int s = src[i];
-    float v = 0.f;
+    const int s = src[i];
+    uint16_t o = 0;
     if (s >= 0) {
-      const int mode = s >> 29;                     // plan.h: PACK_MODE_SHIFT
-      v = theta[s & ((1 << 29) - 1)];
-      if (mode) {                                   // tf32 split for the tcgen05 operands
-        uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-        if (mode == 1) v = __uint_as_float(h);
-        else { uint32_t l; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h))); v = __uint_as_float(l); }
-      }
+      const float v = theta[s & ((1 << 29) - 1)];
+      uint32_t lo; const uint32_t hi = split_pack2(v, 0.f, lo);
+      o = (uint16_t)(((s >> 29) == 1 ? hi : lo) & 0xffffu);
     }
-    arena[i] = v;
+    arena16[i] = o;
   }
+}
+
+// fp32 rows [frames, L] -> split planes (L % 4 == 0)
+__global__ void split_rows_kernel(const float* in, float* out, int L, long long frames) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // float4 index
+  const int L4 = L >> 2;
+  if (i >= frames * L4) return;
+  const long long f = i / L4; const int q = (int)(i - f * L4);
+  split_st4(reinterpret_cast<uint16_t*>(out) + f * 2 * L + 4 * q, L, reinterpret_cast<const float4*>(in)[i]);
 }
 
 __global__ void unpack_kernel(const float* adw, const int* ptr, const int* idx, float* grad, long long n) {

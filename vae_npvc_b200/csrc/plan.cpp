@@ -31,8 +31,8 @@ struct Builder {
     p.n_params += q.size; p.params.push_back(q);
     return (int)p.params.size() - 1;
   }
-  int add_buf(const std::string& name, int64_t per_frame, int64_t fixed, bool train_only) {
-    Buf b; b.name = name; b.per_frame = per_frame; b.fixed = fixed; b.train_only = train_only;
+  int add_buf(const std::string& name, int64_t per_frame, int64_t fixed, bool train_only, bool split = false) {
+    Buf b; b.name = name; b.per_frame = per_frame; b.fixed = fixed; b.train_only = train_only; b.split = split;
     p.bufs.push_back(b); return (int)p.bufs.size() - 1;
   }
   // arena allocation (128-byte aligned); fills pack_src with -1
@@ -46,8 +46,10 @@ struct Builder {
   static Ref aw(int64_t off) { Ref r; r.space = SP_AW; r.off = off; return r; }
   static Ref adw(int64_t off) { Ref r; r.space = SP_ADW; r.off = off; return r; }
   static Ref user(int slot) { Ref r; r.space = SP_USER; r.buf = slot; return r; }
-  static View view(Ref ref, int R, int64_t fs, int rs, int off, int flen, int pred = 0) {
-    View v; v.ref = ref; v.R = R; v.fs = fs; v.rs = rs; v.off = off; v.flen = flen; v.pred = pred; return v;
+  View view(Ref ref, int R, int64_t fs, int rs, int off, int flen, int pred = 0) const {
+    View v; v.ref = ref; v.R = R; v.fs = fs; v.rs = rs; v.off = off; v.flen = flen; v.pred = pred;
+    if (ref.space == SP_WS) v.split = p.bufs[ref.buf].split;     // split buffers: fs == per_frame (whole frames)
+    return v;
   }
   Op& op(int kind, int phase, const std::string& name) {
     Op o; o.kind = kind; o.phase = phase; o.name = name; p.ops.push_back(o); return p.ops.back();
@@ -61,10 +63,18 @@ void json_view(std::ostringstream& o, const char* key, const View& v) {
   o << "\"" << key << "\":{";
   json_ref(o, "ref", v.ref);
   o << ",\"R\":" << v.R << ",\"fs\":" << v.fs << ",\"rs\":" << v.rs << ",\"off\":" << v.off
-    << ",\"flen\":" << v.flen << ",\"pred\":" << v.pred << "}";
+    << ",\"flen\":" << v.flen << ",\"pred\":" << v.pred << ",\"split\":" << v.split << "}";
 }
 
 }  // namespace
+
+// Rows of one frame that go into one <= 128-row tensor-core tile: R itself when it fits (the tile then
+// holds floor(128/R) whole frames), else the largest divisor of R in [16, 128] (a frame spans R/Rb tiles).
+int umma_row_tile(int R) {
+  if (R <= 128) return R;
+  for (int d = 128; d >= 16; d--) if (R % d == 0) return d;
+  return 0;
+}
 
 int64_t Plan::buf_offset(int b, int64_t chunk, bool train) const {
   int64_t off = rup64(arena_w, 64);
@@ -83,6 +93,11 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   p.arch = a;
   Builder B(p);
   char msg[256];
+  // tensor path: activations that feed GEMMs are bf16 hi / lo planes -> 16-byte alignment is 8 elements.
+  // AL pads the channel counts this builder is free to pad; layers whose own channel counts are only
+  // multiples of 4 stay on the CUDA-core kernels (which read the planes with 8-byte loads).
+  const int AL = use_umma ? 8 : 4;
+  const bool SPLIT = use_umma;
 
   // ---------------------------------------------------------------- validate (model/vae.py:37-39)
   if (a.n_enc < 1 || a.n_enc > NPVC_MAX_LAYERS || a.n_gen < 1 || a.n_gen > NPVC_MAX_LAYERS)
@@ -110,7 +125,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   std::vector<GenL> G; {
     int H = a.gen_h, ci = a.gen_c;
     for (int i = 0; i < a.n_gen; i++) {
-      GenL l; l.Ci = ci; l.Cip = rup(ci, 4); l.Co = a.gen_out[i]; l.k = a.gen_kernel[i]; l.s = a.gen_stride[i];
+      GenL l; l.Ci = ci; l.Cip = (i == 0) ? rup(ci, AL) : ci; /* only gen_c is ours to pad */ l.Co = a.gen_out[i]; l.k = a.gen_kernel[i]; l.s = a.gen_stride[i];
       l.Hi = H; l.Ho = H * l.s;
       if (l.k < l.s || l.s < 1) return "generator kernel < stride is not supported";
       l.cl = std::max(l.k - l.s, 0) / 2;
@@ -131,10 +146,10 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     }
   }
   const int z = a.z_dim, nE = a.n_enc, nG = a.n_gen;
-  const int gh = a.gen_h, gc = a.gen_c, gcp = rup(gc, 4), Nm = gh * gcp;
+  const int gh = a.gen_h, gc = a.gen_c, gcp = rup(gc, AL), Nm = gh * gcp;
   const int flat = E.back().Ho * E.back().Co;
   p.out_dim = a.in_h;
-  const int xhld = rup(a.in_h, 4);
+  const int xhld = rup(a.in_h, AL);
 
   // ---------------------------------------------------------------- parameter table
   // tf.trainable_variables() creation order: model/vae.py:20-24 (y_emb), then loss() ->
@@ -320,20 +335,22 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     snprintf(nm, sizeof nm, "mean_e%d", e); b_me[e] = B.add_buf(nm, 1, 0, false);
     if (e < nE - 1) { ae_flen[e] = (E[e + 1].pl + l.Ho + E[e + 1].pr) * l.Co; ae_off[e] = E[e + 1].pl * l.Co; }
     else { ae_flen[e] = L; ae_off[e] = 0; }
-    snprintf(nm, sizeof nm, "a_e%d", e);    b_ae[e] = B.add_buf(nm, ae_flen[e], 0, false);
+    snprintf(nm, sizeof nm, "a_e%d", e);    b_ae[e] = B.add_buf(nm, ae_flen[e], 0, false, SPLIT);
     snprintf(nm, sizeof nm, "rstd_e%d", e); b_re[e] = B.add_buf(nm, 1, 0, false);
     dce_flen[e] = (e_pf[e] + l.Ho + e_pb[e]) * l.Co; dce_off[e] = e_pf[e] * l.Co;
-    snprintf(nm, sizeof nm, "dc_e%d", e);   b_dce[e] = B.add_buf(nm, dce_flen[e], 0, true);
+    snprintf(nm, sizeof nm, "dc_e%d", e);   b_dce[e] = B.add_buf(nm, dce_flen[e], 0, true, SPLIT);
     snprintf(nm, sizeof nm, "da_e%d", e);   b_dae[e] = B.add_buf(nm, L, 0, true);
   }
   p.buf_hz = B.add_buf("hz", 2 * z, 0, false);
   p.buf_mu = B.add_buf("mu", z, 0, false);
   p.buf_lv = B.add_buf("lv", z, 0, false);
   p.buf_z = B.add_buf("z", z, 0, false);
-  int b_dz = B.add_buf("dz", z, 0, true), b_dhz = B.add_buf("dhz", 2 * z, 0, true);
+  // zs: the sampled z (or the caller's z in decode()) as operand planes for the merge GEMM
+  int b_zs = SPLIT ? B.add_buf("zs", z, 0, false, true) : p.buf_z;
+  int b_dz = B.add_buf("dz", z, 0, true), b_dhz = B.add_buf("dhz", 2 * z, 0, true, SPLIT);
   const int hm_flen = (-G[0].lo + gh + G[0].hi) * gcp, hm_off = -G[0].lo * gcp;
-  int b_hm = B.add_buf("hm", hm_flen, 0, false);
-  int b_dhm = B.add_buf("dhm", Nm, 0, true);
+  int b_hm = B.add_buf("hm", hm_flen, 0, false, SPLIT);
+  int b_dhm = B.add_buf("dhm", Nm, 0, true, SPLIT);
   std::vector<int> b_cg(nG, -1), b_mg(nG, -1), b_ag(nG, -1), b_rg(nG, -1), b_dcg(nG, -1), b_dag(nG, -1);
   std::vector<int> ag_flen(nG), ag_off(nG), dcg_flen(nG), dcg_off(nG);
   for (int g = 0; g < nG - 1; g++) {
@@ -343,17 +360,18 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     const GenL& nx = G[g + 1];
     if (!nx.dense) { ag_flen[g] = (-nx.lo + l.Ho + nx.hi) * l.Co; ag_off[g] = -nx.lo * l.Co; }
     else { ag_flen[g] = L; ag_off[g] = 0; }
-    snprintf(nm, sizeof nm, "a_g%d", g);    b_ag[g] = B.add_buf(nm, ag_flen[g], 0, false);
+    snprintf(nm, sizeof nm, "a_g%d", g);    b_ag[g] = B.add_buf(nm, ag_flen[g], 0, false, SPLIT);
     snprintf(nm, sizeof nm, "rstd_g%d", g); b_rg[g] = B.add_buf(nm, 1, 0, false);
     dcg_flen[g] = (l.cl + l.Ho + (l.k - l.s - l.cl)) * l.Co; dcg_off[g] = l.cl * l.Co;
-    snprintf(nm, sizeof nm, "dc_g%d", g);   b_dcg[g] = B.add_buf(nm, dcg_flen[g], 0, true);
+    snprintf(nm, sizeof nm, "dc_g%d", g);   b_dcg[g] = B.add_buf(nm, dcg_flen[g], 0, true, SPLIT);
     snprintf(nm, sizeof nm, "da_g%d", g);   b_dag[g] = B.add_buf(nm, L, 0, true);
   }
   p.buf_xh = B.add_buf("xh", a.in_h, 0, false);
-  int b_dxh = B.add_buf("dxh", xhld, 0, true);
+  int b_dxh = B.add_buf("dxh", xhld, 0, true, SPLIT);
 
   // ---------------------------------------------------------------- ops
   { Op& o = B.op(OP_PACK, PH_PACK, "pack"); o.count = p.arena_w; }
+  if (use_umma) B.op(OP_PACK16, PH_PACK, "pack16");
   {  // P[s,:] = emb[s,:] . BY + b1 + b2 + b3   (model/vae.py:51-61 with the y-branch hoisted per speaker)
     Op& o = B.op(OP_GEMM, PH_PACK, "ptab");
     o.rows_fixed = a.y_dim; o.A = B.view(B.th(poff(P_emb)), 1, z, 0, 0, z); o.K = z;
@@ -392,7 +410,8 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   }
   // generator  (model/vae.py:84-103)
   { Op& o = B.op(OP_ZERO, PH_DEC, "zero_hm"); o.r0 = B.ws(b_hm); o.count = hm_flen; o.per_frame_count = 1; }
-  View V_z = B.view(B.ws(p.buf_z), 1, z, 0, 0, z);
+  if (SPLIT) { Op& o = B.op(OP_SPLIT, PH_DEC, "split_z"); o.r0 = B.ws(p.buf_z); o.r1 = B.ws(b_zs); o.i0 = z; }
+  View V_z = B.view(B.ws(b_zs), 1, z, 0, 0, z);
   View V_hm_rows = B.view(B.ws(b_hm), 1, hm_flen, 0, hm_off, hm_flen);
   {
     Op& o = B.op(OP_GEMM, PH_DEC, "merge");
@@ -510,38 +529,45 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   }
 
   // ---------------------------------------------------------------- tcgen05 routing
-  // GEMM-shaped (F) ops go to the tensor cores: A by TMA from the strided view (whole frames per
-  // 128-row tile), B as K-major [N, Kpad] hi / lo packs derived from the CUDA-core pack.
+  // (F) ops: A = bf16 hi / lo planes read by TMA through the strided view (whole frames per <= 128-row
+  // tile), B = K-major [N, kpad] bf16 hi / lo packs.  (W) ops: both operands are the split views
+  // themselves (the same TMA boxes, consumed as MN-major operands).  bf16x3: hi.hi + hi.lo + lo.hi.
+  p.aw16_off = p.arena_w;
   if (use_umma) {
     if (p.n_params > PACK_INDEX_MASK) return "too many parameters for the pack index encoding";
+    auto view_ok = [&](const View& v) {
+      return v.split && !v.pred && v.off >= 0 && v.off % 8 == 0 && v.rs % 8 == 0 && v.fs % 8 == 0 && umma_row_tile(v.R) > 0;
+    };
+    auto a16_alloc = [&](int64_t n) {
+      int64_t off = p.aw16_count; p.aw16_count = rup64(off + n, 64);
+      p.pack16_src.resize(p.aw16_count, -1); return off;
+    };
     for (Op& o : p.ops) {
+      if (o.rows_fixed || o.a_scalar) continue;
       if (o.kind == OP_WGRAD) {
-        // (W) form on the tensor cores: operands come straight from the activation / gradient views
-        if (o.rows_fixed || o.K < 64 || o.N < 32 || o.C.pred || o.A.pred) continue;     // tiny K/N (E0, G2): CUDA-core wgrads measured faster
-        // producers read 4x4 patches with 16-byte loads
-        if (o.A.fs % 4 || o.A.rs % 4 || o.A.off % 4 || o.C.fs % 4 || o.C.rs % 4 || o.C.off % 4) continue;
+        if (!view_ok(o.A) || !view_ok(o.C) || o.A.R != o.C.R || o.K < 8 || o.N < 8) continue;
         o.umma = 1;
         continue;
       }
-      if (o.kind != OP_GEMM || o.rows_fixed || o.A.pred || o.a_scalar) continue;
-      if (o.A.R > 128 || o.K < 32 || o.N < 16) continue;
-      if (o.A.fs % 4 || o.A.rs % 4 || o.A.off % 4 || o.A.off < 0 || o.B.space != SP_AW) continue;
-      o.kpad = rup(o.K, 32);
+      if (o.kind != OP_GEMM || !view_ok(o.A) || o.K < 8 || o.N < 8 || o.B.space != SP_AW) continue;
+      o.kpad = rup(o.K, 8);
       const int64_t sz = (int64_t)o.N * o.kpad;
-      o.bu_hi = B.aw_alloc(sz); o.bu_lo = B.aw_alloc(sz);
+      o.bu_hi = a16_alloc(sz); o.bu_lo = a16_alloc(sz);
       for (int n = 0; n < o.N; n++) for (int k = 0; k < o.K; k++) {
         int32_t src = p.pack_src[o.B.off + (int64_t)k * o.ldb + n];
         if (src < 0) continue;
-        p.pack_src[o.bu_hi + (int64_t)n * o.kpad + k] = src | (1 << PACK_MODE_SHIFT);
-        p.pack_src[o.bu_lo + (int64_t)n * o.kpad + k] = src | (2 << PACK_MODE_SHIFT);
+        p.pack16_src[o.bu_hi + (int64_t)n * o.kpad + k] = src | (1 << PACK_MODE_SHIFT);
+        p.pack16_src[o.bu_lo + (int64_t)n * o.kpad + k] = src | (2 << PACK_MODE_SHIFT);
       }
       o.umma = 1;
     }
+    p.arena_w = rup64(p.aw16_off + (p.aw16_count + 1) / 2, 64);
   }
 
   // ---------------------------------------------------------------- JSON
   std::ostringstream js;
   js << "{\"n_params\":" << p.n_params << ",\"arena_w\":" << p.arena_w << ",\"arena_dw\":" << p.arena_dw
+     << ",\"aw16_off\":" << p.aw16_off << ",\"aw16_count\":" << p.aw16_count
      << ",\"z\":" << z << ",\"out_dim\":" << p.out_dim << ",\"xh_ld\":" << xhld << ",\"params\":[";
   for (size_t i = 0; i < p.params.size(); i++) {
     const Param& q = p.params[i];
@@ -553,7 +579,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   for (size_t i = 0; i < p.bufs.size(); i++) {
     const Buf& q = p.bufs[i];
     js << (i ? "," : "") << "{\"name\":\"" << q.name << "\",\"per_frame\":" << q.per_frame << ",\"fixed\":" << q.fixed
-       << ",\"train_only\":" << q.train_only << "}";
+       << ",\"train_only\":" << q.train_only << ",\"split\":" << q.split << "}";
   }
   js << "],\"ops\":[";
   for (size_t i = 0; i < p.ops.size(); i++) {

@@ -23,7 +23,9 @@ enum UserSlot { U_X = 0, U_Y = 1, U_EPS = 2 };
 enum Phase { PH_PACK = 0, PH_ENC = 1, PH_SAMPLE = 2, PH_DEC = 3, PH_LOSS = 4, PH_BWD = 5, PH_FINAL = 6 };
 enum OpKind {
   OP_GEMM = 0, OP_WGRAD = 1, OP_LN_FWD = 2, OP_LN_BWD = 3, OP_SAMPLE = 4, OP_SAMPLE_BWD = 5,
-  OP_RECON = 6, OP_SEGSUM = 7, OP_COLSUM = 8, OP_ZERO = 9, OP_PACK = 10, OP_UNPACK = 11
+  OP_RECON = 6, OP_SEGSUM = 7, OP_COLSUM = 8, OP_ZERO = 9, OP_PACK = 10, OP_UNPACK = 11,
+  OP_PACK16 = 12,   // theta -> bf16 hi / lo operand packs (tensor path)
+  OP_SPLIT = 13     // fp32 rows -> bf16 hi / lo planes (r0 -> r1, i0 floats per frame)
 };
 
 struct Ref {
@@ -40,6 +42,7 @@ struct View {
   int off = 0;         // in-frame offset of column 0 of row 0 (may be negative)
   int flen = 0;        // valid in-frame range [0, flen) (used when pred)
   int pred = 0;        // predicate every element on the in-frame range
+  int split = 0;       // the buffer holds bf16 hi / lo planes (see Buf::split); fs == the buffer's per_frame
 };
 
 struct Buf {
@@ -47,6 +50,10 @@ struct Buf {
   int64_t per_frame = 0;   // floats per frame
   int64_t fixed = 0;       // floats independent of n
   int train_only = 0;
+  // split != 0: a frame's `per_frame` floats are stored as two bf16 planes [hi: per_frame][lo: per_frame]
+  // with value = hi + lo (hi = bf16(v), lo = bf16(v - hi)): the tensor-core operand format.  The
+  // tensor path multiplies such operands as hi.hi + hi.lo + lo.hi in fp32 (bf16x3).
+  int split = 0;
 };
 
 struct Op {
@@ -60,7 +67,8 @@ struct Op {
   Ref table; int table_ld = 0;   // + labels (U_Y): C[r,:] += table[y[r], :]
   int64_t rows_fixed = 0;        // >0: row count independent of n (A is not per-frame)
   int a_scalar = 0;              // A needs the scalar (unaligned / predicated) loader
-  // tcgen05 path (OP_GEMM only): B as K-major [N, Kpad] tf32 hi / lo packs in arena_w
+  // tcgen05 path: OP_GEMM reads B as K-major [N, kpad] bf16 hi / lo packs (bf16-element offsets into the
+  // arena16 region); OP_WGRAD reads both operands straight from the split activation / gradient views
   int umma = 0; int64_t bu_hi = 0, bu_lo = 0; int kpad = 0;
   // LN_FWD / LN_BWD
   Ref in, xhat, aout, rstd, gamma, beta, dgamma, dbeta, dbias;
@@ -86,7 +94,10 @@ struct Plan {
   std::vector<Op> ops;
   int64_t arena_w = 0;       // floats: packed operand matrices (fwd part first)
   int64_t arena_dw = 0;      // floats: packed weight gradients (mirror of the fwd part; ws buffer "arena_dw")
-  std::vector<int32_t> pack_src;     // [arena_w]  theta index or -1
+  int64_t aw16_off = 0;      // float offset of the bf16 pack region inside arena_w
+  int64_t aw16_count = 0;    // bf16 elements in it
+  std::vector<int32_t> pack_src;     // [aw16_off]  theta index or -1 (fp32 packs)
+  std::vector<int32_t> pack16_src;   // [aw16_count] theta index | mode << 29, or -1
   std::vector<int32_t> unpack_ptr;   // [n_params+1] CSR over theta
   std::vector<int32_t> unpack_idx;   // positions in arena_dw
   int buf_z = -1, buf_mu = -1, buf_lv = -1, buf_xh = -1, buf_acc = -1, buf_hz = -1, buf_adw = -1, buf_dptab = -1;
@@ -97,12 +108,15 @@ struct Plan {
   int64_t buf_offset(int b, int64_t chunk, bool train) const;   // float offset inside ws
 };
 
-// pack_src entries: -1 = zero; else theta index | mode << 29 (0 copy, 1 tf32 hi, 2 tf32 lo of the residual)
+// pack16_src entries: -1 = zero; else theta index | mode << 29 (1 bf16 hi, 2 bf16 lo of the residual)
 constexpr int PACK_MODE_SHIFT = 29;
 constexpr int32_t PACK_INDEX_MASK = (1 << PACK_MODE_SHIFT) - 1;
 
 // Returns empty string on success, else an error message.  use_umma: route GEMM-shaped ops to the
-// tcgen05 kernel (adds their hi / lo operand packs).
+// tcgen05 kernels: their A operands become split (bf16 hi / lo) buffers, their B operands bf16 packs.
 std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma);
+
+// Rows of one frame per tensor-core tile (0: the view cannot be tiled); see plan.cpp.
+int umma_row_tile(int R);
 
 }  // namespace npvc
