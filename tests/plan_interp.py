@@ -8,8 +8,8 @@ import numpy as np
 
 SP_WS, SP_THETA, SP_GRAD, SP_AW, SP_ADW, SP_USER = 1, 2, 3, 4, 5, 6
 U_X, U_Y, U_EPS = 0, 1, 2
-(OP_GEMM, OP_WGRAD, OP_LN_FWD, OP_LN_BWD, OP_SAMPLE, OP_SAMPLE_BWD, OP_RECON, OP_SEGSUM, OP_COLSUM,
- OP_ZERO, OP_PACK, OP_UNPACK, OP_PACK16, OP_SPLIT) = range(14)
+(OP_GEMM, OP_WGRAD, OP_LN_FWD, OP_LN_BWD, OP_SAMPLE, OP_SAMPLE_BWD, OP_RECON, _UNUSED7, OP_COLSUM,
+ OP_ZERO, OP_PACK, OP_UNPACK, OP_PACK16, OP_ZCAT) = range(14)
 PH_PACK, PH_ENC, PH_SAMPLE, PH_DEC, PH_LOSS, PH_BWD, PH_FINAL = range(7)
 
 LN_EPS = 1e-5
@@ -119,14 +119,18 @@ class Interp:
 
     def op_12(self, op):   # PACK16 (bf16 hi / lo operand packs of the tensor path)
         src = self.tables["pack16_src"]
-        mode = np.where(src >= 0, src >> 29, 0)
-        val = np.where(src >= 0, self.theta[np.maximum(src, 0) & ((1 << 29) - 1)], 0.0)
-        hi, lo = self.split(val)
-        self.aw16[:] = np.where(mode == 1, hi, np.where(mode == 2, lo, 0.0))
+        idx = np.maximum(src, 0) & ((1 << 29) - 1)
+        from_arena, want_lo = (src & (1 << 29)) != 0, (src & (1 << 30)) != 0
+        val = np.where(from_arena, self.aw[np.minimum(idx, self.aw.size - 1)], self.theta[np.minimum(idx, self.theta.size - 1)])
+        hi, lo = self.split(np.where(src >= 0, val, 0.0))
+        self.aw16[:] = np.where(src >= 0, np.where(want_lo, lo, hi), 0.0)
 
-    def op_13(self, op):   # SPLIT: fp32 rows -> planes
-        L, n = op["i0"], self.n
-        self.flat(op["r1"])[0][:n * L] = self.q(self.flat(op["r0"])[0][:n * L])
+    def op_13(self, op):   # ZCAT: zs = [z | one-hot(y)]
+        zd, yp, n = op["i0"], op["i1"], self.n
+        z = self.flat(op["r0"])[0][:n * zd].reshape(n, zd)
+        oh = np.zeros((n, yp)); oh[np.arange(n), self.y] = 1.0
+        zs = np.concatenate([z, oh], 1)
+        self.flat(op["r1"])[0][:n * (zd + yp)] = (self.q(zs) if self.is_split(op["r1"]) else zs).reshape(-1)
 
     def op_11(self, op):   # UNPACK
         ptr, idx = self.tables["unpack_ptr"], self.tables["unpack_idx"]
@@ -155,11 +159,6 @@ class Interp:
             if op[key]["space"]:
                 arr, off = self.flat(op[key])
                 Cv = Cv + arr[off + cols][None, :]
-        if op["table"]["space"]:
-            arr, off = self.flat(op["table"])
-            tab = arr[off:].reshape(-1, op["table_ld"])
-            f = np.arange(rows) // op["C"]["R"]
-            Cv = Cv + tab[self.y[f]][:, :N]
         self.scatter(op["C"], rows, Cv)
 
     def op_1(self, op):    # WGRAD
@@ -253,16 +252,10 @@ class Interp:
         arr, off = self.flat(op["r3"])
         arr[off] += g.sum()
 
-    def op_7(self, op):    # SEGSUM
-        N, ny, n = op["i0"], op["i1"], self.n
-        src = self.flat(op["r0"])[0][:n * N].reshape(n, N)
-        out = self.flat(op["r1"])[0].reshape(ny, N)
-        out[np.isnan(out)] = 0.0
-        np.add.at(out, self.y, src)
-
     def op_8(self, op):    # COLSUM
         N, rows = op["i0"], op["i1"]
-        src = self.flat(op["r0"])[0].reshape(rows, N)
+        arr0, off0 = self.flat(op["r0"])
+        src = arr0[off0:off0 + rows * N].reshape(rows, N)
         arr, off = self.flat(op["r1"])
         arr[off:off + N] += src.sum(0)
 
@@ -273,8 +266,6 @@ class Interp:
     # ---- whole passes -------------------------------------------------------------------
     def loss_fwd_bwd(self, with_grad=True):
         self.buf("acc")[:] = 0.0
-        if with_grad:
-            self.buf("dptab")[:] = 0.0
         for ph in (PH_PACK, PH_ENC, PH_SAMPLE, PH_DEC, PH_LOSS):
             self.run_phase(ph)
         if with_grad:

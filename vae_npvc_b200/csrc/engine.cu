@@ -36,9 +36,10 @@ struct npvc_handle {
   bool use_umma = true;
   std::string umma_allow;            // debug: comma-separated op names allowed on the tensor path ("" = all)
   PFN_tmapEncodeTiled encode = nullptr;
-  struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile; CUtensorMap tAh, tAl, tBh, tBl; };
+  struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile, sw; CUtensorMap tAh, tAl, tBh, tBl; };
   std::map<int, TMaps> tmaps;        // per-op tensor-map cache
   int64_t umma_launches = 0;
+  int umma_min_stages = 0;           // NPVC_UMMA_MIN_STAGES (experiments): below this many 64-wide k-block stages use 32-wide ones (measured slower: more TMA row requests)
   bool profiling = false;
   struct Ev { int op; cudaEvent_t a, b; long long rows; };
   std::vector<Ev> events;
@@ -175,35 +176,39 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   const long long frames = c.n;
   int n_tiles = 1; const int BN = pick_bn(o.N, &n_tiles);
   const RowTiling rt = make_tiling(o.A.R, frames, 128);
+  // k-block: 64 bf16 (128-byte swizzled rows) when >= 4 such stages fit, else 32 (64-byte rows): the
+  // same bytes in flight at twice the pipeline granularity (wide N tiles are L2-latency-bound otherwise)
+  int sw = 128;
+  if ((225 * 1024 - 3072) / (2 * 128 * 128 + 2 * BN * 128) < h->umma_min_stages) sw = 64;
+  if (o.K <= 32) sw = 64;
+  const int bk = sw / 2;
   const void* a_base = resolve(c, o.A.ref);
   uint16_t* arena16 = reinterpret_cast<uint16_t*>(c.ws + h->plan.aw16_off);
   uint16_t* b_hi = arena16 + o.bu_hi; uint16_t* b_lo = arena16 + o.bu_lo;
   auto it = h->tmaps.find(op_index);
-  if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != frames || it->second.bn != BN) {
-    npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile;
-    int rc = make_view_maps(h, c, o.A, o.K, rt, 64, 128, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
+  if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != frames || it->second.bn != BN || it->second.sw != sw) {
+    npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = sw;
+    int rc = make_view_maps(h, c, o.A, o.K, rt, bk, sw, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
     cuuint64_t gdB[2] = {(cuuint64_t)o.kpad, (cuuint64_t)o.N};
     cuuint64_t gsB[1] = {(cuuint64_t)o.kpad * 2};
-    cuuint32_t bxB[2] = {64, (cuuint32_t)BN};
+    cuuint32_t bxB[2] = {(cuuint32_t)bk, (cuuint32_t)BN};
     cuuint32_t es[2] = {1, 1};
     for (int w = 0; w < 2; w++) {
       CUresult r = h->encode(w ? &tm.tBl : &tm.tBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w ? b_lo : b_hi, gdB, gsB, bxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed for " + o.name + " code " + std::to_string((int)r));
     }
     h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
   }
   UmmaArgs g; memset(&g, 0, sizeof g);
-  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + 63) / 64; g.rt = rt; g.n_tiles = n_tiles;
-  const int stage_bytes = 2 * 16384 + 2 * BN * 128;
+  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + bk - 1) / bk; g.rt = rt; g.n_tiles = n_tiles; g.sw = sw;
+  const int stage_bytes = 2 * 128 * sw + 2 * BN * sw;
   g.acc_sets = (4 * BN <= 512) ? 2 : 1;                            // double-buffered accumulators when TMEM allows
   int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
-  int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 8) stages = 8; if (stages < 1) stages = 1;
+  int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
   g.stages = stages;
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
-  g.table = resolve(c, o.table); g.labels = reinterpret_cast<const long long*>(c.y); g.table_ld = o.table_ld;
-  if (g.table && !g.labels) return fail(NPVC_ERR_ARG, "labels (y) required");
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -242,7 +247,7 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   auto it = h->tmaps.find(op_index);
   if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != d_base || it->second.frames != frames || it->second.bn != BN ||
       it->second.rows_tile != rt.rows_tile) {
-    npvc_handle::TMaps tm; tm.a = a_base; tm.b = d_base; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile;
+    npvc_handle::TMaps tm; tm.a = a_base; tm.b = d_base; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = 128;
     int rc = make_view_maps(h, c, o.A, o.K, rt, 64, 128, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
     rc = make_view_maps(h, c, o.C, o.N, rt, d_sw / 2, d_sw, &tm.tBh, &tm.tBl, o.name); if (rc) return rc;
     h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
@@ -301,14 +306,19 @@ int run_op(Ctx& c, const Op& o, int op_index) {
     case OP_PACK16: {
       long long n = p.aw16_count;
       if (n > 0) {
-        pack16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.theta, h->d_pack16_src, reinterpret_cast<uint16_t*>(c.ws + p.aw16_off), n);
+        pack16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.theta, c.ws, h->d_pack16_src, reinterpret_cast<uint16_t*>(c.ws + p.aw16_off), n);
         h->launches++;
       }
       break;
     }
-    case OP_SPLIT: {
-      long long n4 = c.n * (o.i0 / 4);
-      if (n4 > 0) { split_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(resolve(c, o.r0), resolve(c, o.r1), o.i0, c.n); h->launches++; }
+    case OP_ZCAT: {
+      if (!c.y) return fail(NPVC_ERR_ARG, "labels (y) required");
+      long long n4 = c.n * ((o.i0 + o.i1) / 4);
+      if (n4 > 0) {
+        zcat_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1),
+                                                                o.i0, o.i1, c.n, p.bufs[o.r1.buf].split);
+        h->launches++;
+      }
       break;
     }
     case OP_UNPACK: {
@@ -320,11 +330,9 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       GemmArgs g; g.A = dview(c, o.A); g.K = o.K; g.B = resolve(c, o.B); g.ldb = o.ldb; g.N = o.N; g.C = dview(c, o.C);
       g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R;
       g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
-      g.table = resolve(c, o.table); g.labels = reinterpret_cast<const long long*>(c.y); g.table_ld = o.table_ld;
       if (g.rows <= 0) break;
-      if (g.table && !g.labels) return fail(NPVC_ERR_ARG, "labels (y) required");
       if (umma_allowed(h, o)) { int rc = launch_umma(c, o, op_index); if (rc) return rc; break; }
-      if (o.rows_fixed && o.rows_fixed <= 16 && !g.bias0 && !g.table && o.C.ref.space == SP_GRAD && !g.A.pred && g.A.R == 1 && g.C.R == 1 && o.K >= 256) {
+      if (o.rows_fixed && o.rows_fixed <= 16 && !g.bias0 && o.C.ref.space == SP_GRAD && !g.A.pred && g.A.R == 1 && g.C.R == 1 && o.K >= 256) {
         // few-row GEMM accumulated into the (zero-initialised) gradient buffer
         const int kchunk = 128, ks = (o.K + kchunk - 1) / kchunk;
         dim3 grid((unsigned)((o.N + 127) / 128), (unsigned)ks);
@@ -332,7 +340,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
             g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, kchunk);
         h->launches++; break;
       }
-      if (!g.table && !g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && !o.rows_fixed && !g.A.split && !g.C.split) {     // (independent of n: per-frame results must not depend on the batch size)
+      if (!g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && !o.rows_fixed && !g.C.split && !(g.A.split && g.A.pred)) {     // (independent of n: per-frame results must not depend on the batch size)
         RowGemmArgs rg; rg.A = g.A; rg.K = o.K; rg.B = g.B; rg.ldb = o.ldb; rg.N = o.N; rg.C = g.C; rg.rows = g.rows;
         rg.bias0 = g.bias0; rg.bias_mod = o.bias_mod;
         const bool sc = !view_vec_ok(g.A) || (o.K % 4 != 0);
@@ -402,21 +410,6 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       recon_kernel<<<(unsigned)((c.n + wpb - 1) / wpb), wpb * 32, 0, st>>>(
           c.x, resolve(c, o.r1), c.grad ? resolve(c, o.r2) : nullptr, c.grad ? resolve(c, o.r3) : nullptr, acc,
           o.i0, o.i1, 1, c.n, 1.0f / (float)c.n_total, p.bufs[o.r2.buf].split);
-      h->launches++; break;
-    }
-    case OP_SEGSUM: {
-      if (o.i1 <= 16) {
-        const int fpb = 256;
-        dim3 grid((unsigned)((o.i0 + 127) / 128), (unsigned)((c.n + fpb - 1) / fpb));
-        segsum_kernel<<<grid, 128, 0, st>>>(resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb, p.bufs[o.r0.buf].split);
-      } else {
-        const int fpb = 64; size_t sm = (size_t)o.i0 * o.i1 * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(segsum_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-        if (sm > 200 * 1024) return fail(NPVC_ERR_ARG, "y_dim * merge width too large for segsum shared memory");
-        segsum_smem_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 256, sm, st>>>(
-            resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1), o.i0, o.i1, c.n, fpb, p.bufs[o.r0.buf].split);
-      }
       h->launches++; break;
     }
     case OP_COLSUM: {
@@ -506,6 +499,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   npvc_handle* h = new npvc_handle();
   const char* eu = getenv("NPVC_UMMA");            // "0" = CUDA-core GEMMs only (debug / A-B comparisons)
   h->use_umma = !(eu && eu[0] == '0');
+  if (const char* ms = getenv("NPVC_UMMA_MIN_STAGES")) h->umma_min_stages = atoi(ms);
   const char* ea = getenv("NPVC_UMMA_OPS");
   if (ea) h->umma_allow = ea;
   std::string err = build_plan(*arch, h->plan, h->use_umma);
@@ -660,7 +654,6 @@ int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, co
   if (d_grad) {
     CUDA_TRY(cudaMemsetAsync(d_grad, 0, (size_t)p.n_params * 4, st));
     CUDA_TRY(cudaMemsetAsync(ws + p.buf_offset(p.buf_adw, cap, true), 0, (size_t)p.arena_dw * 4, st));
-    CUDA_TRY(cudaMemsetAsync(ws + p.buf_offset(p.buf_dptab, cap, true), 0, (size_t)p.bufs[p.buf_dptab].fixed * 4, st));
   }
   if (repack) {
     Ctx c{h, ws, cap, true, d_theta, nullptr, nullptr, nullptr, nullptr, 0, n, st};

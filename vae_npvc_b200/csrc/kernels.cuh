@@ -63,12 +63,11 @@ __device__ __forceinline__ float lrelu_f(float x) { return fmaxf(x, 0.02f * x); 
 #define NPVC_LOG_2PI 1.8378770664093453f
 
 // =============================================================================================
-// (F) C[rows,N] = A_view[rows,K] . B[K,N] + bias + table[label]   -- 128 x BN tile, BK = 16
+// (F) C[rows,N] = A_view[rows,K] . B[K,N] + bias   -- 128 x BN tile, BK = 16
 // =============================================================================================
 struct GemmArgs {
   DView A; int K; const float* B; int ldb; int N; DView C; long long rows;
   const float* bias0; const float* bias1; const float* bias2; int bias_mod;
-  const float* table; const long long* labels; int table_ld;
 };
 
 template <int BN, bool ASCALAR>
@@ -190,7 +189,6 @@ __global__ void __launch_bounds__(256) gemm_view_kernel(GemmArgs g) {
     const long long f = r / g.C.R; const int j = (int)(r - f * g.C.R);
     const int inf = j * g.C.rs + g.C.off;
     float* cp = g.C.p + f * g.C.fs + inf;
-    const float* trow = g.table ? g.table + (long long)g.labels[f] * g.table_ld : nullptr;
     constexpr int NG = (TN == 8) ? 2 : 1;            // column groups
     constexpr int GW = (TN == 8) ? 4 : TN;           // group width
 #pragma unroll
@@ -206,7 +204,6 @@ __global__ void __launch_bounds__(256) gemm_view_kernel(GemmArgs g) {
           if (g.bias0) t += g.bias0[bi];
           if (g.bias1) t += g.bias1[bi];
           if (g.bias2) t += g.bias2[bi];
-          if (trow) t += trow[n];
         }
         v[j2] = t;
       }
@@ -407,7 +404,7 @@ __global__ void __launch_bounds__(256) rowgemm_kernel(RowGemmArgs g) {
 #pragma unroll
       for (int k4 = 0; k4 < KMAX / 4; k4++) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rok && k4 * 4 < g.K) v = *reinterpret_cast<const float4*>(ap + k4 * 4);
+        if (rok && k4 * 4 < g.K) v = view_ld4(g.A, f, inf + k4 * 4);
         x[q][k4 * 4 + 0] = v.x; x[q][k4 * 4 + 1] = v.y; x[q][k4 * 4 + 2] = v.z; x[q][k4 * 4 + 3] = v.w;
       }
     } else {
@@ -863,55 +860,6 @@ __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float*
   }
 }
 
-// =============================================================================================
-// per-speaker row sums: out[y[f], :] += in[f, :]   (dynamic smem: ny * N floats)
-// =============================================================================================
-__global__ void __launch_bounds__(128) segsum_kernel(const float* in, const long long* y, float* out, int N, int ny,
-                                                     long long frames, int frames_per_block, int in_split) {
-  // thread = column, block = (column tile, frame chunk); the speaker id is uniform across the block,
-  // so "acc[s] += v" is a uniform switch over register accumulators: no shared memory, ny atomics per thread
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const long long f0 = (long long)blockIdx.y * frames_per_block;
-  float acc[16];
-#pragma unroll
-  for (int s = 0; s < 16; s++) acc[s] = 0.f;
-  for (int i = 0; i < frames_per_block; i++) {
-    const long long f = f0 + i; if (f >= frames) break;
-    const int s = (int)y[f];
-    float v = 0.f;
-    if (col < N) v = in_split ? split_ld1(reinterpret_cast<const uint16_t*>(in) + f * 2 * N + col, N) : in[f * N + col];
-    switch (s) {
-      case 0: acc[0] += v; break; case 1: acc[1] += v; break; case 2: acc[2] += v; break; case 3: acc[3] += v; break;
-      case 4: acc[4] += v; break; case 5: acc[5] += v; break; case 6: acc[6] += v; break; case 7: acc[7] += v; break;
-      case 8: acc[8] += v; break; case 9: acc[9] += v; break; case 10: acc[10] += v; break; case 11: acc[11] += v; break;
-      case 12: acc[12] += v; break; case 13: acc[13] += v; break; case 14: acc[14] += v; break; case 15: acc[15] += v; break;
-      default: break;
-    }
-  }
-  if (col < N) {
-#pragma unroll
-    for (int s = 0; s < 16; s++) if (s < ny && acc[s] != 0.f) atomicAdd(&out[(long long)s * N + col], acc[s]);
-  }
-}
-
-// fallback for more than 16 classes: shared-memory accumulators (dynamic smem: ny * N floats)
-__global__ void segsum_smem_kernel(const float* in, const long long* y, float* out, int N, int ny,
-                                   long long frames, int frames_per_block, int in_split) {
-  extern __shared__ float acc[];
-  for (int i = threadIdx.x; i < ny * N; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
-  const long long f0 = (long long)blockIdx.x * frames_per_block;
-  for (int i = 0; i < frames_per_block; i++) {
-    long long f = f0 + i; if (f >= frames) break;
-    int s = (int)y[f];
-    if (s < 0 || s >= ny) continue;
-    for (int c = threadIdx.x; c < N; c += blockDim.x)
-      acc[s * N + c] += in_split ? split_ld1(reinterpret_cast<const uint16_t*>(in) + f * 2 * N + c, N) : in[f * N + c];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < ny * N; i += blockDim.x) { float v = acc[i]; if (v != 0.f) atomicAdd(&out[i], v); }
-}
-
 __global__ void colsum_kernel(const float* in, float* out, int N, int rows) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
@@ -928,29 +876,39 @@ __global__ void pack_kernel(const float* theta, const int* src, float* arena, lo
   if (i < n) { const int s = src[i]; arena[i] = (s >= 0) ? theta[s] : 0.f; }
 }
 
-// bf16 operand packs of the tensor path: src = theta index | mode << 29 (plan.h), mode 1 = bf16(v),
-// mode 2 = bf16(v - bf16(v))
-__global__ void pack16_kernel(const float* theta, const int* src, uint16_t* arena16, long long n) {
+// bf16 operand packs of the tensor path (plan.h): src = index | flags; bit 29: the source is the fp32 pack
+// arena[index] instead of theta[index]; bit 30: store bf16(v - bf16(v)) instead of bf16(v)
+__global__ void pack16_kernel(const float* theta, const float* arena, const int* src, uint16_t* arena16, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const int s = src[i];
     uint16_t o = 0;
     if (s >= 0) {
-      const float v = theta[s & ((1 << 29) - 1)];
+      const int idx = s & ((1 << 29) - 1);
+      const float v = (s & (1 << 29)) ? arena[idx] : theta[idx];
       uint32_t lo; const uint32_t hi = split_pack2(v, 0.f, lo);
-      o = (uint16_t)(((s >> 29) == 1 ? hi : lo) & 0xffffu);
+      o = (uint16_t)(((s & (1 << 30)) ? lo : hi) & 0xffffu);
     }
     arena16[i] = o;
   }
 }
 
-// fp32 rows [frames, L] -> split planes (L % 4 == 0)
-__global__ void split_rows_kernel(const float* in, float* out, int L, long long frames) {
+// zs[f] = [z[f] (zd floats) | one-hot(y[f]) (yp floats)], fp32 or split planes (zd, yp multiples of 4):
+// the merge GEMM's A operand (model/vae.py:64-70,89-90 -- embedding lookup folded into the GEMM)
+__global__ void zcat_kernel(const float* z, const long long* y, float* out, int zd, int yp, long long frames, int out_split) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // float4 index
-  const int L4 = L >> 2;
-  if (i >= frames * L4) return;
-  const long long f = i / L4; const int q = (int)(i - f * L4);
-  split_st4(reinterpret_cast<uint16_t*>(out) + f * 2 * L + 4 * q, L, reinterpret_cast<const float4*>(in)[i]);
+  const int W4 = (zd + yp) >> 2;
+  if (i >= frames * W4) return;
+  const long long f = i / W4; const int q = (int)(i - f * W4);
+  float4 v;
+  if (4 * q < zd) v = reinterpret_cast<const float4*>(z + f * zd)[q];
+  else {
+    const int s = (int)y[f] - (4 * q - zd);
+    v = make_float4(s == 0 ? 1.f : 0.f, s == 1 ? 1.f : 0.f, s == 2 ? 1.f : 0.f, s == 3 ? 1.f : 0.f);
+  }
+  const int W = zd + yp;
+  if (out_split) split_st4(reinterpret_cast<uint16_t*>(out) + f * 2 * W + 4 * q, W, v);
+  else reinterpret_cast<float4*>(out + f * W)[q] = v;
 }
 
 __global__ void unpack_kernel(const float* adw, const int* ptr, const int* idx, float* grad, long long n) {

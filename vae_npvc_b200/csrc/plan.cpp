@@ -216,9 +216,13 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   int64_t A_bhb = B.aw_alloc(2 * z);
   for (int hd = 0; hd < 2; hd++) for (int d = 0; d < z; d++) p.pack_src[A_bhb + hd * z + d] = (int32_t)(poff(P_db[hd]) + d);
   // merge: BZ/BY[d, (h,c')] = W[d, c*gh + h] (reshape to [-1, c, h, w], model/vae.py:94), c' padded to 4
+  // The z-branch operand carries ypad extra rows: row z + s holds the per-speaker table P[s,:] (written by the
+  // "ptab" GEMM at pack time), multiplied by one-hot(y) columns appended to z -- the speaker term rides
+  // in the merge GEMM itself, and its weight-gradient rows ARE the per-speaker sums of the merge gradient.
+  const int ypad = rup(a.y_dim, AL), zk = z + ypad;
   int64_t A_bz[2], A_bm[3];
   for (int w = 0; w < 2; w++) {
-    A_bz[w] = B.aw_alloc((int64_t)z * Nm);
+    A_bz[w] = B.aw_alloc((int64_t)(w == 0 ? zk : z) * Nm);
     for (int d = 0; d < z; d++) for (int h = 0; h < gh; h++) for (int c = 0; c < gc; c++)
       p.pack_src[A_bz[w] + (int64_t)d * Nm + h * gcp + c] = (int32_t)(poff(P_fw[w]) + (int64_t)d * gh * gc + c * gh + h);
   }
@@ -321,12 +325,9 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
 
   // ---------------------------------------------------------------- buffers
   p.buf_acc = B.add_buf("acc", 0, 8, false);                    // 2 doubles: sum KL, sum logP (+pad)
-  int b_ptab = B.add_buf("ptab", 0, (int64_t)a.y_dim * Nm, false);
-  // acc and ptab come first so that theta-derived state (arena_w, ptab) sits at the same offsets in
+  // acc comes first so that theta-derived state (arena_w) sits at the same offsets in
   // the inference and training layouts
   p.buf_adw = B.add_buf("arena_dw", 0, p.arena_dw, true);
-  int b_dptab = B.add_buf("dptab", 0, (int64_t)a.y_dim * Nm, true);
-  p.buf_dptab = b_dptab;
   std::vector<int> b_ce(nE), b_me(nE), b_ae(nE), b_re(nE), b_dce(nE), b_dae(nE);
   std::vector<int> ae_flen(nE), ae_off(nE), dce_flen(nE), dce_off(nE);
   for (int e = 0; e < nE; e++) {
@@ -346,7 +347,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   p.buf_lv = B.add_buf("lv", z, 0, false);
   p.buf_z = B.add_buf("z", z, 0, false);
   // zs: the sampled z (or the caller's z in decode()) as operand planes for the merge GEMM
-  int b_zs = SPLIT ? B.add_buf("zs", z, 0, false, true) : p.buf_z;
+  int b_zs = B.add_buf("zs", zk, 0, false, SPLIT);
   int b_dz = B.add_buf("dz", z, 0, true), b_dhz = B.add_buf("dhz", 2 * z, 0, true, SPLIT);
   const int hm_flen = (-G[0].lo + gh + G[0].hi) * gcp, hm_off = -G[0].lo * gcp;
   int b_hm = B.add_buf("hm", hm_flen, 0, false, SPLIT);
@@ -371,14 +372,15 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
 
   // ---------------------------------------------------------------- ops
   { Op& o = B.op(OP_PACK, PH_PACK, "pack"); o.count = p.arena_w; }
-  if (use_umma) B.op(OP_PACK16, PH_PACK, "pack16");
+
   {  // P[s,:] = emb[s,:] . BY + b1 + b2 + b3   (model/vae.py:51-61 with the y-branch hoisted per speaker)
     Op& o = B.op(OP_GEMM, PH_PACK, "ptab");
     o.rows_fixed = a.y_dim; o.A = B.view(B.th(poff(P_emb)), 1, z, 0, 0, z); o.K = z;
-    o.B = B.aw(A_bz[1]); o.ldb = Nm; o.N = Nm; o.C = B.view(B.ws(b_ptab), 1, Nm, 0, 0, Nm);
+    o.B = B.aw(A_bz[1]); o.ldb = Nm; o.N = Nm; o.C = B.view(B.aw(A_bz[0] + (int64_t)z * Nm), 1, Nm, 0, 0, Nm);
     for (int w = 0; w < 3; w++) o.bias[w] = B.aw(A_bm[w]);
     o.bias_mod = Nm; o.a_scalar = 1;   // theta offsets are not 16B aligned in general
   }
+  if (use_umma) B.op(OP_PACK16, PH_PACK, "pack16");
   // encoder: conv (F) + Layernorm + lrelu   (util/layers.py:47-66, model/vae.py:74-78)
   // LN forward keeps (mean, rstd) per frame; backward recomputes xhat = (c - mean) * rstd from the raw conv
   // output c_l (LN_BWD: `xhat` = c_l, r0 = mean) instead of storing a second activation-sized tensor
@@ -410,13 +412,14 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   }
   // generator  (model/vae.py:84-103)
   { Op& o = B.op(OP_ZERO, PH_DEC, "zero_hm"); o.r0 = B.ws(b_hm); o.count = hm_flen; o.per_frame_count = 1; }
-  if (SPLIT) { Op& o = B.op(OP_SPLIT, PH_DEC, "split_z"); o.r0 = B.ws(p.buf_z); o.r1 = B.ws(b_zs); o.i0 = z; }
-  View V_z = B.view(B.ws(b_zs), 1, z, 0, 0, z);
+  {  // zs = [z | one-hot(y)]  (model/vae.py:64-70,89-90: embedding lookup + the two FCs of _merge)
+    Op& o = B.op(OP_ZCAT, PH_DEC, "zcat"); o.r0 = B.ws(p.buf_z); o.r1 = B.ws(b_zs); o.i0 = z; o.i1 = ypad;
+  }
+  View V_z = B.view(B.ws(b_zs), 1, zk, 0, 0, zk);
   View V_hm_rows = B.view(B.ws(b_hm), 1, hm_flen, 0, hm_off, hm_flen);
   {
     Op& o = B.op(OP_GEMM, PH_DEC, "merge");
-    o.A = V_z; o.K = z; o.B = B.aw(A_bz[0]); o.ldb = Nm; o.N = Nm; o.C = V_hm_rows;
-    o.table = B.ws(b_ptab); o.table_ld = Nm;
+    o.A = V_z; o.K = zk; o.B = B.aw(A_bz[0]); o.ldb = Nm; o.N = Nm; o.C = V_hm_rows;
   }
   std::vector<View> VA_g(nG);
   for (int g = 0; g < nG; g++) {
@@ -479,9 +482,9 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     o.C = B.view(dst, l.Hi, l.Hi * l.Cip, l.Cip, 0, l.Hi * l.Cip);
   }
   View V_dhm = B.view(B.ws(b_dhm), 1, Nm, 0, 0, Nm);
-  {  // merge backward: per-speaker row sums (IndexedSlices of embedding_lookup, duplicates summed)
-    Op& s = B.op(OP_SEGSUM, PH_BWD, "segsum_dhm"); s.r0 = B.ws(b_dhm); s.r1 = B.ws(b_dptab); s.i0 = Nm; s.i1 = a.y_dim;
-    Op& w = B.op(OP_WGRAD, PH_BWD, "wgrad_merge_z"); w.A = V_z; w.K = z; w.C = V_dhm; w.N = Nm; w.B = B.adw(A_bz[0]); w.ldb = Nm;
+  {  // merge backward; rows z.. of the weight gradient = per-speaker sums of dhm (IndexedSlices of
+     // embedding_lookup with duplicates summed)
+    Op& w = B.op(OP_WGRAD, PH_BWD, "wgrad_merge_z"); w.A = V_z; w.K = zk; w.C = V_dhm; w.N = Nm; w.B = B.adw(A_bz[0]); w.ldb = Nm;
     Op& o = B.op(OP_GEMM, PH_BWD, "dgrad_merge_z"); o.A = V_dhm; o.K = Nm; o.B = B.aw(A_bzd[0]); o.ldb = z; o.N = z;
     o.C = B.view(B.ws(b_dz), 1, z, 0, 0, z);
   }
@@ -519,12 +522,12 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   }
   {  // once per call, after all chunks: y-branch grads from the per-speaker sums, then unpack
     View V_emb = B.view(B.th(poff(P_emb)), 1, z, 0, 0, z);
-    View V_dptab = B.view(B.ws(b_dptab), 1, Nm, 0, 0, Nm);
+    View V_dptab = B.view(B.adw(A_bz[0] + (int64_t)z * Nm), 1, Nm, 0, 0, Nm);   // rows z.. of the merge weight gradient
     Op& w = B.op(OP_WGRAD, PH_FINAL, "wgrad_merge_y"); w.rows_fixed = a.y_dim; w.A = V_emb; w.K = z; w.a_scalar = 1;
     w.C = V_dptab; w.N = Nm; w.B = B.adw(A_bz[1]); w.ldb = Nm;
     Op& o = B.op(OP_GEMM, PH_FINAL, "dgrad_emb"); o.rows_fixed = a.y_dim; o.A = V_dptab; o.K = Nm;
     o.B = B.aw(A_bzd[1]); o.ldb = z; o.N = z; o.C = B.view(B.gr(poff(P_emb)), 1, z, 0, 0, z);
-    Op& c = B.op(OP_COLSUM, PH_FINAL, "colsum_dptab"); c.r0 = B.ws(b_dptab); c.r1 = B.adw(A_bm[0]); c.i0 = Nm; c.i1 = a.y_dim;
+    Op& c = B.op(OP_COLSUM, PH_FINAL, "colsum_dptab"); c.r0 = B.adw(A_bz[0] + (int64_t)z * Nm); c.r1 = B.adw(A_bm[0]); c.i0 = Nm; c.i1 = a.y_dim;
     Op& u = B.op(OP_UNPACK, PH_FINAL, "unpack"); u.count = p.n_params;
   }
 
@@ -534,7 +537,8 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   // themselves (the same TMA boxes, consumed as MN-major operands).  bf16x3: hi.hi + hi.lo + lo.hi.
   p.aw16_off = p.arena_w;
   if (use_umma) {
-    if (p.n_params > PACK_INDEX_MASK) return "too many parameters for the pack index encoding";
+    if (p.n_params > PACK_INDEX_MASK || p.arena_w > PACK_INDEX_MASK) return "too many parameters for the pack index encoding";
+    const int64_t ptab_lo = A_bz[0] + (int64_t)z * Nm, ptab_hi = ptab_lo + (int64_t)a.y_dim * Nm;
     auto view_ok = [&](const View& v) {
       return v.split && !v.pred && v.off >= 0 && v.off % 8 == 0 && v.rs % 8 == 0 && v.fs % 8 == 0 && umma_row_tile(v.R) > 0;
     };
@@ -550,14 +554,22 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
         continue;
       }
       if (o.kind != OP_GEMM || !view_ok(o.A) || o.K < 8 || o.N < 8 || o.B.space != SP_AW) continue;
+      // few-tap, few-channel layers over millions of rows (the last stride-3 transposed conv): the overlapping
+      // window boxes cost more TMA row requests than the thread-per-row FFMA kernel costs (measured)
+      if (o.K <= 64 && o.N <= 32) continue;
       o.kpad = rup(o.K, 8);
       const int64_t sz = (int64_t)o.N * o.kpad;
       o.bu_hi = a16_alloc(sz); o.bu_lo = a16_alloc(sz);
       for (int n = 0; n < o.N; n++) for (int k = 0; k < o.K; k++) {
-        int32_t src = p.pack_src[o.B.off + (int64_t)k * o.ldb + n];
-        if (src < 0) continue;
-        p.pack16_src[o.bu_hi + (int64_t)n * o.kpad + k] = src | (1 << PACK_MODE_SHIFT);
-        p.pack16_src[o.bu_lo + (int64_t)n * o.kpad + k] = src | (2 << PACK_MODE_SHIFT);
+        const int64_t q = o.B.off + (int64_t)k * o.ldb + n;
+        int32_t src = p.pack_src[q];
+        if (src < 0) {
+          // rows computed on the device at pack time (the per-speaker table): source = the fp32 pack itself
+          if (!(q >= ptab_lo && q < ptab_hi)) continue;
+          src = (int32_t)q | PACK16_FROM_ARENA;
+        }
+        p.pack16_src[o.bu_hi + (int64_t)n * o.kpad + k] = src;
+        p.pack16_src[o.bu_lo + (int64_t)n * o.kpad + k] = src | PACK16_LO;
       }
       o.umma = 1;
     }
@@ -589,7 +601,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     js << ",\"K\":" << o.K << ",\"N\":" << o.N << ","; json_ref(js, "B", o.B);
     js << ",\"ldb\":" << o.ldb << ","; json_ref(js, "bias0", o.bias[0]); js << ","; json_ref(js, "bias1", o.bias[1]);
     js << ","; json_ref(js, "bias2", o.bias[2]); js << ",\"bias_mod\":" << o.bias_mod << ",";
-    json_ref(js, "table", o.table); js << ",\"table_ld\":" << o.table_ld << ",\"rows_fixed\":" << o.rows_fixed
+    js << "\"rows_fixed\":" << o.rows_fixed
        << ",\"a_scalar\":" << o.a_scalar << ",\"umma\":" << o.umma << ",\"bu_hi\":" << o.bu_hi << ",\"bu_lo\":" << o.bu_lo
        << ",\"kpad\":" << o.kpad << ",";
     json_ref(js, "in", o.in); js << ","; json_ref(js, "xhat", o.xhat); js << ","; json_ref(js, "aout", o.aout); js << ",";

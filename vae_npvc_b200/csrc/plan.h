@@ -23,9 +23,9 @@ enum UserSlot { U_X = 0, U_Y = 1, U_EPS = 2 };
 enum Phase { PH_PACK = 0, PH_ENC = 1, PH_SAMPLE = 2, PH_DEC = 3, PH_LOSS = 4, PH_BWD = 5, PH_FINAL = 6 };
 enum OpKind {
   OP_GEMM = 0, OP_WGRAD = 1, OP_LN_FWD = 2, OP_LN_BWD = 3, OP_SAMPLE = 4, OP_SAMPLE_BWD = 5,
-  OP_RECON = 6, OP_SEGSUM = 7, OP_COLSUM = 8, OP_ZERO = 9, OP_PACK = 10, OP_UNPACK = 11,
+  OP_RECON = 6, OP_COLSUM = 8, OP_ZERO = 9, OP_PACK = 10, OP_UNPACK = 11,
   OP_PACK16 = 12,   // theta -> bf16 hi / lo operand packs (tensor path)
-  OP_SPLIT = 13     // fp32 rows -> bf16 hi / lo planes (r0 -> r1, i0 floats per frame)
+  OP_ZCAT = 13      // zs[f] = [z[f] (i0) | one-hot(y[f]) (i1)]  (r0 -> r1; fp32 or split planes)
 };
 
 struct Ref {
@@ -64,7 +64,6 @@ struct Op {
   int K = 0, N = 0;
   Ref B; int ldb = 0;    // GEMM: B operand; WGRAD: output dB
   Ref bias[3]; int bias_mod = 1;
-  Ref table; int table_ld = 0;   // + labels (U_Y): C[r,:] += table[y[r], :]
   int64_t rows_fixed = 0;        // >0: row count independent of n (A is not per-frame)
   int a_scalar = 0;              // A needs the scalar (unaligned / predicated) loader
   // tcgen05 path: OP_GEMM reads B as K-major [N, kpad] bf16 hi / lo packs (bf16-element offsets into the
@@ -100,7 +99,7 @@ struct Plan {
   std::vector<int32_t> pack16_src;   // [aw16_count] theta index | mode << 29, or -1
   std::vector<int32_t> unpack_ptr;   // [n_params+1] CSR over theta
   std::vector<int32_t> unpack_idx;   // positions in arena_dw
-  int buf_z = -1, buf_mu = -1, buf_lv = -1, buf_xh = -1, buf_acc = -1, buf_hz = -1, buf_adw = -1, buf_dptab = -1;
+  int buf_z = -1, buf_mu = -1, buf_lv = -1, buf_xh = -1, buf_acc = -1, buf_hz = -1, buf_adw = -1;
   int out_dim = 0;           // 513
   std::string json;
 
@@ -108,9 +107,10 @@ struct Plan {
   int64_t buf_offset(int b, int64_t chunk, bool train) const;   // float offset inside ws
 };
 
-// pack16_src entries: -1 = zero; else theta index | mode << 29 (1 bf16 hi, 2 bf16 lo of the residual)
-constexpr int PACK_MODE_SHIFT = 29;
-constexpr int32_t PACK_INDEX_MASK = (1 << PACK_MODE_SHIFT) - 1;
+// pack16_src entries: -1 = zero; else source index | flags: the bf16 hi (or, with PACK16_LO, the bf16 of the
+// residual) of theta[index] (or, with PACK16_FROM_ARENA, of the fp32 pack arena_w[index])
+constexpr int32_t PACK16_FROM_ARENA = 1 << 29, PACK16_LO = 1 << 30;
+constexpr int32_t PACK_INDEX_MASK = (1 << 29) - 1;
 
 // Returns empty string on success, else an error message.  use_umma: route GEMM-shaped ops to the
 // tcgen05 kernels: their A operands become split (bf16 hi / lo) buffers, their B operands bf16 packs.

@@ -3,7 +3,7 @@
 //   is  Ah.Bh  +  (Al.Bh + Ah.Bl)  with fp32 accumulation in TMEM -- ~2^-17 relative, which holds the 1e-4
 //   fp32 parity bar of the path at the bf16 MMA rate (a single bf16 / tf32 pass does not hold it).
 //
-//   (F) umma_fwd_kernel    C[rows,N] = A_view[rows,K] . B[K,N] (+ bias + table[label])
+//   (F) umma_fwd_kernel    C[rows,N] = A_view[rows,K] . B[K,N] (+ bias)
 //       A tiles: TMA boxes over the strided view (k, row-in-frame, row-group, frame) = im2col for free;
 //       B tiles: K-major [N, kpad] bf16 packs.  Both K-major, 128B swizzle, BK = 64.
 //   (W) umma_wgrad_kernel  dB[K,N] += A_view[rows,K]^T . D_view[rows,N]
@@ -31,7 +31,8 @@ struct RowTiling {
 struct UmmaArgs {
   int K, N;              // logical GEMM sizes (wgrad: dB is [K, N])
   int BN;                // N tile
-  int kblocks;           // (F): ceil(K / 64)
+  int kblocks;           // (F): ceil(K / bk)
+  int sw;                // (F): swizzle span = bytes of one operand row per k-block: 128 (bk = 64) or 64 (bk = 32)
   int stages;
   int tmem_cols;
   RowTiling rt;
@@ -39,7 +40,6 @@ struct UmmaArgs {
   int n_tiles, acc_sets;
   DView C;
   const float* bias0; const float* bias1; const float* bias2; int bias_mod;
-  const float* table; const long long* labels; int table_ld;
   // (W)
   int d_sw;              // swizzle span (bytes) of the dC boxes: 128 / 64 / 32 -> 64 / 32 / 16 columns per box
   int rows_al;           // rows_tile rounded up to 16 (MMA K step)
@@ -136,7 +136,7 @@ __device__ __forceinline__ void tile_coords(const RowTiling& rt, long long mt, i
 // (F) persistent forward / dgrad kernel, 192 threads:
 //   warp 0      TMA producer (A hi, A lo, B hi, B lo per 64-wide k-block), runs ahead across tiles
 //   warp 1      TMEM allocator + MMA issuer; accumulators double-buffered in TMEM when 4*BN <= 512
-//   warps 2-5   epilogue (TMEM -> registers -> bias / table -> fp32 or split store), overlapped with the
+//   warps 2-5   epilogue (TMEM -> registers -> bias -> fp32 or split store), overlapped with the
 //               next tile's mainloop through the accf / acce barriers
 // =============================================================================================
 __global__ void __launch_bounds__(192, 1)
@@ -145,8 +145,10 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   using namespace umma;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_tile_bytes = (uint32_t)g.BN * 128u;
-  const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
+  const uint32_t sw = (uint32_t)g.sw;
+  const int bk = g.sw >> 1, ksteps = bk >> 4;
+  const uint32_t a_tile_bytes = (uint32_t)BM * sw, b_tile_bytes = (uint32_t)g.BN * sw;
+  const uint32_t stage_bytes = 2u * a_tile_bytes + 2u * b_tile_bytes;
   const uint32_t bar_base = sbase + (uint32_t)g.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(g.stages + s); };
@@ -177,7 +179,7 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint32_t tx = 2u * (uint32_t)g.rt.rows_tile * 128u + 2u * b_tile_bytes;
+      const uint32_t tx = 2u * (uint32_t)g.rt.rows_tile * sw + 2u * b_tile_bytes;
       uint32_t it = 0;
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const long long mt = t / g.n_tiles; const int n0 = (int)(t - mt * g.n_tiles) * g.BN;
@@ -187,10 +189,10 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t st = sbase + (uint32_t)s * stage_bytes;
           mbar_expect_tx(full_bar(s), tx);
-          tma_load_4d(st, &tmAh, full_bar(s), kb * BK, 0, a0, (int)f0);
-          tma_load_4d(st + A_TILE_BYTES, &tmAl, full_bar(s), kb * BK, 0, a0, (int)f0);
-          tma_load_2d(st + 2u * A_TILE_BYTES, &tmBh, full_bar(s), kb * BK, n0);
-          tma_load_2d(st + 2u * A_TILE_BYTES + b_tile_bytes, &tmBl, full_bar(s), kb * BK, n0);
+          tma_load_4d(st, &tmAh, full_bar(s), kb * bk, 0, a0, (int)f0);
+          tma_load_4d(st + a_tile_bytes, &tmAl, full_bar(s), kb * bk, 0, a0, (int)f0);
+          tma_load_2d(st + 2u * a_tile_bytes, &tmBh, full_bar(s), kb * bk, n0);
+          tma_load_2d(st + 2u * a_tile_bytes + b_tile_bytes, &tmBl, full_bar(s), kb * bk, n0);
         }
       }
     }
@@ -209,10 +211,9 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           mbar_wait(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-          const uint64_t ah = make_sdesc(st, 0, 128), al = make_sdesc(st + A_TILE_BYTES, 0, 128);
-          const uint64_t bh = make_sdesc(st + 2u * A_TILE_BYTES, 0, 128), bl = make_sdesc(st + 2u * A_TILE_BYTES + b_tile_bytes, 0, 128);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; k4++) {                  // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr >> 4) field
+          const uint64_t ah = make_sdesc(st, 0, sw), al = make_sdesc(st + a_tile_bytes, 0, sw);
+          const uint64_t bh = make_sdesc(st + 2u * a_tile_bytes, 0, sw), bl = make_sdesc(st + 2u * a_tile_bytes + b_tile_bytes, 0, sw);
+          for (int k4 = 0; k4 < ksteps; k4++) {             // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr >> 4) field
             const uint64_t o = (uint64_t)(k4 * 2);
             const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
             mma_bf16(acc, ah + o, bh + o, idesc, first);                       // main products
@@ -252,13 +253,12 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       int a0; long long f0; tile_coords(g.rt, mt, a0, f0);
       const long long f = f0 + fl; const int a = a0 + al;
       const bool row_ok = (row_local < g.rt.rows_tile) && (f < g.rt.frames) && (a < g.rt.Ra);
-      float* cp = nullptr; uint16_t* chp = nullptr; int inf = 0; const float* trow = nullptr;
+      float* cp = nullptr; uint16_t* chp = nullptr; int inf = 0;
       if (row_ok) {
         const int j = a * g.rt.Rb + b_in;
         inf = j * g.C.rs + g.C.off;
         cp = g.C.p + f * g.C.fs + inf;
         chp = reinterpret_cast<uint16_t*>(g.C.p) + f * 2 * g.C.fs + inf;
-        if (g.table) trow = g.table + (long long)g.labels[f] * g.table_ld;
       }
       mbar_wait(accf_bar(buf), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -275,10 +275,8 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; e++) {
-            const int n = nb + e;
             float tt = __uint_as_float(v[q * 4 + e]) + __uint_as_float(w[q * 4 + e]);
             if (g.bias0) tt += bias_s[c0 + q * 4 + e];
-            if (trow && n < g.N) tt += trow[n];
             o[e] = tt;
           }
           bool full = (nb + 4 <= g.N);
