@@ -166,9 +166,30 @@ def _layernorm(x, scale, offset):
     return (x - m) * torch.rsqrt(v + LN_EPS) * scale.reshape(1, -1, 1, 1) + offset.reshape(1, -1, 1, 1)
 
 
-def _lrelu(x):
-    """util/layers.py:147-149: tf.maximum(x, leak*x), leak=0.02."""
-    return torch.maximum(x, LEAK * x)
+class _LreluWithBranch(torch.autograd.Function):
+    """lrelu whose BACKWARD takes the branch (slope 1 or leak) from a given mask instead of from its own
+    input.  lrelu' is discontinuous at 0: a pre-activation closer to 0 than the fp32 rounding error of
+    the forward legitimately takes the other branch in an fp32 implementation (TensorFlow included)
+    and moves that element's gradient by 0.98*dy.  Gradient-parity tests therefore hand the oracle the
+    branches the implementation under test actually took (and separately check that they differ from
+    the oracle's own only where |pre-activation| is tiny)."""
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        ctx.save_for_backward(pos)
+        return torch.maximum(x, LEAK * x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        return g * torch.where(pos, torch.ones_like(g), torch.full_like(g, LEAK)), None
+
+
+def _lrelu(x, pos=None):
+    """util/layers.py:147-149: tf.maximum(x, leak*x), leak=0.02.  pos: see _LreluWithBranch."""
+    if pos is None:
+        return torch.maximum(x, LEAK * x)
+    return _LreluWithBranch.apply(x, torch.as_tensor(pos, dtype=torch.bool).reshape(x.shape))
 
 
 def toeplitz_index(k, H):
@@ -180,7 +201,7 @@ def toeplitz_index(k, H):
     return np.clip(t, 0, k - 1), ((t >= 0) & (t < k))
 
 
-def encoder(P, arch, x, acts=None):
+def encoder(P, arch, x, acts=None, lrelu_pos=None):
     """model/vae.py:72-82.  x: [N,1,513,1] -> (mu, lv) [N, z]."""
     for i, (ci, co, k, s, H, Ho, pl, pr) in enumerate(enc_geometry(arch)):
         p = "Encoder/Conv2d-%d" % i
@@ -189,7 +210,7 @@ def encoder(P, arch, x, acts=None):
         x = F.pad(x, (0, 0, pl, pr))                               # SAME padding on H
         x = F.conv2d(x, W.permute(3, 2, 0, 1), b, stride=(s, 1))   # -> OIHW
         x = _layernorm(x, P[p + "/layernorm.scale"], P[p + "/layernorm.offset"])
-        x = _lrelu(x)
+        x = _lrelu(x, None if lrelu_pos is None else lrelu_pos.get("enc%d" % i))
         if acts is not None:
             acts["enc%d" % i] = x
     f = x.reshape(x.shape[0], -1)                                  # slim.flatten of NCHW: c*H + h
@@ -198,7 +219,7 @@ def encoder(P, arch, x, acts=None):
     return mu, lv
 
 
-def generator(P, arch, z, y, acts=None):
+def generator(P, arch, z, y, acts=None, lrelu_pos=None):
     """model/vae.py:84-103.  z [N,z], y [N] int64 -> xh NCHW [N,1,513,1]."""
     g = arch["generator"]
     h, w, c = g["hwc"]
@@ -231,7 +252,7 @@ def generator(P, arch, z, y, acts=None):
             x = full[:, :, cl:cl + s * H, :] + b.reshape(1, -1, 1, 1)
         if i < len(gg) - 1:
             x = _layernorm(x, P["Generator/ConvT-LN%d.scale" % i], P["Generator/ConvT-LN%d.offset" % i])
-            x = _lrelu(x)
+            x = _lrelu(x, None if lrelu_pos is None else lrelu_pos.get("gen%d" % i))
         if acts is not None:
             acts["gen%d" % i] = x
     return x
@@ -256,17 +277,19 @@ def _as_torch(params, dtype, requires_grad=False):
     return P
 
 
-def forward(arch, params, x, y, eps, dtype=torch.float64, with_grads=False, with_acts=False):
+def forward(arch, params, x, y, eps, dtype=torch.float64, with_grads=False, with_acts=False, lrelu_pos=None):
     """model/vae.py:106-130 ``loss``.  x [N,513]; y [N] int64; eps [N,z] (the N(0,1) draw of
-    GaussianSampleLayer made explicit).  Returns dict of numpy arrays."""
+    GaussianSampleLayer made explicit).  Returns dict of numpy arrays.
+    lrelu_pos: optional {"enc<i>" / "gen<i>": bool [N,C,H,1]} branch masks for the lrelu BACKWARD
+    (see _LreluWithBranch); the forward values never depend on it."""
     P = _as_torch(params, dtype, requires_grad=with_grads)
     xt = torch.tensor(np.asarray(x), dtype=dtype).reshape(-1, 1, arch["hwc"][0], 1)
     yt = torch.tensor(np.asarray(y), dtype=torch.int64)
     et = torch.tensor(np.asarray(eps), dtype=dtype)
     acts = {} if with_acts else None
-    mu, lv = encoder(P, arch, xt, acts)
+    mu, lv = encoder(P, arch, xt, acts, lrelu_pos)
     z = mu + et * torch.sqrt(torch.exp(lv))                        # util/layers.py:152-156
-    xh = generator(P, arch, z, yt, acts)
+    xh = generator(P, arch, z, yt, acts, lrelu_pos)
     D_KL = kld(mu, lv).mean()
     logP = log_density(xt.reshape(xt.shape[0], -1), xh.reshape(xh.shape[0], -1)).mean()
     G = -logP + D_KL

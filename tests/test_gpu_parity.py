@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from oracle import convvae_ref as R
+from parity_util import check_branches, lrelu_branches
 
 pytestmark = pytest.mark.gpu
 TOL_OUT, TOL_GRAD = 1e-4, 1e-3
@@ -42,7 +43,12 @@ def _check_against_oracle(eng, arch, n, seed=1, n_speakers=None):
     torch.cuda.synchronize()
     # oracle sees the same fp32-rounded inputs and weights
     P32 = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in P.items()}
-    ref = R.forward(arch, P32, x.astype(np.float32), y, eps.astype(np.float32), with_grads=True)
+    fwd = R.forward(arch, P32, x.astype(np.float32), y, eps.astype(np.float32), with_acts=True)
+    # lrelu' is discontinuous at 0: the oracle differentiates with the branches the CUDA path took, which
+    # may differ from its own only where the pre-activation is within fp32 rounding distance of zero
+    pos = lrelu_branches(lambda name: eng.debug_buffer(name, n).cpu().numpy(), arch, P32, n)
+    check_branches(pos, fwd["acts"])
+    ref = R.forward(arch, P32, x.astype(np.float32), y, eps.astype(np.float32), with_grads=True, lrelu_pos=pos)
     for k in ("z", "mu", "lv", "xh"):
         assert rel(out[k], ref[k]) <= TOL_OUT, (k, rel(out[k], ref[k]))
     lo = out["losses"].cpu().numpy()

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 import plan_interp as PI
+from parity_util import check_branches, lrelu_branches
 from oracle import convvae_ref as R
 from vae_npvc_b200 import lib
 
@@ -41,7 +42,7 @@ def test_param_table_matches_reference_variable_order(arch):
         off += t["size"]
 
 
-@pytest.mark.parametrize("n,umma", [(1, 0), (3, 0), (3, 1)])
+@pytest.mark.parametrize("n,umma", [(1, 0), (3, 0), (3, 1), (8, 1)])
 def test_plan_matches_oracle(arch, n, umma, monkeypatch):
     """umma=0: CUDA-core plan, exact in fp64.  umma=1: the tcgen05 routing with tf32 hi+lo operand
     planes and packs (bf16x3: hi.hi + hi.lo + lo.hi, ~2^-17 per product, so fp64 agreement drops to ~1e-5)."""
@@ -52,8 +53,11 @@ def test_plan_matches_oracle(arch, n, umma, monkeypatch):
     tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx")}
     P = R.init_params(arch, 0)
     x, y, eps = R.make_inputs(arch, n)
-    out = PI.Interp(plan, tables, R.flatten_params(arch, P, np.float64), n, x, y, eps).loss_fwd_bwd()
-    ref = R.forward(arch, P, x, y, eps, with_grads=True)
+    it = PI.Interp(plan, tables, R.flatten_params(arch, P, np.float64), n, x, y, eps)
+    out = it.loss_fwd_bwd()
+    pos = lrelu_branches(it.buf, arch, P, n)                      # the oracle differentiates with the plan's lrelu branches
+    check_branches(pos, R.forward(arch, P, x, y, eps, with_acts=True)["acts"])
+    ref = R.forward(arch, P, x, y, eps, with_grads=True, lrelu_pos=pos)
     assert (sum(op.get("umma", 0) for op in plan["ops"]) > 10) == bool(umma)
     for k in ("mu", "lv", "z", "xh"):
         assert rel(out[k], ref[k]) < tol_out, k

@@ -12,6 +12,9 @@ import plan_interp as PI
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 arch = vcc2016_vae_arch()
+if len(sys.argv) > 2:                                   # an alternative architecture of tests/conftest.py
+    import conftest, copy
+    arch = copy.deepcopy(conftest.ALT_ARCHS[sys.argv[2]])
 eng = Engine(arch, "cuda:0")
 P = R.init_params(arch, 0)
 theta64 = R.flatten_params(arch, P, np.float64)

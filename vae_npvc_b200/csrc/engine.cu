@@ -80,6 +80,13 @@ DView dview(const Ctx& c, const View& v) {
   d.split = v.split;
   return d;
 }
+// threads per frame of the register-resident Layernorm kernels (0: use the shared-memory kernels)
+int ln_group(int L, int Cn, int out_off, int out_flen) {
+  if (L % 8 || out_off % 8 || out_flen % 8 || Cn % 8 || Cn > 2048) return 0;     // a thread's 8 elements = 8 consecutive channels
+  for (int G = 32; G <= 256; G *= 2)
+    if (L <= 32 * G && (8 * G) % Cn == 0) return G;
+  return 0;
+}
 bool view_vec_ok(const DView& d) {
   return !d.pred && ((reinterpret_cast<uintptr_t>(d.p) & 15) == 0) && (d.fs % 4 == 0) && (d.rs % 4 == 0) && (d.off % 4 == 0);
 }
@@ -380,7 +387,16 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       g.rstd = resolve(c, o.rstd); g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta);
       g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
       g.out_split = p.bufs[o.aout.buf].split;
-      ln_fwd_kernel<<<(unsigned)c.n, 256, (size_t)o.L * sizeof(float), st>>>(g); h->launches++; break;
+      const int G = ln_group(o.L, o.Cn, o.out_off, o.out_flen);
+      if (G) {
+        const long long fbs = (c.n + 256 / G - 1) / (256 / G);
+        long long blocks = (long long)h->sm_count * 8; if (blocks > fbs) blocks = fbs;
+        if (G == 32) ln_fwd_reg_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(g);
+        else if (G == 64) ln_fwd_reg_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(g);
+        else if (G == 128) ln_fwd_reg_kernel<128><<<(unsigned)blocks, 256, 0, st>>>(g);
+        else ln_fwd_reg_kernel<256><<<(unsigned)blocks, 256, 0, st>>>(g);
+      } else ln_fwd_kernel<<<(unsigned)c.n, 256, (size_t)o.L * sizeof(float), st>>>(g);
+      h->launches++; break;
     }
     case OP_LN_BWD: {
       LnBwdArgs g; g.dy = resolve(c, o.in); g.cin = resolve(c, o.xhat); g.mean = resolve(c, o.r0); g.rstd = resolve(c, o.rstd);
@@ -388,8 +404,22 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       g.dgamma = resolve(c, o.dgamma); g.dbeta = resolve(c, o.dbeta); g.dbias = resolve(c, o.dbias);
       g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
       g.out_split = p.bufs[o.aout.buf].split;
-      long long blocks = (long long)h->sm_count * 8; if (blocks > c.n) blocks = c.n;
-      ln_bwd_kernel<<<(unsigned)blocks, 256, (size_t)(2 * o.L + 3 * o.Cn) * sizeof(float), st>>>(g); h->launches++; break;
+      // frames of <= 2048 floats: register-resident kernel; larger frames keep more bytes in flight per SM
+      // through the shared-memory kernel (measured)
+      int G = ln_group(o.L, o.Cn, o.out_off, o.out_flen); if (G > 64) G = 0;
+      if (G) {
+        const long long fbs = (c.n + 256 / G - 1) / (256 / G);
+        long long blocks = (long long)h->sm_count * 4; if (blocks > fbs) blocks = fbs;
+        const size_t sm = (size_t)5 * o.Cn * sizeof(float);
+        if (G == 32) ln_bwd_reg_kernel<32><<<(unsigned)blocks, 256, sm, st>>>(g);
+        else if (G == 64) ln_bwd_reg_kernel<64><<<(unsigned)blocks, 256, sm, st>>>(g);
+        else if (G == 128) ln_bwd_reg_kernel<128><<<(unsigned)blocks, 256, sm, st>>>(g);
+        else ln_bwd_reg_kernel<256><<<(unsigned)blocks, 256, sm, st>>>(g);
+      } else {
+        long long blocks = (long long)h->sm_count * 8; if (blocks > c.n) blocks = c.n;
+        ln_bwd_kernel<<<(unsigned)blocks, 256, (size_t)(2 * o.L + 3 * o.Cn) * sizeof(float), st>>>(g);
+      }
+      h->launches++; break;
     }
     case OP_SAMPLE: {
       const int z = o.i0, fpb = 8;

@@ -773,6 +773,183 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
 }
 
 // =============================================================================================
+// Register-resident Layernorm kernels (the fast path): G threads own one frame, each thread holds up to
+// 4 units of 8 consecutive elements in registers -- one global read, group reductions by warp shuffles
+// (+ one shared-memory hop when G > 32), 16-byte plane stores.  Requirements (else the kernels above):
+// L, out_off, out_flen multiples of 8; L <= 32 G; Cn divides 8 G (a thread's channels are then fixed).
+// =============================================================================================
+template <int G, int NV>
+__device__ __forceinline__ void group_sum(float (&v)[NV], float* red /* [8][NV] */) {
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = warp_sum(v[i]);
+  if (G > 32) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) red[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+    const int w0 = (warp / (G / 32)) * (G / 32);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < G / 32; w++) t += red[(w0 + w) * NV + i];
+      v[i] = t;
+    }
+  }
+}
+__device__ __forceinline__ void ld8(const float* p, float (&x)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+// 8 consecutive outputs at element index e of a frame: fp32 (two float4) or planes (one uint4 per plane)
+__device__ __forceinline__ void st8(float* base, long long f, int flen, int e, const float (&o)[8], int split) {
+  if (split) {
+    uint16_t* hp = reinterpret_cast<uint16_t*>(base) + f * 2 * flen + e;
+    uint4 h, l;
+    h.x = split_pack2(o[0], o[1], l.x); h.y = split_pack2(o[2], o[3], l.y);
+    h.z = split_pack2(o[4], o[5], l.z); h.w = split_pack2(o[6], o[7], l.w);
+    *reinterpret_cast<uint4*>(hp) = h; *reinterpret_cast<uint4*>(hp + flen) = l;
+  } else {
+    float4* op = reinterpret_cast<float4*>(base + f * flen + e);
+    op[0] = make_float4(o[0], o[1], o[2], o[3]); op[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+// zero the pad units of an output frame: units [0, off8) and [off8 + L8, F8)
+__device__ __forceinline__ void zero_pads(float* base, long long f, int flen, int off8, int L8, int F8, int t, int G, int split) {
+  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int npad = F8 - L8;
+  for (int p = t; p < npad; p += G) st8(base, f, flen, 8 * (p < off8 ? p : p + L8), z, split);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) ln_fwd_reg_kernel(LnFwdArgs g) {
+  constexpr int V = 4, FPB = 256 / G;
+  __shared__ float red[8];
+  const int t = threadIdx.x % G, grp = threadIdx.x / G;
+  const int L8 = g.L >> 3, off8 = g.out_off >> 3, F8 = g.out_flen >> 3;
+  float gm[8], bt[8];
+  { const int c0 = (8 * t) % g.Cn;
+#pragma unroll
+    for (int e = 0; e < 8; e++) { gm[e] = g.gamma[c0 + e]; bt[e] = g.beta[c0 + e]; } }
+  const float invL = 1.0f / (float)g.L;
+  for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
+    const long long f = fb * FPB + grp; const bool fok = f < g.frames;
+    float x[V][8];
+    float s[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const int u = t + k * G;
+      if (fok && u < L8) {
+        ld8(g.in + f * g.L + 8 * u, x[k]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) s[0] += x[k][e];
+      }
+    }
+    group_sum<G, 1>(s, red);
+    const float mean = s[0] * invL;
+    float q[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      if (fok && t + k * G < L8) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) { const float d = x[k][e] - mean; q[0] = fmaf(d, d, q[0]); }
+      }
+    }
+    group_sum<G, 1>(q, red);
+    const float rs = rsqrtf(q[0] * invL + NPVC_LN_EPS);
+    if (!fok) continue;                    // (no block-wide barrier after this point in the iteration)
+    if (t == 0) { g.rstd[f] = rs; g.mean[f] = mean; }
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const int u = t + k * G;
+      if (u < L8) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) o[e] = lrelu_f(fmaf((x[k][e] - mean) * rs, gm[e], bt[e]));
+        st8(g.aout, f, g.out_flen, 8 * (u + off8), o, g.out_split);
+      }
+    }
+    zero_pads(g.aout, f, g.out_flen, off8, L8, F8, t, G, g.out_split);
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
+  constexpr int V = 4, FPB = 256 / G;
+  extern __shared__ __align__(16) float chs[];   // [3 * Cn] channel sums: dgamma | dbeta | dbias, then [2 * Cn] gamma | beta
+  __shared__ float red[16];
+  const int t = threadIdx.x % G, grp = threadIdx.x / G;
+  const int L8 = g.L >> 3, off8 = g.out_off >> 3, F8 = g.out_flen >> 3;
+  float* sgm = chs + 3 * g.Cn; float* sbt = sgm + g.Cn;
+  for (int i = threadIdx.x; i < 3 * g.Cn; i += blockDim.x) chs[i] = 0.f;
+  for (int i = threadIdx.x; i < g.Cn; i += blockDim.x) { sgm[i] = g.gamma[i]; sbt[i] = g.beta[i]; }
+  __syncthreads();
+  const int c0 = (8 * t) % g.Cn;
+  float adg[8], adb[8], adc[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) adg[e] = adb[e] = adc[e] = 0.f;
+  const float invL = 1.0f / (float)g.L;
+  for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
+    const long long f = fb * FPB + grp; const bool fok = f < g.frames;
+    float dx[V][8], xh[V][8];
+    float rs = 0.f, mu = 0.f;
+    if (fok) { rs = g.rstd[f]; mu = g.mean[f]; }
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const int u = t + k * G;
+      if (fok && u < L8) { ld8(g.dy + f * g.L + 8 * u, dx[k]); ld8(g.cin + f * g.L + 8 * u, xh[k]); }
+    }
+    float s[2] = {0.f, 0.f};
+    float gm[8], bt[8];                                           // this thread's 8 channels (fixed: Cn | 8 G)
+    { const float4 a = *reinterpret_cast<const float4*>(sgm + c0), b = *reinterpret_cast<const float4*>(sgm + c0 + 4);
+      const float4 c = *reinterpret_cast<const float4*>(sbt + c0), d = *reinterpret_cast<const float4*>(sbt + c0 + 4);
+      gm[0] = a.x; gm[1] = a.y; gm[2] = a.z; gm[3] = a.w; gm[4] = b.x; gm[5] = b.y; gm[6] = b.z; gm[7] = b.w;
+      bt[0] = c.x; bt[1] = c.y; bt[2] = c.z; bt[3] = c.w; bt[4] = d.x; bt[5] = d.y; bt[6] = d.z; bt[7] = d.w; }
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      if (fok && t + k * G < L8) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const float h = (xh[k][e] - mu) * rs;                 // xhat, as the forward formed it
+          const float u = fmaf(h, gm[e], bt[e]);
+          const float du = dx[k][e] * (u >= 0.f ? 1.0f : 0.02f);
+          const float ox = du * gm[e];
+          s[0] += ox; s[1] = fmaf(ox, h, s[1]);
+          adg[e] = fmaf(du, h, adg[e]); adb[e] += du;
+          dx[k][e] = ox; xh[k][e] = h;
+        }
+      }
+    }
+    group_sum<G, 2>(s, red);
+    if (!fok) continue;
+    const float s1 = s[0] * invL, s2 = s[1] * invL;
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const int u = t + k * G;
+      if (u < L8) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { o[e] = rs * (dx[k][e] - s1 - xh[k][e] * s2); adc[e] += o[e]; }
+        st8(g.dc, f, g.out_flen, 8 * (u + off8), o, g.out_split);
+      }
+    }
+    zero_pads(g.dc, f, g.out_flen, off8, L8, F8, t, G, g.out_split);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    atomicAdd(&chs[c0 + e], adg[e]); atomicAdd(&chs[g.Cn + c0 + e], adb[e]); atomicAdd(&chs[2 * g.Cn + c0 + e], adc[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < g.Cn; i += blockDim.x) {
+    atomicAdd(&g.dgamma[i], chs[i]); atomicAdd(&g.dbeta[i], chs[g.Cn + i]); atomicAdd(&g.dbias[i], chs[2 * g.Cn + i]);
+  }
+}
+
+// =============================================================================================
 // sampler + KL  (util/layers.py:152-156,170-183); blockDim = 2z threads, thread = column
 // =============================================================================================
 __global__ void sample_kl_kernel(const float* hz, const float* eps, float* mu, float* lv, float* zout,
