@@ -156,7 +156,7 @@ RowTiling make_tiling(int R, long long frames, int row_target) {
   else { t.FB = 1; t.Ab = row_target / t.Rb; if (t.Ab < 1) t.Ab = 1; if (t.Ab > t.Ra) t.Ab = t.Ra; }
   t.TA = (t.Ra + t.Ab - 1) / t.Ab;
   t.rows_tile = t.Rb * t.Ab * t.FB;
-  t.frames = frames; t.m_tiles = ((frames + t.FB - 1) / t.FB) * t.TA;
+  t.frames = (int)frames; t.m_tiles = (int)(((frames + t.FB - 1) / t.FB) * t.TA);
   return t;
 }
 
@@ -281,7 +281,7 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
     double cost = (waves < 1.0 ? 1.0 / waves : std::ceil(waves) / waves) + 0.01 * waves;
     if (cost < best - 1e-9) { best = cost; S = cand; }
   }
-  g.tiles_per_split = (rt.m_tiles + S - 1) / S;
+  g.tiles_per_split = (int)((rt.m_tiles + S - 1) / S);
   S = (rt.m_tiles + g.tiles_per_split - 1) / g.tiles_per_split;
   g.out = resolve(c, o.B); g.ld = o.ldb;
   static bool attr_set = false;

@@ -25,7 +25,7 @@ namespace npvc {
 struct RowTiling {
   int Rb, Ra, Ab, FB, TA;     // TA = ceil(Ra / Ab) tiles per frame block
   int rows_tile;              // Rb * Ab * FB
-  long long frames, m_tiles;  // m_tiles = ceil(frames / FB) * TA
+  int frames, m_tiles;        // m_tiles = ceil(frames / FB) * TA
 };
 
 struct UmmaArgs {
@@ -43,7 +43,7 @@ struct UmmaArgs {
   // (W)
   int d_sw;              // swizzle span (bytes) of the dC boxes: 128 / 64 / 32 -> 64 / 32 / 16 columns per box
   int rows_al;           // rows_tile rounded up to 16 (MMA K step)
-  long long tiles_per_split;
+  int tiles_per_split;
   float* out; int ld;
 };
 
@@ -125,10 +125,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr) : "memory");
 }
 // M tile -> TMA coordinates (row-group a0, frame f0)
-__device__ __forceinline__ void tile_coords(const RowTiling& rt, long long mt, int& a0, long long& f0) {
-  const long long fb = mt / rt.TA;
-  a0 = (int)(mt - fb * rt.TA) * rt.Ab; f0 = fb * rt.FB;
+__device__ __forceinline__ void tile_coords(const RowTiling& rt, int mt, int& a0, int& f0) {
+  const int fb = mt / rt.TA;
+  a0 = (mt - fb * rt.TA) * rt.Ab; f0 = fb * rt.FB;
 }
+// One lane of a converged warp.  The role loops below are executed by ALL lanes of their warp (warp-uniform
+// control flow and operands) and only the tcgen05 / TMA instruction itself sits under this predicate:
+// issuing them from inside an `if (lane == 0)` region makes the compiler wrap every uniform-datapath
+// instruction in an elect / branch loop (measured: ~2000 cycles per k-block of pure issue overhead).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor without the start address (added per stage: (addr & 0x3FFFF) >> 4)
+__device__ __forceinline__ uint64_t sdesc_base(uint32_t lbo, uint32_t sw) { return make_sdesc(0u, lbo, sw); }
+__device__ __forceinline__ uint64_t sdesc_at(uint64_t base, uint32_t saddr) { return base | (uint64_t)((saddr & 0x3FFFF) >> 4); }
 
 }  // namespace umma
 
@@ -159,7 +171,7 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   float* bias_s = reinterpret_cast<float*>(gen_base + (tmem_slot - sbase) + 16);      // [256] effective bias of the current N tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total_tiles = g.rt.m_tiles * g.n_tiles;
+  const int total_tiles = g.rt.m_tiles * g.n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
@@ -177,52 +189,55 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const uint32_t tx = 2u * (uint32_t)g.rt.rows_tile * sw + 2u * b_tile_bytes;
-      uint32_t it = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const long long mt = t / g.n_tiles; const int n0 = (int)(t - mt * g.n_tiles) * g.BN;
-        int a0; long long f0; tile_coords(g.rt, mt, a0, f0);
-        for (int kb = 0; kb < g.kblocks; kb++, it++) {
-          const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+    // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
+    const uint32_t tx = 2u * (uint32_t)g.rt.rows_tile * sw + 2u * b_tile_bytes;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t / g.n_tiles; const int n0 = (t - mt * g.n_tiles) * g.BN;
+      int a0, f0; tile_coords(g.rt, mt, a0, f0);
+      for (int kb = 0; kb < g.kblocks; kb++, it++) {
+        const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        if (elect_one()) {
           mbar_expect_tx(full_bar(s), tx);
-          tma_load_4d(st, &tmAh, full_bar(s), kb * bk, 0, a0, (int)f0);
-          tma_load_4d(st + a_tile_bytes, &tmAl, full_bar(s), kb * bk, 0, a0, (int)f0);
+          tma_load_4d(st, &tmAh, full_bar(s), kb * bk, 0, a0, f0);
+          tma_load_4d(st + a_tile_bytes, &tmAl, full_bar(s), kb * bk, 0, a0, f0);
           tma_load_2d(st + 2u * a_tile_bytes, &tmBh, full_bar(s), kb * bk, n0);
           tma_load_2d(st + 2u * a_tile_bytes + b_tile_bytes, &tmBl, full_bar(s), kb * bk, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(g.BN, false);
-      uint32_t it = 0; int lt = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
-        const int buf = lt % g.acc_sets; const uint32_t aph = (uint32_t)((lt / g.acc_sets) & 1);
-        mbar_wait(acce_bar(buf), aph ^ 1u);                 // epilogue has drained this accumulator set
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
+    const uint32_t idesc = make_idesc(g.BN, false);
+    const uint64_t dbase = sdesc_base(0, sw);
+    uint32_t it = 0; int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
+      const int buf = lt % g.acc_sets; const uint32_t aph = (uint32_t)((lt / g.acc_sets) & 1);
+      mbar_wait(acce_bar(buf), aph ^ 1u);                 // epilogue has drained this accumulator set
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * g.BN), acc2 = acc + (uint32_t)g.BN;
+      for (int kb = 0; kb < g.kblocks; kb++, it++) {
+        const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
+        mbar_wait(full_bar(s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * g.BN);
-        for (int kb = 0; kb < g.kblocks; kb++, it++) {
-          const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
-          mbar_wait(full_bar(s), ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-          const uint64_t ah = make_sdesc(st, 0, sw), al = make_sdesc(st + a_tile_bytes, 0, sw);
-          const uint64_t bh = make_sdesc(st + 2u * a_tile_bytes, 0, sw), bl = make_sdesc(st + 2u * a_tile_bytes + b_tile_bytes, 0, sw);
+        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        const uint64_t ah = sdesc_at(dbase, st), al = sdesc_at(dbase, st + a_tile_bytes);
+        const uint64_t bh = sdesc_at(dbase, st + 2u * a_tile_bytes), bl = sdesc_at(dbase, st + 2u * a_tile_bytes + b_tile_bytes);
+        if (elect_one()) {
           for (int k4 = 0; k4 < ksteps; k4++) {             // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr >> 4) field
             const uint64_t o = (uint64_t)(k4 * 2);
             const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
-            mma_bf16(acc, ah + o, bh + o, idesc, first);                       // main products
-            mma_bf16(acc + (uint32_t)g.BN, al + o, bh + o, idesc, first);      // corrections: separate accumulator
-            mma_bf16(acc + (uint32_t)g.BN, ah + o, bl + o, idesc, 1u);         //  (tensor-core fp32 accumulation truncates)
+            mma_bf16(acc, ah + o, bh + o, idesc, first);         // main products
+            mma_bf16(acc2, al + o, bh + o, idesc, first);        // corrections: separate accumulator
+            mma_bf16(acc2, ah + o, bl + o, idesc, 1u);           //  (tensor-core fp32 accumulation truncates)
           }
           umma_commit(empty_bar(s));                  // frees the smem stage when these MMAs retire
+          if (kb == g.kblocks - 1) umma_commit(accf_bar(buf));
         }
-        umma_commit(accf_bar(buf));
+        __syncwarp();
       }
     }
   } else {
@@ -234,13 +249,13 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const int grp = row_local / g.rt.Rb, b_in = row_local - grp * g.rt.Rb;
     const int fl = grp / g.rt.Ab, al = grp - fl * g.rt.Ab;
     int lt = 0, n0_staged = -1;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
-      const long long mt = t / g.n_tiles; const int n0 = (int)(t - mt * g.n_tiles) * g.BN;
-      if (g.bias0 && n0 != n0_staged) {             // (bias0 + bias1 + bias2)[n % bias_mod] for this tile's columns
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
+      const int mt = t / g.n_tiles; const int n0 = (t - mt * g.n_tiles) * g.BN;
+      if (n0 != n0_staged) {                        // (bias0 + bias1 + bias2)[n % bias_mod] for this tile's columns (0 without bias)
         asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's readers are done
         for (int c = et; c < g.BN; c += 128) {
           const int n = n0 + c; float b = 0.f;
-          if (n < g.N) {
+          if (g.bias0 && n < g.N) {
             const int bi = n % g.bias_mod;
             b = g.bias0[bi]; if (g.bias1) b += g.bias1[bi]; if (g.bias2) b += g.bias2[bi];
           }
@@ -250,15 +265,19 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         n0_staged = n0;
       }
       const int buf = lt % g.acc_sets; const uint32_t aph = (uint32_t)((lt / g.acc_sets) & 1);
-      int a0; long long f0; tile_coords(g.rt, mt, a0, f0);
+      int a0, f0; tile_coords(g.rt, mt, a0, f0);
       const long long f = f0 + fl; const int a = a0 + al;
       const bool row_ok = (row_local < g.rt.rows_tile) && (f < g.rt.frames) && (a < g.rt.Ra);
-      float* cp = nullptr; uint16_t* chp = nullptr; int inf = 0;
+      float* cp = nullptr; uint16_t* chp = nullptr;
+      int n_lo = 0, n_hi = 0; bool al16 = false;      // this row's valid columns [n_lo, n_hi); 16-byte aligned chunks
       if (row_ok) {
         const int j = a * g.rt.Rb + b_in;
-        inf = j * g.C.rs + g.C.off;
+        const int inf = j * g.C.rs + g.C.off;
         cp = g.C.p + f * g.C.fs + inf;
         chp = reinterpret_cast<uint16_t*>(g.C.p) + f * 2 * g.C.fs + inf;
+        n_hi = g.N;
+        if (g.C.pred) { n_lo = inf < 0 ? -inf : 0; if (g.C.flen - inf < n_hi) n_hi = g.C.flen - inf; }
+        al16 = g.C.split ? ((((inf + n0) & 7) == 0) && ((g.C.fs & 7) == 0)) : ((reinterpret_cast<uintptr_t>(cp + n0) & 15) == 0);
       }
       mbar_wait(accf_bar(buf), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -268,40 +287,36 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         tmem_ld16(acc + (uint32_t)c0, v);
         tmem_ld16(acc + (uint32_t)(g.BN + c0), w);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!row_ok) continue;
+        const int nb = n0 + c0;
+        if (!row_ok || nb >= n_hi || nb + 16 <= n_lo) continue;
+        float o[16];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const int nb = n0 + c0 + q * 4;
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            float tt = __uint_as_float(v[q * 4 + e]) + __uint_as_float(w[q * 4 + e]);
-            if (g.bias0) tt += bias_s[c0 + q * 4 + e];
-            o[e] = tt;
-          }
-          bool full = (nb + 4 <= g.N);
-          if (g.C.pred) full = full && (inf + nb >= 0) && (inf + nb + 4 <= g.C.flen);
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * q);
+          o[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + __uint_as_float(w[4 * q + 0]) + b4.x;
+          o[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + __uint_as_float(w[4 * q + 1]) + b4.y;
+          o[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + __uint_as_float(w[4 * q + 2]) + b4.z;
+          o[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + __uint_as_float(w[4 * q + 3]) + b4.w;
+        }
+        if (al16 && nb >= n_lo && nb + 16 <= n_hi) {                        // the common case: whole aligned chunk
           if (g.C.split) {
-            if (full && (((inf + nb) & 3) == 0)) split_st4(chp + nb, g.C.fs, make_float4(o[0], o[1], o[2], o[3]));
-            else {
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const int n = nb + e;
-                bool ok = n < g.N;
-                if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
-                if (ok) split_st1(chp + n, g.C.fs, o[e]);
-              }
+            for (int h8 = 0; h8 < 2; h8++) {
+              uint4 hh, ll;
+              hh.x = split_pack2(o[8 * h8 + 0], o[8 * h8 + 1], ll.x); hh.y = split_pack2(o[8 * h8 + 2], o[8 * h8 + 3], ll.y);
+              hh.z = split_pack2(o[8 * h8 + 4], o[8 * h8 + 5], ll.z); hh.w = split_pack2(o[8 * h8 + 6], o[8 * h8 + 7], ll.w);
+              *reinterpret_cast<uint4*>(chp + nb + 8 * h8) = hh; *reinterpret_cast<uint4*>(chp + g.C.fs + nb + 8 * h8) = ll;
             }
-          } else if (full && ((reinterpret_cast<uintptr_t>(cp + nb) & 15) == 0)) {
-            *reinterpret_cast<float4*>(cp + nb) = make_float4(o[0], o[1], o[2], o[3]);
           } else {
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int n = nb + e;
-              bool ok = n < g.N;
-              if (g.C.pred) ok = ok && (inf + n >= 0) && (inf + n < g.C.flen);
-              if (ok) cp[n] = o[e];
-            }
+            for (int q = 0; q < 4; q++)
+              *reinterpret_cast<float4*>(cp + nb + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          }
+        } else {                                                              // edges: N tail, predicated range, odd alignment
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            const int n = nb + e;
+            if (n >= n_lo && n < n_hi) { if (g.C.split) split_st1(chp + n, g.C.fs, o[e]); else cp[n] = o[e]; }
           }
         }
       }
@@ -348,10 +363,10 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * g.BN;
-  const long long t_begin = (long long)blockIdx.z * g.tiles_per_split;
-  long long t_end = t_begin + g.tiles_per_split; if (t_end > g.rt.m_tiles) t_end = g.rt.m_tiles;
+  const int t_begin = (int)blockIdx.z * g.tiles_per_split;
+  int t_end = t_begin + g.tiles_per_split; if (t_end > g.rt.m_tiles) t_end = g.rt.m_tiles;
   if (t_begin >= t_end) return;                       // uniform per CTA
-  const int ntl = (int)(t_end - t_begin);
+  const int ntl = t_end - t_begin;
 
   // rows of a box region beyond the TMA box are never written: they must read as zero
   if (g.rows_al > g.rt.rows_tile) {
@@ -375,49 +390,53 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const uint32_t tx = 2u * (2u * (uint32_t)g.rt.rows_tile * 128u + (uint32_t)d_boxes * (uint32_t)g.rt.rows_tile * (uint32_t)g.d_sw);
-      for (int i = 0; i < ntl; i++) {
-        const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
-        int a0; long long f0; tile_coords(g.rt, t_begin + i, a0, f0);
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+    // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
+    const uint32_t tx = 2u * (2u * (uint32_t)g.rt.rows_tile * 128u + (uint32_t)d_boxes * (uint32_t)g.rt.rows_tile * (uint32_t)g.d_sw);
+    for (int i = 0; i < ntl; i++) {
+      const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
+      int a0, f0; tile_coords(g.rt, t_begin + i, a0, f0);
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+      if (elect_one()) {
         mbar_expect_tx(full_bar(s), tx);
 #pragma unroll
         for (int b = 0; b < 2; b++) {
-          tma_load_4d(st + (uint32_t)b * a_region, &tmAh, full_bar(s), m0 + 64 * b, 0, a0, (int)f0);
-          tma_load_4d(st + a_plane + (uint32_t)b * a_region, &tmAl, full_bar(s), m0 + 64 * b, 0, a0, (int)f0);
+          tma_load_4d(st + (uint32_t)b * a_region, &tmAh, full_bar(s), m0 + 64 * b, 0, a0, f0);
+          tma_load_4d(st + a_plane + (uint32_t)b * a_region, &tmAl, full_bar(s), m0 + 64 * b, 0, a0, f0);
         }
         for (int b = 0; b < d_boxes; b++) {
-          tma_load_4d(st + 2u * a_plane + (uint32_t)b * d_region, &tmDh, full_bar(s), n0 + dw * b, 0, a0, (int)f0);
-          tma_load_4d(st + 2u * a_plane + d_plane + (uint32_t)b * d_region, &tmDl, full_bar(s), n0 + dw * b, 0, a0, (int)f0);
+          tma_load_4d(st + 2u * a_plane + (uint32_t)b * d_region, &tmDh, full_bar(s), n0 + dw * b, 0, a0, f0);
+          tma_load_4d(st + 2u * a_plane + d_plane + (uint32_t)b * d_region, &tmDl, full_bar(s), n0 + dw * b, 0, a0, f0);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(g.BN, true);
-      const int ksteps = g.rows_al >> 4;
-      for (int i = 0; i < ntl; i++) {
-        const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
-        mbar_wait(full_bar(s), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-        for (int ks = 0; ks < ksteps; ks++) {               // 16 view rows per MMA
-          const uint32_t ao = (uint32_t)ks * 16u * 128u, dof = (uint32_t)ks * 16u * (uint32_t)g.d_sw;
-          const uint64_t ah = make_sdesc(st + ao, a_region, 128), al = make_sdesc(st + a_plane + ao, a_region, 128);
-          const uint64_t dh = make_sdesc(st + 2u * a_plane + dof, d_region, (uint32_t)g.d_sw);
-          const uint64_t dl = make_sdesc(st + 2u * a_plane + d_plane + dof, d_region, (uint32_t)g.d_sw);
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
+    const uint32_t idesc = make_idesc(g.BN, true);
+    const int ksteps = g.rows_al >> 4;
+    const uint64_t abase = sdesc_base(a_region, 128), dbase = sdesc_base(d_region, (uint32_t)g.d_sw);
+    const uint32_t acc2 = tmem_base + (uint32_t)g.BN;
+    for (int i = 0; i < ntl; i++) {
+      const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
+      mbar_wait(full_bar(s), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+      const uint64_t ah0 = sdesc_at(abase, st), al0 = sdesc_at(abase, st + a_plane);
+      const uint64_t dh0 = sdesc_at(dbase, st + 2u * a_plane), dl0 = sdesc_at(dbase, st + 2u * a_plane + d_plane);
+      const uint64_t astep = (uint64_t)((16u * 128u) >> 4), dstep = (uint64_t)((16u * (uint32_t)g.d_sw) >> 4);   // 16 view rows per MMA
+      if (elect_one()) {
+        for (int ks = 0; ks < ksteps; ks++) {
+          const uint64_t ah = ah0 + astep * ks, al = al0 + astep * ks, dh = dh0 + dstep * ks, dl = dl0 + dstep * ks;
           const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
-          mma_bf16(tmem_base, ah, dh, idesc, first);                       // main products
-          mma_bf16(tmem_base + (uint32_t)g.BN, al, dh, idesc, first);      // corrections
-          mma_bf16(tmem_base + (uint32_t)g.BN, ah, dl, idesc, 1u);
+          mma_bf16(tmem_base, ah, dh, idesc, first);          // main products
+          mma_bf16(acc2, al, dh, idesc, first);               // corrections
+          mma_bf16(acc2, ah, dl, idesc, 1u);
         }
         umma_commit(empty_bar(s));
+        if (i == ntl - 1) umma_commit(accum_bar);
       }
-      umma_commit(accum_bar);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2-5)
