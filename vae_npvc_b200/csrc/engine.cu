@@ -210,7 +210,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + bk - 1) / bk; g.rt = rt; g.n_tiles = n_tiles; g.sw = sw;
   const int stage_bytes = 2 * 128 * sw + 2 * BN * sw;
-  g.acc_sets = (4 * BN <= 512) ? 2 : 1;                            // double-buffered accumulators when TMEM allows
+  g.acc_sets = 512 / (2 * BN); if (g.acc_sets > 4) g.acc_sets = 4; if (g.acc_sets < 1) g.acc_sets = 1;   // accumulator ring in TMEM: the epilogue of tile i overlaps the mainloops of the next tiles
   int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
   int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
   g.stages = stages;
@@ -221,7 +221,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 5) + 32 + 1024;   // + bias_s[256]
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 9) + 32 + 1024;   // + bias_s[256]
   long long total = rt.m_tiles * n_tiles;
   unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
   umma_fwd_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);

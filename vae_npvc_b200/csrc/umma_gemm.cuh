@@ -147,7 +147,7 @@ __device__ __forceinline__ uint64_t sdesc_at(uint64_t base, uint32_t saddr) { re
 // =============================================================================================
 // (F) persistent forward / dgrad kernel, 192 threads:
 //   warp 0      TMA producer (A hi, A lo, B hi, B lo per 64-wide k-block), runs ahead across tiles
-//   warp 1      TMEM allocator + MMA issuer; accumulators double-buffered in TMEM when 4*BN <= 512
+//   warp 1      TMEM allocator + MMA issuer; up to 4 accumulator sets in TMEM (512 / (2*BN) columns allow)
 //   warps 2-5   epilogue (TMEM -> registers -> bias -> fp32 or split store), overlapped with the
 //               next tile's mainloop through the accf / acce barriers
 // =============================================================================================
@@ -165,8 +165,8 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(g.stages + s); };
   auto accf_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * g.stages + b); };
-  auto acce_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * g.stages + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * g.stages + 4);
+  auto acce_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * g.stages + 4 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * g.stages + 8);
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
   float* bias_s = reinterpret_cast<float*>(gen_base + (tmem_slot - sbase) + 16);      // [256] effective bias of the current N tile
 
@@ -176,7 +176,7 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
     for (int s = 0; s < g.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+    for (int b = 0; b < 4; b++) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
