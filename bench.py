@@ -262,24 +262,37 @@ def main():
     prof = machine.engine.handle.profile()
     machine.engine.handle.profile_enable(False)
     tot_ms = sum(p["ms"] for p in prof)
-    top = max(prof, key=lambda p: p["ms"])
+    top = max(prof, key=lambda p: p["ms"])                           # the dominant kernel of the step
     gemm_like = [p for p in prof if p["kind"] in (0, 1)]
     top_ms = top["ms"] / top["calls"]
-    top_flops = 2.0 * (top["rows"] / top["calls"]) * top["K"] * top["N"] if top["kind"] in (0, 1) else 0.0
-    achieved_tf = top_flops / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))["bytes_per_launch"].get(top["name"])
-    roofline = {
-        "bound": "tensor", "kernel": top["name"], "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
-        "frac": achieved_tf / pk["tf"], "traffic": traffic, "peak_source": pk["source"] + " bf16 dense (sustained)",
-        "share_of_step": top["ms"] / tot_ms if tot_ms else None,
-        "note": "fp32 path: algorithmic FLOPs (2*rows*K*N of the dense contraction) / CUDA-event time of that op; "
-                "3xTF32 on tcgen05 caps this fraction at 1/6 of the bf16 peak",
-        "ops_ms_per_step": {p["name"]: round(p["ms"] / PS, 4) for p in sorted(prof, key=lambda p: -p["ms"])[:12]},
-        "gemm_ms_share": sum(p["ms"] for p in gemm_like) / tot_ms if tot_ms else None,
-    }
+    ops_ms = {p["name"]: round(p["ms"] / PS, 4) for p in sorted(prof, key=lambda p: -p["ms"])[:12]}
+    common = {"kernel": top["name"], "traffic": traffic, "share_of_step": top["ms"] / tot_ms if tot_ms else None,
+              "ops_ms_per_step": ops_ms, "gemm_ms_share": sum(p["ms"] for p in gemm_like) / tot_ms if tot_ms else None}
+    if top.get("tensor"):
+        # tcgen05 op: algorithmic FLOPs of the dense contraction (2*rows*K*N) / CUDA-event time of the op
+        top_flops = 2.0 * (top["rows"] / top["calls"]) * top["K"] * top["N"]
+        achieved = top_flops / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
+        roofline = dict(bound="tensor", achieved=achieved, peak=pk["tf"], unit="TFLOP/s", frac=achieved / pk["tf"],
+                        peak_source=pk["source"] + " bf16 dense (sustained)",
+                        note="fp32 path on bf16 tensor cores: every product is 3 bf16 MMAs (hi.hi + hi.lo + lo.hi), "
+                             "so 1/3 of the bf16 peak is the ceiling of this fraction", **common)
+    else:
+        # CUDA-core / streaming op: algorithmic bytes (every operand buffer once) / CUDA-event time of the op
+        achieved = top["bytes"] / top["calls"] / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
+        roofline = dict(bound="hbm", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
+                        peak_source=pk["source"] + " copy bandwidth",
+                        note="algorithmic bytes = each operand buffer of the op read / written once", **common)
+    # the largest tensor-core op as well, for the record
+    tens = [p for p in prof if p.get("tensor")]
+    if tens:
+        tt = max(tens, key=lambda p: p["ms"]); tms = tt["ms"] / tt["calls"]
+        tf = 2.0 * (tt["rows"] / tt["calls"]) * tt["K"] * tt["N"] / (tms * 1e-3) / 1e12
+        roofline["top_tensor_op"] = {"kernel": tt["name"], "achieved_tflops": tf, "frac_of_bf16_peak": tf / pk["tf"],
+                                     "frac_of_bf16x3_ceiling": 3.0 * tf / pk["tf"]}
     fps_gpu = value / world
     extra = {
         "flop_per_frame": FLOP_PER_FRAME_TRAIN, "achieved_tflops_whole_step": fps_gpu * FLOP_PER_FRAME_TRAIN / 1e12,

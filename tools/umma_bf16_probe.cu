@@ -28,6 +28,7 @@ struct Cfg {
   uint32_t b_box_bytes; int b_boxes;
   int a_sw, b_sw;       // swizzle span in bytes (128 / 64 / 32)
   uint32_t a_region, b_region;   // smem stride between boxes (>= box bytes, multiple of 1024)
+  int row_shift;        // F form: the A descriptor starts row_shift rows into the loaded tile (tap of a stride-1 window)
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, int sw) {
@@ -78,7 +79,7 @@ __global__ void probe(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int ks = 0; ks < c.ksteps; ks++) {
       uint64_t ad, bd;
       if (!c.wform) {   // K-major: 16 bf16 = 32 bytes along the swizzled row per k-step
-        ad = make_desc(a_s + ks * 32, 0, 8 * c.a_sw, c.a_sw);
+        ad = make_desc(a_s + ks * 32 + c.row_shift * c.a_sw, 0, 8 * c.a_sw, c.a_sw);
         bd = make_desc(b_s + ks * 32, 0, 8 * c.b_sw, c.b_sw);
       } else {          // MN-major: 16 rows of the box per k-step; LBO = next MN block (box), SBO = next 8-row group
         ad = make_desc(a_s + ks * 16 * c.a_sw, c.a_region, 8 * c.a_sw, c.a_sw);
@@ -141,7 +142,7 @@ static int run_w(int rows, int Kw, int Nw, int N, int a_sw, int b_sw, int lda, i
   const int a_el = a_sw / 2, b_el = b_sw / 2;
   if (enc2d(&tA, dA, Kw, rows, (uint64_t)lda * 2, a_el, rows, a_sw)) return 1;
   if (enc2d(&tB, dD, Nw, rows, (uint64_t)ldd * 2, b_el, rows, b_sw)) return 1;
-  Cfg c; c.wform = 1; c.N = N; c.ksteps = (rows + 15) / 16;
+  Cfg c; c.wform = 1; c.N = N; c.ksteps = (rows + 15) / 16; c.row_shift = 0;
   c.a_boxes = 128 / a_el; c.b_boxes = (N + b_el - 1) / b_el;
   c.a_box_bytes = rows * a_sw; c.b_box_bytes = rows * b_sw;
   c.a_sw = a_sw; c.b_sw = b_sw;
@@ -159,16 +160,16 @@ static int run_w(int rows, int Kw, int Nw, int N, int a_sw, int b_sw, int lda, i
   return 0;
 }
 
-// F form: A[rows<=128][K], B[N][K]
-static int run_f(int rows, int K, int N, int sw) {
+// F form: A[rows<=128][K], B[N][K]; shift: output row m uses A row m + shift (rows - shift valid outputs)
+static int run_f(int rows, int K, int N, int sw, int shift = 0) {
   const int kel = sw / 2;    // k elements per box row
   std::vector<__nv_bfloat16> A((size_t)rows * K), B((size_t)N * K);
   for (auto& v : A) v = __float2bfloat16(rnd());
   for (auto& v : B) v = __float2bfloat16(rnd());
   const int Kc = K < kel ? K : kel;
   std::vector<float> R(128 * N, 0.f), O(128 * N);
-  for (int m = 0; m < rows; m++) for (int n = 0; n < N; n++) {
-    double s = 0; for (int k = 0; k < Kc; k++) s += (double)__bfloat162float(A[(size_t)m * K + k]) * __bfloat162float(B[(size_t)n * K + k]);
+  for (int m = 0; m + shift < rows; m++) for (int n = 0; n < N; n++) {
+    double s = 0; for (int k = 0; k < Kc; k++) s += (double)__bfloat162float(A[(size_t)(m + shift) * K + k]) * __bfloat162float(B[(size_t)n * K + k]);
     R[m * N + n] = (float)s;
   }
   __nv_bfloat16 *dA, *dB; float* dO;
@@ -178,7 +179,7 @@ static int run_f(int rows, int K, int N, int sw) {
   CUtensorMap tA, tB;
   if (enc2d(&tA, dA, K, rows, (uint64_t)K * 2, kel, rows, sw)) return 1;
   if (enc2d(&tB, dB, K, N, (uint64_t)K * 2, kel, N, sw)) return 1;
-  Cfg c; c.wform = 0; c.N = N; c.ksteps = kel / 16; c.a_boxes = 1; c.b_boxes = 1;
+  Cfg c; c.wform = 0; c.N = N; c.ksteps = kel / 16; c.a_boxes = 1; c.b_boxes = 1; c.row_shift = shift;
   c.a_box_bytes = rows * sw; c.b_box_bytes = N * sw; c.a_sw = c.b_sw = sw;
   c.a_region = 128 * sw; c.b_region = ((uint32_t)(N * sw) + 1023u) & ~1023u;
   size_t smem = (size_t)c.a_region + c.b_region + 2048;
@@ -188,8 +189,8 @@ static int run_f(int rows, int K, int N, int sw) {
   if (e != cudaSuccess) { printf("F rows=%d K=%d N=%d: CUDA error %s\n", rows, K, N, cudaGetErrorString(e)); return 1; }
   cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
   double err = 0, mx = 0;
-  for (size_t i = 0; i < O.size(); i++) { double d = fabs((double)O[i] - R[i]); if (!(d <= err)) err = d; mx = fmax(mx, fabs(R[i])); }
-  printf("F form rows=%3d K=%3d N=%3d sw=%3d: max|err| %.3e (max|ref| %.3e)\n", rows, K, N, sw, err, mx);
+  for (size_t i = 0; i < (size_t)(rows - shift) * N; i++) { double d = fabs((double)O[i] - R[i]); if (!(d <= err)) err = d; mx = fmax(mx, fabs(R[i])); }
+  printf("F form rows=%3d K=%3d N=%3d sw=%3d shift=%d: max|err| %.3e (max|ref| %.3e)\n", rows, K, N, sw, shift, err, mx);
   cudaFree(dA); cudaFree(dB); cudaFree(dO);
   return 0;
 }
@@ -204,6 +205,8 @@ int main() {
   rc |= run_f(128, 64, 64, 128);
   rc |= run_f(114, 48, 32, 128);       // rows < 128 (zeroed tail), K < 64 (TMA zero fill)
   rc |= run_f(128, 32, 64, 64);        // 64-byte swizzle, 32-element k-block
+  for (int sh = 1; sh <= 3; sh++) { rc |= run_f(128, 64, 64, 128, sh); rc |= run_f(120, 32, 48, 64, sh); rc |= run_f(118, 16, 32, 32, sh); }
+  rc |= run_f(128, 64, 64, 128, 9);
   rc |= run_w(64, 128, 64, 64, 128, 128, 128, 64);
   rc |= run_w(128, 128, 128, 128, 128, 128, 136, 136);
   rc |= run_w(114, 48, 24, 32, 128, 64, 48, 24);    // G2-like: Kw=48 (second A box fully OOB), Nw=24 in a 64-byte box

@@ -41,7 +41,7 @@ struct npvc_handle {
   int64_t umma_launches = 0;
   int umma_min_stages = 0;           // NPVC_UMMA_MIN_STAGES (experiments): below this many 64-wide k-block stages use 32-wide ones (measured slower: more TMA row requests)
   bool profiling = false;
-  struct Ev { int op; cudaEvent_t a, b; long long rows; };
+  struct Ev { int op; cudaEvent_t a, b; long long rows, frames; };
   std::vector<Ev> events;
   std::string profile_json;
 };
@@ -464,7 +464,7 @@ int run_phase(Ctx& c, int phase) {
     const Op& o = ops[i];
     if (o.phase != phase) continue;
     if (!c.grad && (o.kind == OP_UNPACK)) continue;
-    npvc_handle::Ev ev{(int)i, nullptr, nullptr, 0};
+    npvc_handle::Ev ev{(int)i, nullptr, nullptr, 0, c.n};
     if (c.h->profiling) {
       cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
       ev.rows = (o.kind == OP_GEMM || o.kind == OP_WGRAD) ? (o.rows_fixed ? o.rows_fixed : c.n * o.A.R) : c.n;
@@ -594,19 +594,29 @@ int npvc_profile_enable(npvc_handle* h, int32_t enable) {
 const char* npvc_profile_json(npvc_handle* h) {
   if (!h) return "[]";
   const std::vector<Op>& ops = h->plan.ops;
-  std::vector<double> ms(ops.size(), 0.0); std::vector<long long> calls(ops.size(), 0), rows(ops.size(), 0);
+  std::vector<double> ms(ops.size(), 0.0); std::vector<long long> calls(ops.size(), 0), rows(ops.size(), 0), frames(ops.size(), 0);
   for (auto& e : h->events) {
     cudaEventSynchronize(e.b);
     float t = 0.f; cudaEventElapsedTime(&t, e.a, e.b);
-    ms[e.op] += t; calls[e.op]++; rows[e.op] += e.rows;
+    ms[e.op] += t; calls[e.op]++; rows[e.op] += e.rows; frames[e.op] += e.frames;
     cudaEventDestroy(e.a); cudaEventDestroy(e.b);
   }
   h->events.clear();
   std::string js = "["; bool first = true; char buf[512];
   for (size_t i = 0; i < ops.size(); i++) {
     if (!calls[i]) continue;
-    snprintf(buf, sizeof buf, "%s{\"name\":\"%s\",\"kind\":%d,\"calls\":%lld,\"ms\":%.6f,\"rows\":%lld,\"K\":%d,\"N\":%d}",
-             first ? "" : ",", ops[i].name.c_str(), ops[i].kind, calls[i], ms[i], rows[i], ops[i].K, ops[i].N);
+    // algorithmic (compulsory) bytes of the op, summed over its calls: every operand buffer once
+    const Op& o = ops[i]; const Plan& p = h->plan;
+    auto frame_floats = [&](const Ref& r) -> double { return r.space == SP_WS ? (double)p.bufs[r.buf].per_frame : 0.0; };
+    double per_frame = 0.0, fixed = 0.0;
+    if (o.kind == OP_GEMM) { per_frame = frame_floats(o.A.ref) + (o.A.ref.space == SP_USER ? p.arch.in_h : 0) + frame_floats(o.C.ref); fixed = (double)o.K * o.N; }
+    else if (o.kind == OP_WGRAD) { per_frame = frame_floats(o.A.ref) + (o.A.ref.space == SP_USER ? p.arch.in_h : 0) + frame_floats(o.C.ref); fixed = (double)o.K * o.N; }
+    else if (o.kind == OP_LN_FWD) per_frame = o.L + o.out_flen;
+    else if (o.kind == OP_LN_BWD) per_frame = 2.0 * o.L + o.out_flen;
+    const double bytes = 4.0 * (per_frame * (double)frames[i] + fixed * (double)calls[i]);
+    const bool tensor = o.umma && umma_allowed(h, o);
+    snprintf(buf, sizeof buf, "%s{\"name\":\"%s\",\"kind\":%d,\"calls\":%lld,\"ms\":%.6f,\"rows\":%lld,\"K\":%d,\"N\":%d,\"tensor\":%d,\"bytes\":%.0f}",
+             first ? "" : ",", o.name.c_str(), o.kind, calls[i], ms[i], rows[i], o.K, o.N, tensor ? 1 : 0, bytes);
     js += buf; first = false;
   }
   js += "]";
