@@ -39,6 +39,7 @@ struct npvc_handle {
   struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile, sw; CUtensorMap tAh, tAl, tBh, tBl; };
   std::map<int, TMaps> tmaps;        // per-op tensor-map cache
   int64_t umma_launches = 0;
+  int umma_tap = 1;                  // NPVC_UMMA_TAP=0: conv-shaped layers through the overlapping-window boxes (A/B comparisons)
   int umma_min_stages = 0;           // NPVC_UMMA_MIN_STAGES (experiments): below this many 64-wide k-block stages use 32-wide ones (measured slower: more TMA row requests)
   bool profiling = false;
   struct Ev { int op; cudaEvent_t a, b; long long rows, frames; };
@@ -155,6 +156,7 @@ RowTiling make_tiling(int R, long long frames, int row_target) {
   if (t.Ra == 1) { t.FB = row_target / t.Rb; if (t.FB < 1) t.FB = 1; t.Ab = 1; }
   else { t.FB = 1; t.Ab = row_target / t.Rb; if (t.Ab < 1) t.Ab = 1; if (t.Ab > t.Ra) t.Ab = t.Ra; }
   t.TA = (t.Ra + t.Ab - 1) / t.Ab;
+  t.RbH = t.Rb;
   t.rows_tile = t.Rb * t.Ab * t.FB;
   t.frames = (int)frames; t.m_tiles = (int)(((frames + t.FB - 1) / t.FB) * t.TA);
   return t;
@@ -178,9 +180,89 @@ int make_view_maps(npvc_handle* h, const Ctx& c, const View& v, int extent, cons
   return NPVC_OK;
 }
 
+// Tap mode of the forward kernel (umma_gemm.cuh): eligible when the view is a conv window with 16 / 32 / 64
+// channels per tap, one N tile, and the weights of all taps plus >= 2 activation stages fit shared memory.
+struct TapGeom { bool ok; int sw, P, hr, BN, b_tile_al, stages; RowTiling rt; };
+TapGeom tap_geometry(const Op& o, long long frames) {
+  TapGeom t; memset(&t, 0, sizeof t);
+  const int C = o.tap_C, T = o.tap_T, s = o.tap_s;
+  if (T <= 0 || !(C == 16 || C == 32 || C == 64) || o.N > 256 || o.A.R < 2 || o.A.rs != s * C || o.K != T * C) return t;
+  t.sw = 2 * C; t.P = s; t.hr = (T - 1) / s;
+  t.BN = (o.N + 15) / 16 * 16;
+  t.b_tile_al = (t.BN * t.sw + 1023) / 1024 * 1024;
+  RowTiling& r = t.rt;
+  r.Rb = umma_row_tile(o.A.R); if (r.Rb <= 0) return t;
+  r.Ra = o.A.R / r.Rb; r.RbH = r.Rb + t.hr;
+  if (r.RbH > 128) return t;
+  if (r.Ra == 1) { r.FB = 128 / r.RbH; r.Ab = 1; } else { r.FB = 1; r.Ab = 128 / r.RbH; if (r.Ab > r.Ra) r.Ab = r.Ra; }
+  r.TA = (r.Ra + r.Ab - 1) / r.Ab;
+  r.rows_tile = r.RbH * r.Ab * r.FB;
+  r.frames = (int)frames; r.m_tiles = (int)(((frames + r.FB - 1) / r.FB) * r.TA);
+  const int bres = T * 2 * t.b_tile_al, stage = t.P * 2 * 128 * t.sw;
+  t.stages = (225 * 1024 - 4096 - bres) / stage; if (t.stages > 8) t.stages = 8;
+  t.ok = t.stages >= 2;
+  return t;
+}
+
+int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
+  npvc_handle* h = c.h; cudaStream_t st = c.st;
+  const RowTiling& rt = tg.rt; const int BN = tg.BN, sw = tg.sw, C = o.tap_C;
+  const void* a_base = resolve(c, o.A.ref);
+  uint16_t* arena16 = reinterpret_cast<uint16_t*>(c.ws + h->plan.aw16_off);
+  uint16_t* b_hi = arena16 + o.bu_hi; uint16_t* b_lo = arena16 + o.bu_lo;
+  auto it = h->tmaps.find(op_index);
+  if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != rt.frames || it->second.bn != BN || it->second.sw != -sw) {
+    npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = rt.frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = -sw;   // (negative: tap-mode maps)
+    // A: (column within the s*C wide position group, row-in-group incl. halo, row-group, frame); groups overlap by the halo
+    uint16_t* base = reinterpret_cast<uint16_t*>(resolve(c, o.A.ref)) + o.A.off;
+    const cuuint64_t fsb = (cuuint64_t)o.A.fs * 4;
+    cuuint64_t gd[4] = {(cuuint64_t)(o.tap_s * C), (cuuint64_t)rt.RbH, (cuuint64_t)rt.Ra, (cuuint64_t)rt.frames};
+    cuuint64_t gs[3] = {(cuuint64_t)o.A.rs * 2, rt.Ra == 1 ? fsb : (cuuint64_t)rt.Rb * o.A.rs * 2, fsb};
+    cuuint32_t bx[4] = {(cuuint32_t)C, (cuuint32_t)rt.RbH, (cuuint32_t)rt.Ab, (cuuint32_t)rt.FB};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle swz = sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    for (int w = 0; w < 2; w++) {
+      CUresult r = h->encode(w ? &tm.tAl : &tm.tAh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base + (w ? o.A.fs : 0), gd, gs, bx, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(tap A) failed for " + o.name + " code " + std::to_string((int)r));
+    }
+    cuuint64_t gdB[2] = {(cuuint64_t)o.kpad, (cuuint64_t)o.N};
+    cuuint64_t gsB[1] = {(cuuint64_t)o.kpad * 2};
+    cuuint32_t bxB[2] = {(cuuint32_t)C, (cuuint32_t)BN};
+    for (int w = 0; w < 2; w++) {
+      CUresult r = h->encode(w ? &tm.tBl : &tm.tBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w ? b_lo : b_hi, gdB, gsB, bxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(tap B) failed for " + o.name + " code " + std::to_string((int)r));
+    }
+    h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
+  }
+  UmmaArgs g; memset(&g, 0, sizeof g);
+  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = 1; g.rt = rt; g.n_tiles = 1; g.sw = sw;
+  g.tapT = o.tap_T; g.tapC = C; g.tapP = tg.P; g.b_tile_al = tg.b_tile_al;
+  g.acc_sets = 512 / (2 * BN); if (g.acc_sets > 4) g.acc_sets = 4; if (g.acc_sets < 1) g.acc_sets = 1;
+  int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
+  g.stages = tg.stages;
+  g.C = dview(c, o.C);
+  g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 1024;
+  unsigned grid = (unsigned)(rt.m_tiles < h->sm_count ? rt.m_tiles : h->sm_count);
+  umma_fwd_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  h->launches++; h->umma_launches++;
+  return NPVC_OK;
+}
+
 int launch_umma(Ctx& c, const Op& o, int op_index) {
   npvc_handle* h = c.h; cudaStream_t st = c.st;
   const long long frames = c.n;
+  if (h->umma_tap) {
+    const TapGeom tg = tap_geometry(o, frames);
+    if (tg.ok) return launch_umma_tap(c, o, op_index, tg);
+  }
   int n_tiles = 1; const int BN = pick_bn(o.N, &n_tiles);
   const RowTiling rt = make_tiling(o.A.R, frames, 128);
   // k-block: 64 bf16 (128-byte swizzled rows) when >= 4 such stages fit, else 32 (64-byte rows): the
@@ -221,7 +303,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 9) + 32 + 1024;   // + bias_s[256]
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 1024;   // + bias_s[256]
   long long total = rt.m_tiles * n_tiles;
   unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
   umma_fwd_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
@@ -338,7 +420,11 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       g.rows = o.rows_fixed ? o.rows_fixed : c.n * o.A.R;
       g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
       if (g.rows <= 0) break;
-      if (umma_allowed(h, o)) { int rc = launch_umma(c, o, op_index); if (rc) return rc; break; }
+      const bool row_shaped = !g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && !o.rows_fixed && !g.C.split && !(g.A.split && g.A.pred);
+      // few-tap, few-channel layers over millions of rows: through the overlapping-window boxes of the generic tensor
+      // kernel they cost more than the thread-per-row FFMA kernel (measured) -- tensor cores only in tap mode
+      const bool tensor_ok = umma_allowed(h, o) && (!row_shaped || (h->umma_tap && tap_geometry(o, c.n).ok));
+      if (tensor_ok) { int rc = launch_umma(c, o, op_index); if (rc) return rc; break; }
       if (o.rows_fixed && o.rows_fixed <= 16 && !g.bias0 && o.C.ref.space == SP_GRAD && !g.A.pred && g.A.R == 1 && g.C.R == 1 && o.K >= 256) {
         // few-row GEMM accumulated into the (zero-initialised) gradient buffer
         const int kchunk = 128, ks = (o.K + kchunk - 1) / kchunk;
@@ -347,7 +433,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
             g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, kchunk);
         h->launches++; break;
       }
-      if (!g.bias1 && !g.bias2 && o.K <= 64 && o.N <= 32 && !o.rows_fixed && !g.C.split && !(g.A.split && g.A.pred)) {     // (independent of n: per-frame results must not depend on the batch size)
+      if (row_shaped) {     // (independent of n: per-frame results must not depend on the batch size)
         RowGemmArgs rg; rg.A = g.A; rg.K = o.K; rg.B = g.B; rg.ldb = o.ldb; rg.N = o.N; rg.C = g.C; rg.rows = g.rows;
         rg.bias0 = g.bias0; rg.bias_mod = o.bias_mod;
         const bool sc = !view_vec_ok(g.A) || (o.K % 4 != 0);
@@ -530,6 +616,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   const char* eu = getenv("NPVC_UMMA");            // "0" = CUDA-core GEMMs only (debug / A-B comparisons)
   h->use_umma = !(eu && eu[0] == '0');
   if (const char* ms = getenv("NPVC_UMMA_MIN_STAGES")) h->umma_min_stages = atoi(ms);
+  if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
   const char* ea = getenv("NPVC_UMMA_OPS");
   if (ea) h->umma_allow = ea;
   std::string err = build_plan(*arch, h->plan, h->use_umma);

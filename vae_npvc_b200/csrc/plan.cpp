@@ -392,6 +392,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     snprintf(nm, sizeof nm, "conv_e%d", e);
     Op& o = B.op(OP_GEMM, PH_ENC, nm);
     o.A = VA_e[e]; o.K = l.k * l.Ci; o.a_scalar = (e == 0); o.B = B.aw(A_we[e]); o.ldb = l.Co; o.N = l.Co;
+    o.tap_T = l.k; o.tap_C = l.Ci; o.tap_s = l.s;
     o.C = B.view(B.ws(b_ce[e]), l.Ho, l.Ho * l.Co, l.Co, 0, l.Ho * l.Co);
     o.bias[0] = B.th(poff(P_eb[e])); o.bias_mod = l.Co;
     snprintf(nm, sizeof nm, "ln_e%d", e);
@@ -431,6 +432,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     if (!l.dense) {
       VA_g[g] = B.view(src, l.Hi, sflen, l.Cip, 0, sflen);
       o.A = VA_g[g]; o.K = l.wn * l.Cip; o.B = B.aw(A_gf[g]); o.ldb = ld_gf[g]; o.N = l.s * l.Co;
+      o.tap_T = l.wn; o.tap_C = l.Cip; o.tap_s = 1;
       o.C = B.view(B.ws(b_cg[g]), l.Hi, l.Ho * l.Co, l.s * l.Co, 0, l.Ho * l.Co);
       o.bias[0] = B.th(poff(P_gb[g])); o.bias_mod = l.Co;
       snprintf(nm, sizeof nm, "ln_g%d", g);
@@ -477,6 +479,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     snprintf(nm, sizeof nm, "dgrad_g%d", g);
     Op& o = B.op(OP_GEMM, PH_BWD, nm);
     o.A = B.view(B.ws(b_dcg[g]), l.Hi, dcg_flen[g], l.s * l.Co, 0, dcg_flen[g]); o.K = l.k * l.Co;
+    o.tap_T = l.k; o.tap_C = l.Co; o.tap_s = l.s;
     o.B = B.aw(A_gd[g]); o.ldb = ld_gd[g]; o.N = l.Cip;
     Ref dst = (g > 0) ? B.ws(b_dag[g - 1]) : B.ws(b_dhm);
     o.C = B.view(dst, l.Hi, l.Hi * l.Cip, l.Cip, 0, l.Hi * l.Cip);
@@ -517,6 +520,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
       int R = e_q1[e] - e_q0[e] + 1;
       o.A = B.view(B.ws(b_dce[e]), R, dce_flen[e], l.Co, (e_q0[e] - (e_wn[e] - 1) + e_pf[e]) * l.Co, dce_flen[e]);
       o.K = e_wn[e] * l.Co; o.B = B.aw(A_ed[e]); o.ldb = l.s * l.Ci; o.N = l.s * l.Ci;
+      o.tap_T = e_wn[e]; o.tap_C = l.Co; o.tap_s = 1;
       o.C = B.view(B.ws(b_dae[e - 1]), R, l.Hi * l.Ci, l.s * l.Ci, (l.s * e_q0[e] - l.pl) * l.Ci, l.Hi * l.Ci, 1);
     }
   }
@@ -554,9 +558,6 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
         continue;
       }
       if (o.kind != OP_GEMM || !view_ok(o.A) || o.K < 8 || o.N < 8 || o.B.space != SP_AW) continue;
-      // few-tap, few-channel layers over millions of rows (the last stride-3 transposed conv): the overlapping
-      // window boxes cost more TMA row requests than the thread-per-row FFMA kernel costs (measured)
-      if (o.K <= 64 && o.N <= 32) continue;
       o.kpad = rup(o.K, 8);
       const int64_t sz = (int64_t)o.N * o.kpad;
       o.bu_hi = a16_alloc(sz); o.bu_lo = a16_alloc(sz);
@@ -603,7 +604,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     js << ","; json_ref(js, "bias2", o.bias[2]); js << ",\"bias_mod\":" << o.bias_mod << ",";
     js << "\"rows_fixed\":" << o.rows_fixed
        << ",\"a_scalar\":" << o.a_scalar << ",\"umma\":" << o.umma << ",\"bu_hi\":" << o.bu_hi << ",\"bu_lo\":" << o.bu_lo
-       << ",\"kpad\":" << o.kpad << ",";
+       << ",\"kpad\":" << o.kpad << ",\"tap\":[" << o.tap_T << "," << o.tap_C << "," << o.tap_s << "],";
     json_ref(js, "in", o.in); js << ","; json_ref(js, "xhat", o.xhat); js << ","; json_ref(js, "aout", o.aout); js << ",";
     json_ref(js, "rstd", o.rstd); js << ","; json_ref(js, "gamma", o.gamma); js << ","; json_ref(js, "beta", o.beta); js << ",";
     json_ref(js, "dgamma", o.dgamma); js << ","; json_ref(js, "dbeta", o.dbeta); js << ","; json_ref(js, "dbias", o.dbias);

@@ -69,6 +69,8 @@ struct Op {
   // tcgen05 path: OP_GEMM reads B as K-major [N, kpad] bf16 hi / lo packs (bf16-element offsets into the
   // arena16 region); OP_WGRAD reads both operands straight from the split activation / gradient views
   int umma = 0; int64_t bu_hi = 0, bu_lo = 0; int kpad = 0;
+  // conv-shaped A view: K = tap_T taps x tap_C channels, consecutive rows tap_s positions apart (0: not a window view)
+  int tap_T = 0, tap_C = 0, tap_s = 0;
   // LN_FWD / LN_BWD
   Ref in, xhat, aout, rstd, gamma, beta, dgamma, dbeta, dbias;
   int L = 0, Cn = 0, out_flen = 0, out_off = 0;

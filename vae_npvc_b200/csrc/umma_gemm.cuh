@@ -24,7 +24,8 @@ namespace npvc {
 //   (FB > 1 only when Ra == 1).  Local row r = (fl * Ab + al) * Rb + b.
 struct RowTiling {
   int Rb, Ra, Ab, FB, TA;     // TA = ceil(Ra / Ab) tiles per frame block
-  int rows_tile;              // Rb * Ab * FB
+  int RbH;                    // accumulator rows per row-group: Rb, or Rb + halo rows in tap mode (halo rows are discarded)
+  int rows_tile;              // RbH * Ab * FB
   int frames, m_tiles;        // m_tiles = ceil(frames / FB) * TA
 };
 
@@ -38,6 +39,11 @@ struct UmmaArgs {
   RowTiling rt;
   // (F)
   int n_tiles, acc_sets;
+  // tap mode (conv-shaped views, tapT > 0): the tile's positions are loaded ONCE as tapP phase tiles of
+  // [rows + halo][tapC] (no window overlap); tap t = tapP * m + ph multiplies phase tile ph shifted by m
+  // rows (row-shifted K-major descriptor) with the resident weight tile of tap t.  sw = 2 * tapC bytes.
+  int tapT, tapC, tapP;
+  int b_tile_al;         // tap mode: bytes of one resident weight tile (BN * sw rounded up to 1024)
   DView C;
   const float* bias0; const float* bias1; const float* bias2; int bias_mod;
   // (W)
@@ -160,13 +166,18 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const uint32_t sw = (uint32_t)g.sw;
   const int bk = g.sw >> 1, ksteps = bk >> 4;
   const uint32_t a_tile_bytes = (uint32_t)BM * sw, b_tile_bytes = (uint32_t)g.BN * sw;
-  const uint32_t stage_bytes = 2u * a_tile_bytes + 2u * b_tile_bytes;
-  const uint32_t bar_base = sbase + (uint32_t)g.stages * stage_bytes;
+  const bool tap = g.tapT > 0;
+  // tap mode: [resident weights: tapT x (hi, lo) tiles][stages x tapP x (hi, lo) A tiles]
+  const uint32_t bres_bytes = tap ? (uint32_t)g.tapT * 2u * (uint32_t)g.b_tile_al : 0u;
+  const uint32_t stage_bytes = tap ? (uint32_t)g.tapP * 2u * a_tile_bytes : 2u * a_tile_bytes + 2u * b_tile_bytes;
+  const uint32_t ring = sbase + bres_bytes;
+  const uint32_t bar_base = ring + (uint32_t)g.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(g.stages + s); };
   auto accf_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * g.stages + b); };
   auto acce_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * g.stages + 4 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * g.stages + 8);
+  const uint32_t bres_bar = bar_base + 8u * (uint32_t)(2 * g.stages + 8);
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * g.stages + 10);      // (keeps bias_s 16-byte aligned)
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
   float* bias_s = reinterpret_cast<float*>(gen_base + (tmem_slot - sbase) + 16);      // [256] effective bias of the current N tile
 
@@ -177,6 +188,7 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
     for (int s = 0; s < g.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 4; b++) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -188,7 +200,69 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
 
-  if (warp == 0) {
+  if (warp == 0 && tap) {
+    // ------------------------------------------------------------------ TMA producer, tap mode
+    if (elect_one()) {                               // the weights of every tap, once per CTA
+      mbar_expect_tx(bres_bar, (uint32_t)g.tapT * 2u * b_tile_bytes);
+      for (int t = 0; t < g.tapT; t++) {
+        tma_load_2d(sbase + (uint32_t)(2 * t) * (uint32_t)g.b_tile_al, &tmBh, bres_bar, t * g.tapC, 0);
+        tma_load_2d(sbase + (uint32_t)(2 * t + 1) * (uint32_t)g.b_tile_al, &tmBl, bres_bar, t * g.tapC, 0);
+      }
+    }
+    __syncwarp();
+    const uint32_t tx = 2u * (uint32_t)g.tapP * (uint32_t)g.rt.rows_tile * sw;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      int a0, f0; tile_coords(g.rt, t, a0, f0);
+      const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const uint32_t st = ring + (uint32_t)s * stage_bytes;
+      if (elect_one()) {
+        mbar_expect_tx(full_bar(s), tx);
+        for (int p = 0; p < g.tapP; p++) {             // phase p = columns [p * tapC, (p + 1) * tapC) of the s * tapC wide rows
+          tma_load_4d(st + (uint32_t)(2 * p) * a_tile_bytes, &tmAh, full_bar(s), p * g.tapC, 0, a0, f0);
+          tma_load_4d(st + (uint32_t)(2 * p + 1) * a_tile_bytes, &tmAl, full_bar(s), p * g.tapC, 0, a0, f0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1 && tap) {
+    // ------------------------------------------------------------------ MMA issuer, tap mode
+    const uint32_t idesc = make_idesc(g.BN, false);
+    const uint64_t dbase = sdesc_base(0, sw);
+    const int ksteps_c = g.tapC >> 4;
+    mbar_wait(bres_bar, 0);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      const int buf = (int)(it % (uint32_t)g.acc_sets); const uint32_t aph = (it / (uint32_t)g.acc_sets) & 1u;
+      mbar_wait(acce_bar(buf), aph ^ 1u);
+      const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
+      mbar_wait(full_bar(s), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * g.BN), acc2 = acc + (uint32_t)g.BN;
+      const uint32_t st = ring + (uint32_t)s * stage_bytes;
+      if (elect_one()) {
+        int pz = 0, m = 0;                                // tap tp = tapP * m + pz
+        for (int tp = 0; tp < g.tapT; tp++) {
+          const uint32_t at = st + (uint32_t)(2 * pz) * a_tile_bytes + (uint32_t)m * sw;   // row shift by m
+          const uint64_t ah = sdesc_at(dbase, at), al = sdesc_at(dbase, at + a_tile_bytes);
+          const uint64_t bh = sdesc_at(dbase, sbase + (uint32_t)(2 * tp) * (uint32_t)g.b_tile_al);
+          const uint64_t bl = sdesc_at(dbase, sbase + (uint32_t)(2 * tp + 1) * (uint32_t)g.b_tile_al);
+          for (int k4 = 0; k4 < ksteps_c; k4++) {
+            const uint64_t o = (uint64_t)(k4 * 2);
+            const uint32_t first = (tp > 0 || k4 > 0) ? 1u : 0u;
+            mma_bf16(acc, ah + o, bh + o, idesc, first);
+            mma_bf16(acc2, al + o, bh + o, idesc, first);
+            mma_bf16(acc2, ah + o, bl + o, idesc, 1u);
+          }
+          if (++pz == g.tapP) { pz = 0; m++; }
+        }
+        umma_commit(empty_bar(s));
+        umma_commit(accf_bar(buf));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
     const uint32_t tx = 2u * (uint32_t)g.rt.rows_tile * sw + 2u * b_tile_bytes;
     uint32_t it = 0;
@@ -246,7 +320,7 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const int row_local = lq * 32 + lane;
     const int et = threadIdx.x - 64;                // 0..127 within the epilogue group
     // local row -> (frame-in-tile, row-group-in-tile, row-in-group)
-    const int grp = row_local / g.rt.Rb, b_in = row_local - grp * g.rt.Rb;
+    const int grp = row_local / g.rt.RbH, b_in = row_local - grp * g.rt.RbH;
     const int fl = grp / g.rt.Ab, al = grp - fl * g.rt.Ab;
     int lt = 0, n0_staged = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
@@ -267,7 +341,7 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       const int buf = lt % g.acc_sets; const uint32_t aph = (uint32_t)((lt / g.acc_sets) & 1);
       int a0, f0; tile_coords(g.rt, mt, a0, f0);
       const long long f = f0 + fl; const int a = a0 + al;
-      const bool row_ok = (row_local < g.rt.rows_tile) && (f < g.rt.frames) && (a < g.rt.Ra);
+      const bool row_ok = (row_local < g.rt.rows_tile) && (b_in < g.rt.Rb) && (f < g.rt.frames) && (a < g.rt.Ra);
       float* cp = nullptr; uint16_t* chp = nullptr;
       int n_lo = 0, n_hi = 0; bool al16 = false;      // this row's valid columns [n_lo, n_hi); 16-byte aligned chunks
       if (row_ok) {
