@@ -186,7 +186,7 @@ struct TapGeom { bool ok; int sw, P, hr, BN, b_tile_al, stages; RowTiling rt; };
 TapGeom tap_geometry(const Op& o, long long frames) {
   TapGeom t; memset(&t, 0, sizeof t);
   const int C = o.tap_C, T = o.tap_T, s = o.tap_s;
-  if (T <= 0 || !(C == 16 || C == 32 || C == 64) || o.N > 256 || o.A.R < 2 || o.A.rs != s * C || o.K != T * C) return t;
+  if (T <= 0 || !(C == 16 || C == 32 || C == 64) || o.N > 256 || o.A.R < 2 || o.A.rs != s * C || o.K > T * C || o.K <= (T - 1) * C) return t;   // (a last tap may be partly beyond K: its weights are TMA zero fill)
   t.sw = 2 * C; t.P = s; t.hr = (T - 1) / s;
   t.BN = (o.N + 15) / 16 * 16;
   t.b_tile_al = (t.BN * t.sw + 1023) / 1024 * 1024;
@@ -239,7 +239,7 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = 1; g.rt = rt; g.n_tiles = 1; g.sw = sw;
   g.tapT = o.tap_T; g.tapC = C; g.tapP = tg.P; g.b_tile_al = tg.b_tile_al;
-  g.acc_sets = 512 / (2 * BN); if (g.acc_sets > 4) g.acc_sets = 4; if (g.acc_sets < 1) g.acc_sets = 1;
+  g.acc_sets = 512 / (2 * BN) >= 4 ? 4 : (512 / (2 * BN) >= 2 ? 2 : 1);
   int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
   g.stages = tg.stages;
   g.C = dview(c, o.C);
@@ -249,9 +249,9 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 1024;
+  const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 2048;
   unsigned grid = (unsigned)(rt.m_tiles < h->sm_count ? rt.m_tiles : h->sm_count);
-  umma_fwd_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  umma_fwd_kernel<<<grid, 320, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -292,7 +292,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + bk - 1) / bk; g.rt = rt; g.n_tiles = n_tiles; g.sw = sw;
   const int stage_bytes = 2 * 128 * sw + 2 * BN * sw;
-  g.acc_sets = 512 / (2 * BN); if (g.acc_sets > 4) g.acc_sets = 4; if (g.acc_sets < 1) g.acc_sets = 1;   // accumulator ring in TMEM: the epilogue of tile i overlaps the mainloops of the next tiles
+  g.acc_sets = 512 / (2 * BN) >= 4 ? 4 : (512 / (2 * BN) >= 2 ? 2 : 1);   // accumulator ring in TMEM: the epilogue of tile i overlaps the mainloops of the next tiles
   int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
   int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
   g.stages = stages;
@@ -303,10 +303,10 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 1024;   // + bias_s[256]
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 2048;   // + bias_s[256]
   long long total = rt.m_tiles * n_tiles;
   unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
-  umma_fwd_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  umma_fwd_kernel<<<grid, 320, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }

@@ -476,13 +476,21 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     w.A = VA_g[g]; w.K = l.wn * l.Cip; w.N = l.s * l.Co;
     w.C = B.view(B.ws(b_dcg[g]), l.Hi, dcg_flen[g], l.s * l.Co, dcg_off[g], dcg_flen[g]);
     w.B = B.adw(A_gf[g]); w.ldb = ld_gf[g];
-    snprintf(nm, sizeof nm, "dgrad_g%d", g);
-    Op& o = B.op(OP_GEMM, PH_BWD, nm);
-    o.A = B.view(B.ws(b_dcg[g]), l.Hi, dcg_flen[g], l.s * l.Co, 0, dcg_flen[g]); o.K = l.k * l.Co;
-    o.tap_T = l.k; o.tap_C = l.Co; o.tap_s = l.s;
-    o.B = B.aw(A_gd[g]); o.ldb = ld_gd[g]; o.N = l.Cip;
-    Ref dst = (g > 0) ? B.ws(b_dag[g - 1]) : B.ws(b_dhm);
-    o.C = B.view(dst, l.Hi, l.Hi * l.Cip, l.Cip, 0, l.Hi * l.Cip);
+    // dgrad of the transposed conv = strided conv over the padded gradient.  With 8 channels a tap is half an
+    // MMA K step: split the rows by parity, so that each half sees 16-element taps (2 positions) at a whole
+    // number of taps per row step (2*s*Co/16) -- two GEMMs over interleaved views of the same buffers.
+    const int halves = (use_umma && l.Co == 8 && (l.s * l.Co) % 8 == 0 && l.Hi >= 2) ? 2 : 1;
+    for (int hf = 0; hf < halves; hf++) {
+      if (halves == 1) snprintf(nm, sizeof nm, "dgrad_g%d", g); else snprintf(nm, sizeof nm, "dgrad_g%d_%s", g, hf ? "odd" : "even");
+      Op& o = B.op(OP_GEMM, PH_BWD, nm);
+      const int R = (halves == 1) ? l.Hi : (hf ? l.Hi / 2 : (l.Hi + 1) / 2);
+      o.A = B.view(B.ws(b_dcg[g]), R, dcg_flen[g], halves * l.s * l.Co, hf * l.s * l.Co, dcg_flen[g]); o.K = l.k * l.Co;
+      if (halves == 1) { o.tap_T = l.k; o.tap_C = l.Co; o.tap_s = l.s; }
+      else { o.tap_C = 16; o.tap_T = cdiv(l.k * l.Co, 16); o.tap_s = 2 * l.s * l.Co / 16; }
+      o.B = B.aw(A_gd[g]); o.ldb = ld_gd[g]; o.N = l.Cip;
+      Ref dst = (g > 0) ? B.ws(b_dag[g - 1]) : B.ws(b_dhm);
+      o.C = B.view(dst, R, l.Hi * l.Cip, halves * l.Cip, hf * l.Cip, l.Hi * l.Cip);
+    }
   }
   View V_dhm = B.view(B.ws(b_dhm), 1, Nm, 0, 0, Nm);
   {  // merge backward; rows z.. of the weight gradient = per-speaker sums of dhm (IndexedSlices of

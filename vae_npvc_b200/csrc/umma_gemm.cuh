@@ -151,13 +151,14 @@ __device__ __forceinline__ uint64_t sdesc_at(uint64_t base, uint32_t saddr) { re
 }  // namespace umma
 
 // =============================================================================================
-// (F) persistent forward / dgrad kernel, 192 threads:
+// (F) persistent forward / dgrad kernel, 320 threads:
 //   warp 0      TMA producer (A hi, A lo, B hi, B lo per 64-wide k-block), runs ahead across tiles
 //   warp 1      TMEM allocator + MMA issuer; up to 4 accumulator sets in TMEM (512 / (2*BN) columns allow)
-//   warps 2-5   epilogue (TMEM -> registers -> bias -> fp32 or split store), overlapped with the
-//               next tile's mainloop through the accf / acce barriers
+//   warps 2-9   two epilogue groups of 4 warps (TMEM -> registers -> bias -> fp32 or split store): group 0 takes
+//               the CTA's even tiles, group 1 the odd ones, overlapped with the next tiles' mainloops through
+//               the accf / acce barriers (small-K layers are bound by the per-tile epilogue latency)
 // =============================================================================================
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
   using namespace umma;
@@ -179,7 +180,7 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const uint32_t bres_bar = bar_base + 8u * (uint32_t)(2 * g.stages + 8);
   const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * g.stages + 10);      // (keeps bias_s 16-byte aligned)
   uint8_t* gen_base = smem_raw + (sbase - smem_u32(smem_raw));
-  float* bias_s = reinterpret_cast<float*>(gen_base + (tmem_slot - sbase) + 16);      // [256] effective bias of the current N tile
+  float* bias_all = reinterpret_cast<float*>(gen_base + (tmem_slot - sbase) + 16);    // [2][256] effective bias of each epilogue group's current N tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = g.rt.m_tiles * g.n_tiles;
@@ -318,15 +319,21 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     // ------------------------------------------------------------------ epilogue warps
     const int lq = warp & 3;                        // TMEM lane quarter this warp may access
     const int row_local = lq * 32 + lane;
-    const int et = threadIdx.x - 64;                // 0..127 within the epilogue group
+    const int eg = (warp - 2) >> 2;                  // epilogue group: tiles with (local tile index & 1) == eg
+    const int et = (threadIdx.x - 64) & 127;        // 0..127 within the epilogue group
+    float* bias_s = bias_all + eg * 256;
     // local row -> (frame-in-tile, row-group-in-tile, row-in-group)
     const int grp = row_local / g.rt.RbH, b_in = row_local - grp * g.rt.RbH;
     const int fl = grp / g.rt.Ab, al = grp - fl * g.rt.Ab;
+    // Each accumulator set (and its barriers) must be served by ONE group, phase after phase (parity waits):
+    // with an even number of sets the tile parity picks the group; with a single set group 0 serves every tile.
+    const int egmask = (g.acc_sets & 1) ? 0 : 1;
     int lt = 0, n0_staged = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
+      if ((lt & egmask) != eg) continue;
       const int mt = t / g.n_tiles; const int n0 = (t - mt * g.n_tiles) * g.BN;
       if (n0 != n0_staged) {                        // (bias0 + bias1 + bias2)[n % bias_mod] for this tile's columns (0 without bias)
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's readers are done
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");          // previous tile's readers are done
         for (int c = et; c < g.BN; c += 128) {
           const int n = n0 + c; float b = 0.f;
           if (g.bias0 && n < g.N) {
@@ -335,7 +342,7 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           }
           bias_s[c] = b;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
         n0_staged = n0;
       }
       const int buf = lt % g.acc_sets; const uint32_t aph = (uint32_t)((lt / g.acc_sets) & 1);
@@ -356,13 +363,10 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       mbar_wait(accf_bar(buf), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * g.BN) + ((uint32_t)(lq * 32) << 16);
-      for (int c0 = 0; c0 < g.BN; c0 += 16) {
-        uint32_t v[16], w[16];
-        tmem_ld16(acc + (uint32_t)c0, v);
-        tmem_ld16(acc + (uint32_t)(g.BN + c0), w);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // 16 accumulator columns -> bias -> store (whole aligned chunk / aligned groups of 4 / single elements)
+      auto emit16 = [&](const uint32_t (&v)[16], const uint32_t (&w)[16], int c0) {
         const int nb = n0 + c0;
-        if (!row_ok || nb >= n_hi || nb + 16 <= n_lo) continue;
+        if (!row_ok || nb >= n_hi || nb + 16 <= n_lo) return;
         float o[16];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -388,11 +392,30 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           }
         } else {                                                              // edges: N tail, predicated range, odd alignment
 #pragma unroll
-          for (int e = 0; e < 16; e++) {
-            const int n = nb + e;
-            if (n >= n_lo && n < n_hi) { if (g.C.split) split_st1(chp + n, g.C.fs, o[e]); else cp[n] = o[e]; }
+          for (int q = 0; q < 4; q++) {
+            const int n4 = nb + 4 * q;
+            if (al16 && n4 >= n_lo && n4 + 4 <= n_hi) {
+              if (g.C.split) split_st4(chp + n4, g.C.fs, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+              else *reinterpret_cast<float4*>(cp + n4) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const int n = n4 + e;
+                if (n >= n_lo && n < n_hi) { if (g.C.split) split_st1(chp + n, g.C.fs, o[4 * q + e]); else cp[n] = o[4 * q + e]; }
+              }
+            }
           }
         }
+      };
+      for (int c0 = 0; c0 < g.BN; c0 += 32) {            // two 16-column chunks per TMEM round trip
+        uint32_t v0[16], w0[16], v1[16], w1[16];
+        const bool two = c0 + 16 < g.BN;
+        tmem_ld16(acc + (uint32_t)c0, v0);
+        tmem_ld16(acc + (uint32_t)(g.BN + c0), w0);
+        if (two) { tmem_ld16(acc + (uint32_t)(c0 + 16), v1); tmem_ld16(acc + (uint32_t)(g.BN + c0 + 16), w1); }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        emit16(v0, w0, c0);
+        if (two) emit16(v1, w1, c0 + 16);
       }
       // this accumulator set may be overwritten by the MMA warp now
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
