@@ -29,6 +29,7 @@ struct npvc_handle {
   int32_t* d_pack16_src = nullptr;
   int32_t* d_unpack_ptr = nullptr;
   int32_t* d_unpack_idx = nullptr;
+  int32_t* d_heavy = nullptr; int n_heavy = 0;     // parameters with >= UNPACK_HEAVY packed-gradient entries
   bool tables_on_device = false;
   int64_t launches = 0;
   int64_t last_chunk = 0; bool last_train = false;
@@ -412,8 +413,14 @@ int run_op(Ctx& c, const Op& o, int op_index) {
     }
     case OP_UNPACK: {
       long long n = p.n_params;
-      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.ws + p.buf_offset(p.buf_adw, c.chunk_cap, c.train), h->d_unpack_ptr, h->d_unpack_idx, c.grad, n);
-      h->launches++; break;
+      const float* adw = c.ws + p.buf_offset(p.buf_adw, c.chunk_cap, c.train);
+      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(adw, h->d_unpack_ptr, h->d_unpack_idx, c.grad, n);
+      h->launches++;
+      if (h->n_heavy > 0) {
+        unpack_heavy_kernel<<<(unsigned)((h->n_heavy * 32LL + 255) / 256), 256, 0, st>>>(adw, h->d_unpack_ptr, h->d_unpack_idx, h->d_heavy, h->n_heavy, c.grad);
+        h->launches++;
+      }
+      break;
     }
     case OP_GEMM: {
       GemmArgs g; g.A = dview(c, o.A); g.K = o.K; g.B = resolve(c, o.B); g.ldb = o.ldb; g.N = o.N; g.C = dview(c, o.C);
@@ -427,7 +434,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       if (tensor_ok) { int rc = launch_umma(c, o, op_index); if (rc) return rc; break; }
       if (o.rows_fixed && o.rows_fixed <= 16 && !g.bias0 && o.C.ref.space == SP_GRAD && !g.A.pred && g.A.R == 1 && g.C.R == 1 && o.K >= 256) {
         // few-row GEMM accumulated into the (zero-initialised) gradient buffer
-        const int kchunk = 128, ks = (o.K + kchunk - 1) / kchunk;
+        const int kchunk = 32, ks = (o.K + kchunk - 1) / kchunk;
         dim3 grid((unsigned)((o.N + 127) / 128), (unsigned)ks);
         fewrows_gemm_kernel<<<grid, 128, (size_t)o.rows_fixed * kchunk * sizeof(float), st>>>(
             g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, kchunk);
@@ -586,6 +593,13 @@ int ensure_tables(npvc_handle* h) {
   CUDA_TRY(cudaMemcpy(h->d_pack_src, p.pack_src.data(), p.pack_src.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(h->d_unpack_ptr, p.unpack_ptr.data(), p.unpack_ptr.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(h->d_unpack_idx, p.unpack_idx.data(), p.unpack_idx.size() * 4, cudaMemcpyHostToDevice));
+  {
+    std::vector<int32_t> heavy;
+    for (int64_t t = 0; t < p.n_params; t++) if (p.unpack_ptr[t + 1] - p.unpack_ptr[t] >= UNPACK_HEAVY) heavy.push_back((int32_t)t);
+    h->n_heavy = (int)heavy.size();
+    CUDA_TRY(cudaMalloc(&h->d_heavy, (heavy.size() + 1) * 4));
+    if (!heavy.empty()) CUDA_TRY(cudaMemcpy(h->d_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice));
+  }
   h->tables_on_device = true;
   return NPVC_OK;
 }
@@ -629,7 +643,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
 
 void npvc_destroy(npvc_handle* h) {
   if (!h) return;
-  if (h->tables_on_device) { cudaFree(h->d_pack_src); cudaFree(h->d_pack16_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); }
+  if (h->tables_on_device) { cudaFree(h->d_pack_src); cudaFree(h->d_pack16_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); cudaFree(h->d_heavy); }
   delete h;
 }
 

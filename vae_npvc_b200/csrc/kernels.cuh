@@ -1088,14 +1088,29 @@ __global__ void zcat_kernel(const float* z, const long long* y, float* out, int 
   else reinterpret_cast<float4*>(out + f * W)[q] = v;
 }
 
+// grad[t] += sum of the packed-gradient entries of parameter t (CSR).  Parameters gathered from many
+// positions (the 1025-tap kernel: one Toeplitz diagonal of up to 513 entries each) are left to
+// unpack_heavy_kernel (one warp per parameter).
+constexpr int UNPACK_HEAVY = 32;
 __global__ void unpack_kernel(const float* adw, const int* ptr, const int* idx, float* grad, long long n) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   int b = ptr[t], e = ptr[t + 1];
-  if (b == e) return;
+  if (b == e || e - b >= UNPACK_HEAVY) return;
   float s = 0.f;
   for (int i = b; i < e; i++) s += adw[idx[i]];
   grad[t] += s;
+}
+__global__ void unpack_heavy_kernel(const float* adw, const int* ptr, const int* idx, const int* heavy, int n_heavy, float* grad) {
+  const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= n_heavy) return;
+  const int t = heavy[w];
+  const int b = ptr[t], e = ptr[t + 1];
+  float s = 0.f;
+  for (int i = b + lane; i < e; i += 32) s += adw[idx[i]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) grad[t] += s;
 }
 
 // TF-form Adam (trainer/vae.py:16-24): theta -= lr_t * m / (sqrt(v) + eps)
