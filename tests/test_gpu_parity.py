@@ -205,6 +205,22 @@ def test_alternative_architectures_on_gpu(alt_arch):
     _check_against_oracle(e2, alt_arch, 29)
 
 
+def test_gradients_stay_finite_over_many_passes(eng, arch):
+    """Regression: an operand tile may never multiply bits from outside its own frame, not even by a zero
+    weight (NaN * 0).  The parity-split dgrad's last tap once read 16 bytes past the last frame's plane:
+    ~1.5 % of the passes, depending on the neighbouring buffer's bits, produced NaN gradients."""
+    n = 8
+    theta = eng.init_theta(0, 0.1)
+    grad = torch.empty_like(theta)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    for _ in range(150):
+        x = (torch.rand(n, 513, generator=g) * 2 - 1).to(eng.device)
+        y = torch.randint(0, arch["y_dim"], (n,), generator=g).to(eng.device)
+        eps = torch.randn(n, arch["z_dim"], generator=g).to(eng.device)
+        out = eng.loss_fwd_bwd(theta, x, y, eps, grad=grad, outputs=False)
+        assert bool(torch.isfinite(grad).all()) and bool(torch.isfinite(out["losses"]).all())
+
+
 def test_tanhize_and_record_reader(eng):
     g = torch.Generator(device="cpu").manual_seed(3)
     xmin = torch.randn(513, generator=g) - 3; xmax = xmin + 1 + torch.rand(513, generator=g)
@@ -223,7 +239,9 @@ def test_plugin_surface_trains(arch, tmp_path):
     from importlib import import_module
     MODEL = getattr(import_module("model.vae"), "ConvVAE")
     TRAINER = getattr(import_module("trainer.vae"), "VAETrainer")
-    a = dict(arch); a["training"] = dict(arch["training"], max_iter=30, lr=1e-3)
+    # lr 3e-4: at 1e-3 Adam(beta1 = 0.5) on 64 frames diverges around step 25 (exp(logsigma^2) overflows to NaN
+    # at a step that depends on the atomics' summation order) -- the check is "the plugin trains", not a stability test
+    a = dict(arch); a["training"] = dict(arch["training"], max_iter=30, lr=3e-4)
     machine = MODEL(a)
     g = torch.Generator(device="cpu").manual_seed(0)
     image = (torch.rand(64, 1, 513, 1, generator=g) * 2 - 1).cuda(); label = torch.randint(0, 10, (64,), generator=g).cuda()

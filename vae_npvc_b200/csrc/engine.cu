@@ -40,6 +40,9 @@ struct npvc_handle {
   struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile, sw; CUtensorMap tAh, tAl, tBh, tBl; };
   std::map<int, TMaps> tmaps;        // per-op tensor-map cache
   int64_t umma_launches = 0;
+  int wgrad_smem_kb = 225;           // NPVC_WGRAD_SMEM_KB
+  int overlap_wgrad = 1;             // NPVC_OVERLAP=0: weight gradients on the caller's stream (A/B comparisons, per-op profiling)
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int umma_tap = 1;                  // NPVC_UMMA_TAP=0: conv-shaped layers through the overlapping-window boxes (A/B comparisons)
   int umma_min_stages = 0;           // NPVC_UMMA_MIN_STAGES (experiments): below this many 64-wide k-block stages use 32-wide ones (measured slower: more TMA row requests)
   bool profiling = false;
@@ -331,7 +334,8 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   const int m_tiles_k = (o.K + 127) / 128;
   // rows per stage: keep >= 3 stages in shared memory
   const int per_row = 512 + 4 * BN;
-  int row_target = (220 * 1024 / 3 / per_row) / 16 * 16; if (row_target > 128) row_target = 128; if (row_target < 16) row_target = 16;
+  const int budget = h->wgrad_smem_kb * 1024;       // < 227 KB leaves shared memory for a co-resident Layernorm block (side-stream overlap)
+  int row_target = ((budget - 5 * 1024) / 3 / per_row) / 16 * 16; if (row_target > 128) row_target = 128; if (row_target < 16) row_target = 16;
   const RowTiling rt = make_tiling(o.A.R, frames, row_target);
   const void* a_base = resolve(c, o.A.ref); const void* d_base = resolve(c, o.C.ref);
   auto it = h->tmaps.find(op_index);
@@ -349,7 +353,7 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   const int d_region = (g.rows_al * d_sw + 1023) / 1024 * 1024;
   const int stage_bytes = 2 * (2 * g.rows_al * 128) + 2 * d_boxes * d_region;
   int tc = 32; while (tc < 2 * BN) tc *= 2; g.tmem_cols = tc;
-  int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 8) stages = 8; if (stages < 1) stages = 1;
+  int stages = (budget - 3072) / stage_bytes; if (stages > 8) stages = 8; if (stages < 1) stages = 1;
   g.stages = stages;
   // split the reduction so that tiles * S fills whole waves of SMs, each CTA keeping enough row
   // tiles to amortise its 128 x BN atomic epilogue
@@ -552,21 +556,41 @@ int run_op(Ctx& c, const Op& o, int op_index) {
 }
 
 int run_phase(Ctx& c, int phase) {
-  const std::vector<Op>& ops = c.h->plan.ops;
+  npvc_handle* h = c.h;
+  const std::vector<Op>& ops = h->plan.ops;
+  // Backward: the weight gradients are off the critical path (nothing reads the packed gradient before the
+  // final unpack, every activation / gradient buffer is written once per pass), so they are forked onto a
+  // side stream behind an event and joined at the end of the phase: the L2-bound wgrad GEMMs overlap the
+  // HBM-bound Layernorm backward kernels and the tails of the dgrad GEMMs.  Still ordered w.r.t. the
+  // caller's stream (fork / join events only); nothing synchronises the device.
+  const bool fork = (phase == PH_BWD) && h->overlap_wgrad && !h->profiling;
+  const cudaStream_t main_st = c.st;
+  bool forked = false;
+  if (fork && !h->side) {
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) return fail(NPVC_ERR_CUDA, "cudaStreamCreate failed");
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  }
   for (size_t i = 0; i < ops.size(); i++) {
     const Op& o = ops[i];
     if (o.phase != phase) continue;
     if (!c.grad && (o.kind == OP_UNPACK)) continue;
     npvc_handle::Ev ev{(int)i, nullptr, nullptr, 0, c.n};
-    if (c.h->profiling) {
+    if (h->profiling) {
       cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
       ev.rows = (o.kind == OP_GEMM || o.kind == OP_WGRAD) ? (o.rows_fixed ? o.rows_fixed : c.n * o.A.R) : c.n;
       cudaEventRecord(ev.a, c.st);
     }
+    const bool on_side = fork && o.kind == OP_WGRAD;
+    if (on_side) {                                   // everything issued so far on the caller's stream happens-before this op
+      cudaEventRecord(h->ev_fork, main_st); cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+      c.st = h->side; forked = true;
+    }
     int rc = run_op(c, o, (int)i);
-    if (c.h->profiling) { cudaEventRecord(ev.b, c.st); c.h->events.push_back(ev); }
+    c.st = main_st;
+    if (h->profiling) { cudaEventRecord(ev.b, c.st); h->events.push_back(ev); }
     if (rc) return rc;
   }
+  if (forked) { cudaEventRecord(h->ev_join, h->side); cudaStreamWaitEvent(main_st, h->ev_join, 0); }
   return NPVC_OK;
 }
 
@@ -631,6 +655,8 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   h->use_umma = !(eu && eu[0] == '0');
   if (const char* ms = getenv("NPVC_UMMA_MIN_STAGES")) h->umma_min_stages = atoi(ms);
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
+  if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
+  if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }
   const char* ea = getenv("NPVC_UMMA_OPS");
   if (ea) h->umma_allow = ea;
   std::string err = build_plan(*arch, h->plan, h->use_umma);
@@ -643,6 +669,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
 
 void npvc_destroy(npvc_handle* h) {
   if (!h) return;
+  if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
   if (h->tables_on_device) { cudaFree(h->d_pack_src); cudaFree(h->d_pack16_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); cudaFree(h->d_heavy); }
   delete h;
 }

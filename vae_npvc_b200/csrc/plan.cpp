@@ -20,6 +20,9 @@ inline int cdivs(int a, int b) { return -fdiv(-a, b); }                         
 struct EncL { int Ci, Co, k, s, Hi, Ho, pl, pr; };
 struct GenL { int Ci, Cip, Co, k, s, Hi, Ho, cl, dense, lo, hi, wn; };
 
+// dgrad of a transposed conv with 8 output channels: rows split by parity into two GEMMs (see the op list)
+inline bool gen_parity_split(int Co, int s, int Hi, bool use_umma) { return use_umma && Co == 8 && (s * Co) % 8 == 0 && Hi >= 2; }
+
 struct Builder {
   Plan& p;
   explicit Builder(Plan& pl) : p(pl) {}
@@ -364,6 +367,9 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     snprintf(nm, sizeof nm, "a_g%d", g);    b_ag[g] = B.add_buf(nm, ag_flen[g], 0, false, SPLIT);
     snprintf(nm, sizeof nm, "rstd_g%d", g); b_rg[g] = B.add_buf(nm, 1, 0, false);
     dcg_flen[g] = (l.cl + l.Ho + (l.k - l.s - l.cl)) * l.Co; dcg_off[g] = l.cl * l.Co;
+    // parity-split dgrad (below): its last 16-element tap reaches past the k*Co window -- those elements meet
+    // zero weights, so they must be zeros of this frame's own plane, never a neighbour's bits (NaN * 0)
+    if (gen_parity_split(l.Co, l.s, l.Hi, use_umma)) dcg_flen[g] += cdiv(l.k * l.Co, 16) * 16 - l.k * l.Co;
     snprintf(nm, sizeof nm, "dc_g%d", g);   b_dcg[g] = B.add_buf(nm, dcg_flen[g], 0, true, SPLIT);
     snprintf(nm, sizeof nm, "da_g%d", g);   b_dag[g] = B.add_buf(nm, L, 0, true);
   }
@@ -479,7 +485,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     // dgrad of the transposed conv = strided conv over the padded gradient.  With 8 channels a tap is half an
     // MMA K step: split the rows by parity, so that each half sees 16-element taps (2 positions) at a whole
     // number of taps per row step (2*s*Co/16) -- two GEMMs over interleaved views of the same buffers.
-    const int halves = (use_umma && l.Co == 8 && (l.s * l.Co) % 8 == 0 && l.Hi >= 2) ? 2 : 1;
+    const int halves = gen_parity_split(l.Co, l.s, l.Hi, use_umma) ? 2 : 1;
     for (int hf = 0; hf < halves; hf++) {
       if (halves == 1) snprintf(nm, sizeof nm, "dgrad_g%d", g); else snprintf(nm, sizeof nm, "dgrad_g%d_%s", g, hf ? "odd" : "even");
       Op& o = B.op(OP_GEMM, PH_BWD, nm);

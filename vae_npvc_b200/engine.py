@@ -6,6 +6,8 @@ CUDA device (or without the built extension) the constructors raise.
 """
 import math
 
+import os
+
 import torch
 
 from . import lib as _lib
@@ -128,6 +130,8 @@ class Engine:
         if eps.shape != (n, self.z_dim):
             raise ValueError("eps must be [n, z_dim]")
         ws = self.workspace(n, True)
+        if os.environ.get("NPVC_DEBUG_POISON"):          # bring-up: every byte the pass does not write itself reads as NaN
+            ws.fill_(0xFF); self._packed_for = None
         repack = self._packed_for != (theta.data_ptr(), theta._version, ws.data_ptr())
         out = {}
         if outputs:
