@@ -40,6 +40,7 @@ struct npvc_handle {
   struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile, sw; CUtensorMap tAh, tAl, tBh, tBl; };
   std::map<int, TMaps> tmaps;        // per-op tensor-map cache
   int64_t umma_launches = 0;
+  int ln_bulk = 1;                   // NPVC_LN_BULK=0: shared-memory Layernorm backward for large frames (A/B comparisons)
   int wgrad_smem_kb = 225;           // NPVC_WGRAD_SMEM_KB
   int overlap_wgrad = 1;             // NPVC_OVERLAP=0: weight gradients on the caller's stream (A/B comparisons, per-op profiling)
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -512,6 +513,15 @@ int run_op(Ctx& c, const Op& o, int op_index) {
         else if (G == 64) ln_bwd_reg_kernel<64><<<(unsigned)blocks, 256, sm, st>>>(g);
         else if (G == 128) ln_bwd_reg_kernel<128><<<(unsigned)blocks, 256, sm, st>>>(g);
         else ln_bwd_reg_kernel<256><<<(unsigned)blocks, 256, sm, st>>>(g);
+      } else if (ln_group(o.L, o.Cn, o.out_off, o.out_flen) && 2048 % o.Cn == 0 && h->ln_bulk &&
+                 (size_t)(4 * o.L + 5 * o.Cn) * sizeof(float) <= 100 * 1024) {
+        // large frames: double-buffered bulk-async frame stream (3 blocks / SM at L = 4104)
+        const size_t sm = (size_t)(4 * o.L + 5 * o.Cn) * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(ln_bwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; }
+        int per_sm = (int)((220 * 1024) / (sm + 1024)); if (per_sm > 3) per_sm = 3; if (per_sm < 1) per_sm = 1;
+        long long blocks = (long long)h->sm_count * per_sm; if (blocks > c.n) blocks = c.n;
+        ln_bwd_bulk_kernel<<<(unsigned)blocks, 256, sm, st>>>(g);
       } else {
         long long blocks = (long long)h->sm_count * 8; if (blocks > c.n) blocks = c.n;
         ln_bwd_kernel<<<(unsigned)blocks, 256, (size_t)(2 * o.L + 3 * o.Cn) * sizeof(float), st>>>(g);
@@ -656,6 +666,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* ms = getenv("NPVC_UMMA_MIN_STAGES")) h->umma_min_stages = atoi(ms);
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
+  if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
   if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }
   const char* ea = getenv("NPVC_UMMA_OPS");
   if (ea) h->umma_allow = ea;

@@ -950,6 +950,97 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
 }
 
 // =============================================================================================
+// Layernorm + lrelu backward for LARGE frames (more than 2048 floats): persistent blocks, the (dy, c) rows of
+// frame i+1 arrive by bulk async copy (cp.async.bulk + mbarrier) while frame i is processed from shared
+// memory, so the frame stream never stalls on the per-frame reductions.  Same arithmetic and requirements
+// as ln_bwd_reg_kernel (units of 8 elements, a thread's channels fixed: Cn divides 2048).
+// dynamic smem: [2 stages][2][L] floats | [3 Cn] channel sums | [2 Cn] gamma, beta
+// =============================================================================================
+__global__ void __launch_bounds__(256, 3) ln_bwd_bulk_kernel(LnBwdArgs g) {
+  extern __shared__ __align__(16) float bsm[];
+  __shared__ float red[40];
+  __shared__ __align__(8) unsigned long long mbar[2];
+  const int L = g.L, L8 = L >> 3, off8 = g.out_off >> 3, F8 = g.out_flen >> 3;
+  float* chs = bsm + 4 * L; float* sgm = chs + 3 * g.Cn; float* sbt = sgm + g.Cn;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]);
+  const uint32_t bytes = (uint32_t)L * 4u;
+  auto issue = [&](long long f, int st) {              // thread 0: both rows of frame f -> stage st
+    const uint32_t bar = bar0 + 8u * (uint32_t)st;
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(bsm + (size_t)st * 2 * L), d1 = d0 + bytes;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic accesses to this stage are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d0), "l"(g.dy + f * L), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d1), "l"(g.cin + f * L), "r"(bytes), "r"(bar) : "memory");
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 3 * g.Cn; i += blockDim.x) chs[i] = 0.f;
+  for (int i = threadIdx.x; i < g.Cn; i += blockDim.x) { sgm[i] = g.gamma[i]; sbt[i] = g.beta[i]; }
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < g.frames) issue(blockIdx.x, 0);
+  const int c0 = (8 * threadIdx.x) % g.Cn;            // this thread's 8 channels (blockDim * 8 = 2048 is a multiple of Cn)
+  float gm[8], bt[8], adg[8], adb[8], adc[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) { gm[e] = sgm[c0 + e]; bt[e] = sbt[c0 + e]; adg[e] = adb[e] = adc[e] = 0.f; }
+  const float invL = 1.0f / (float)L;
+  int k = 0;
+  for (long long f = blockIdx.x; f < g.frames; f += gridDim.x, k++) {
+    const int st = k & 1;
+    if (threadIdx.x == 0 && f + gridDim.x < g.frames) issue(f + gridDim.x, st ^ 1);   // (stage st^1 was released by the barrier that ended iteration k-1)
+    const float rs = g.rstd[f], mu = g.mean[f];
+    {                                                  // wait for this frame's rows
+      const uint32_t bar = bar0 + 8u * (uint32_t)st, parity = (uint32_t)((k >> 1) & 1);
+      uint32_t done = 0;
+      while (!done) asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+    float* sdy = bsm + (size_t)st * 2 * L; float* sc = sdy + L;
+    float s1 = 0.f, s2 = 0.f;
+    // pass 1 (in place): dy -> dxhat = dy * lrelu'(u) * gamma, c -> xhat; partial sums, dgamma / dbeta
+    for (int u = threadIdx.x; u < L8; u += blockDim.x) {
+      float d[8], h[8];
+      ld8(sdy + 8 * u, d); ld8(sc + 8 * u, h);
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        h[e] = (h[e] - mu) * rs;                       // xhat, as the forward formed it
+        const float uu = fmaf(h[e], gm[e], bt[e]);
+        const float du = d[e] * (uu >= 0.f ? 1.0f : 0.02f);
+        d[e] = du * gm[e];
+        s1 += d[e]; s2 = fmaf(d[e], h[e], s2);
+        adg[e] = fmaf(du, h[e], adg[e]); adb[e] += du;
+      }
+      float4* pd = reinterpret_cast<float4*>(sdy + 8 * u); float4* ph = reinterpret_cast<float4*>(sc + 8 * u);
+      pd[0] = make_float4(d[0], d[1], d[2], d[3]); pd[1] = make_float4(d[4], d[5], d[6], d[7]);
+      ph[0] = make_float4(h[0], h[1], h[2], h[3]); ph[1] = make_float4(h[4], h[5], h[6], h[7]);
+    }
+    s1 = block_sum(s1, red) * invL;
+    s2 = block_sum(s2, red) * invL;
+    // pass 2: dc = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) -> padded output frame
+    for (int u = threadIdx.x; u < L8; u += blockDim.x) {
+      float d[8], h[8], o[8];
+      ld8(sdy + 8 * u, d); ld8(sc + 8 * u, h);
+#pragma unroll
+      for (int e = 0; e < 8; e++) { o[e] = rs * (d[e] - s1 - h[e] * s2); adc[e] += o[e]; }
+      st8(g.dc, f, g.out_flen, 8 * (u + off8), o, g.out_split);
+    }
+    zero_pads(g.dc, f, g.out_flen, off8, L8, F8, threadIdx.x, blockDim.x, g.out_split);
+    __syncthreads();                                   // every thread is done with stage st
+  }
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    atomicAdd(&chs[c0 + e], adg[e]); atomicAdd(&chs[g.Cn + c0 + e], adb[e]); atomicAdd(&chs[2 * g.Cn + c0 + e], adc[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < g.Cn; i += blockDim.x) {
+    atomicAdd(&g.dgamma[i], chs[i]); atomicAdd(&g.dbeta[i], chs[g.Cn + i]); atomicAdd(&g.dbias[i], chs[2 * g.Cn + i]);
+  }
+}
+
+// =============================================================================================
 // sampler + KL  (util/layers.py:152-156,170-183); blockDim = 2z threads, thread = column
 // =============================================================================================
 __global__ void sample_kl_kernel(const float* hz, const float* eps, float* mu, float* lv, float* zout,
