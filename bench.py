@@ -169,7 +169,8 @@ def main():
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the ONE JSON line (NCCL_DEBUG=VERSION prints a banner there)
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the ONE JSON line: NCCL prints its version banner (and
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")   # warnings) to stdout unless given a file
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     arch = vcc2016_vae_arch()
