@@ -44,6 +44,7 @@ struct npvc_handle {
   int wgrad_smem_kb = 225;           // NPVC_WGRAD_SMEM_KB
   int overlap_wgrad = 1;             // NPVC_OVERLAP=0: weight gradients on the caller's stream (A/B comparisons, per-op profiling)
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int umma_groups = 4;               // NPVC_UMMA_GROUPS: epilogue groups of the forward kernel (1, 2 or 4; <= accumulator sets)
   int umma_tap = 1;                  // NPVC_UMMA_TAP=0: conv-shaped layers through the overlapping-window boxes (A/B comparisons)
   int umma_min_stages = 0;           // NPVC_UMMA_MIN_STAGES (experiments): below this many 64-wide k-block stages use 32-wide ones (measured slower: more TMA row requests)
   bool profiling = false;
@@ -204,7 +205,7 @@ TapGeom tap_geometry(const Op& o, long long frames) {
   r.rows_tile = r.RbH * r.Ab * r.FB;
   r.frames = (int)frames; r.m_tiles = (int)(((frames + r.FB - 1) / r.FB) * r.TA);
   const int bres = T * 2 * t.b_tile_al, stage = t.P * 2 * 128 * t.sw;
-  t.stages = (225 * 1024 - 4096 - bres) / stage; if (t.stages > 8) t.stages = 8;
+  t.stages = (225 * 1024 - 6144 - bres) / stage; if (t.stages > 8) t.stages = 8;
   t.ok = t.stages >= 2;
   return t;
 }
@@ -254,9 +255,9 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 2048;
+  const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 4096;
   unsigned grid = (unsigned)(rt.m_tiles < h->sm_count ? rt.m_tiles : h->sm_count);
-  umma_fwd_kernel<<<grid, 320, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  umma_fwd_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -273,7 +274,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   // k-block: 64 bf16 (128-byte swizzled rows) when >= 4 such stages fit, else 32 (64-byte rows): the
   // same bytes in flight at twice the pipeline granularity (wide N tiles are L2-latency-bound otherwise)
   int sw = 128;
-  if ((225 * 1024 - 3072) / (2 * 128 * 128 + 2 * BN * 128) < h->umma_min_stages) sw = 64;
+  if ((225 * 1024 - 6144) / (2 * 128 * 128 + 2 * BN * 128) < h->umma_min_stages) sw = 64;
   if (o.K <= 32) sw = 64;
   const int bk = sw / 2;
   const void* a_base = resolve(c, o.A.ref);
@@ -299,7 +300,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   const int stage_bytes = 2 * 128 * sw + 2 * BN * sw;
   g.acc_sets = 512 / (2 * BN) >= 4 ? 4 : (512 / (2 * BN) >= 2 ? 2 : 1);   // accumulator ring in TMEM: the epilogue of tile i overlaps the mainloops of the next tiles
   int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
-  int stages = (225 * 1024 - 3072) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
+  int stages = (225 * 1024 - 6144) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
   g.stages = stages;
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
@@ -308,10 +309,10 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 2048;   // + bias_s[256]
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 4096;   // + bias_s[256]
   long long total = rt.m_tiles * n_tiles;
   unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
-  umma_fwd_kernel<<<grid, 320, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  umma_fwd_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -665,6 +666,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   h->use_umma = !(eu && eu[0] == '0');
   if (const char* ms = getenv("NPVC_UMMA_MIN_STAGES")) h->umma_min_stages = atoi(ms);
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
+  if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
   if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
   if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }

@@ -135,6 +135,22 @@ __device__ __forceinline__ void tile_coords(const RowTiling& rt, int mt, int& a0
   const int fb = mt / rt.TA;
   a0 = (mt - fb * rt.TA) * rt.Ab; f0 = fb * rt.FB;
 }
+// Ring position (stage / accumulator set) and its mbarrier phase, advanced without divisions: the role loops
+// of the few-tap layers are paced by their serial instruction streams.
+struct RingPos {
+  int idx; uint32_t phase; int n;
+  __device__ __forceinline__ RingPos(int n_) : idx(0), phase(0u), n(n_) {}
+  __device__ __forceinline__ void advance() { if (++idx == n) { idx = 0; phase ^= 1u; } }
+};
+// Tile iterator of one CTA (tiles blockIdx.x, blockIdx.x + gridDim.x, ...) in (frame block, row-group tile) form
+struct TileIter {
+  int fb, ta, dfb, dta, TA;
+  __device__ __forceinline__ TileIter(const RowTiling& rt) : TA(rt.TA) {
+    fb = (int)blockIdx.x / rt.TA; ta = (int)blockIdx.x - fb * rt.TA;
+    dfb = (int)gridDim.x / rt.TA; dta = (int)gridDim.x - dfb * rt.TA;
+  }
+  __device__ __forceinline__ void advance() { fb += dfb; ta += dta; if (ta >= TA) { ta -= TA; fb++; } }
+};
 // One lane of a converged warp.  The role loops below are executed by ALL lanes of their warp (warp-uniform
 // control flow and operands) and only the tcgen05 / TMA instruction itself sits under this predicate:
 // issuing them from inside an `if (lane == 0)` region makes the compiler wrap every uniform-datapath
@@ -148,6 +164,28 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ uint64_t sdesc_base(uint32_t lbo, uint32_t sw) { return make_sdesc(0u, lbo, sw); }
 __device__ __forceinline__ uint64_t sdesc_at(uint64_t base, uint32_t saddr) { return base | (uint64_t)((saddr & 0x3FFFF) >> 4); }
 
+// The MMAs of one tile in tap mode, taps and phases known at compile time: every descriptor is the stage's
+// base descriptor plus a constant (the MMA warp's serial instruction stream paces the few-tap layers).
+//   a0d / b0d: descriptors of phase tile 0 (hi plane) of the stage / of tap 0's resident weight tile (hi)
+//   a_tile16 / b_tile16 / sw16: tile pitches and the row pitch in 16-byte units
+template <int T, int P>
+__device__ __forceinline__ void issue_taps(uint32_t acc, uint32_t acc2, uint64_t a0d, uint64_t b0d, uint32_t a_tile16,
+                                           uint32_t b_tile16, uint32_t sw16, int ksteps_c, uint32_t idesc) {
+#pragma unroll
+  for (int tp = 0; tp < T; tp++) {
+    const int pz = tp % P, m = tp / P;                  // tap tp = P * m + pz: phase tile pz, shifted by m rows
+    const uint64_t ah = a0d + (uint64_t)((uint32_t)(2 * pz) * a_tile16 + (uint32_t)m * sw16), al = ah + a_tile16;
+    const uint64_t bh = b0d + (uint64_t)((uint32_t)(2 * tp) * b_tile16), bl = bh + b_tile16;
+    for (int k4 = 0; k4 < ksteps_c; k4++) {             // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr >> 4) field
+      const uint64_t o = (uint64_t)(k4 * 2);
+      const uint32_t first = (tp > 0 || k4 > 0) ? 1u : 0u;
+      mma_bf16(acc, ah + o, bh + o, idesc, first);      // main products
+      mma_bf16(acc2, al + o, bh + o, idesc, first);     // corrections: separate accumulator
+      mma_bf16(acc2, ah + o, bl + o, idesc, 1u);
+    }
+  }
+}
+
 }  // namespace umma
 
 // =============================================================================================
@@ -158,7 +196,7 @@ __device__ __forceinline__ uint64_t sdesc_at(uint64_t base, uint32_t saddr) { re
 //               the CTA's even tiles, group 1 the odd ones, overlapped with the next tiles' mainloops through
 //               the accf / acce barriers (small-K layers are bound by the per-tile epilogue latency)
 // =============================================================================================
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
   using namespace umma;
@@ -212,11 +250,11 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     }
     __syncwarp();
     const uint32_t tx = 2u * (uint32_t)g.tapP * (uint32_t)g.rt.rows_tile * sw;
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
-      int a0, f0; tile_coords(g.rt, t, a0, f0);
-      const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
-      mbar_wait(empty_bar(s), ph ^ 1u);
+    RingPos sp(g.stages); TileIter ti(g.rt);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, sp.advance(), ti.advance()) {
+      const int a0 = ti.ta * g.rt.Ab, f0 = ti.fb * g.rt.FB;
+      const int s = sp.idx;
+      mbar_wait(empty_bar(s), sp.phase ^ 1u);
       const uint32_t st = ring + (uint32_t)s * stage_bytes;
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), tx);
@@ -232,31 +270,39 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const uint32_t idesc = make_idesc(g.BN, false);
     const uint64_t dbase = sdesc_base(0, sw);
     const int ksteps_c = g.tapC >> 4;
+    const uint64_t b0d = sdesc_at(dbase, sbase);
     mbar_wait(bres_bar, 0);
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
-      const int buf = (int)(it % (uint32_t)g.acc_sets); const uint32_t aph = (it / (uint32_t)g.acc_sets) & 1u;
-      mbar_wait(acce_bar(buf), aph ^ 1u);
-      const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
-      mbar_wait(full_bar(s), ph);
+    RingPos sp(g.stages), ap(g.acc_sets);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, sp.advance(), ap.advance()) {
+      const int buf = ap.idx;
+      mbar_wait(acce_bar(buf), ap.phase ^ 1u);
+      const int s = sp.idx;
+      mbar_wait(full_bar(s), sp.phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * g.BN), acc2 = acc + (uint32_t)g.BN;
       const uint32_t st = ring + (uint32_t)s * stage_bytes;
+      const uint64_t a0d = sdesc_at(dbase, st);
       if (elect_one()) {
-        int pz = 0, m = 0;                                // tap tp = tapP * m + pz
-        for (int tp = 0; tp < g.tapT; tp++) {
-          const uint32_t at = st + (uint32_t)(2 * pz) * a_tile_bytes + (uint32_t)m * sw;   // row shift by m
-          const uint64_t ah = sdesc_at(dbase, at), al = sdesc_at(dbase, at + a_tile_bytes);
-          const uint64_t bh = sdesc_at(dbase, sbase + (uint32_t)(2 * tp) * (uint32_t)g.b_tile_al);
-          const uint64_t bl = sdesc_at(dbase, sbase + (uint32_t)(2 * tp + 1) * (uint32_t)g.b_tile_al);
-          for (int k4 = 0; k4 < ksteps_c; k4++) {
-            const uint64_t o = (uint64_t)(k4 * 2);
-            const uint32_t first = (tp > 0 || k4 > 0) ? 1u : 0u;
-            mma_bf16(acc, ah + o, bh + o, idesc, first);
-            mma_bf16(acc2, al + o, bh + o, idesc, first);
-            mma_bf16(acc2, ah + o, bl + o, idesc, 1u);
+        const uint32_t a16 = a_tile_bytes >> 4, b16 = (uint32_t)g.b_tile_al >> 4, sw16 = sw >> 4;
+        // the tap / phase combinations of the supported layer shapes, unrolled; anything else: generic loop
+        if (g.tapT == 3 && g.tapP == 1) issue_taps<3, 1>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc);
+        else if (g.tapT == 7 && g.tapP == 3) issue_taps<7, 3>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc);
+        else if (g.tapT == 4 && g.tapP == 3) issue_taps<4, 3>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc);
+        else if (g.tapT == 9 && g.tapP == 3) issue_taps<9, 3>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc);
+        else {
+          int pz = 0, m = 0;                              // tap tp = tapP * m + pz
+          for (int tp = 0; tp < g.tapT; tp++) {
+            const uint64_t ah = a0d + (uint64_t)((uint32_t)(2 * pz) * a16 + (uint32_t)m * sw16), al = ah + a16;   // row shift by m
+            const uint64_t bh = b0d + (uint64_t)((uint32_t)(2 * tp) * b16), bl = bh + b16;
+            for (int k4 = 0; k4 < ksteps_c; k4++) {
+              const uint64_t o = (uint64_t)(k4 * 2);
+              const uint32_t first = (tp > 0 || k4 > 0) ? 1u : 0u;
+              mma_bf16(acc, ah + o, bh + o, idesc, first);
+              mma_bf16(acc2, al + o, bh + o, idesc, first);
+              mma_bf16(acc2, ah + o, bl + o, idesc, 1u);
+            }
+            if (++pz == g.tapP) { pz = 0; m++; }
           }
-          if (++pz == g.tapP) { pz = 0; m++; }
         }
         umma_commit(empty_bar(s));
         umma_commit(accf_bar(buf));
@@ -266,13 +312,13 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
     const uint32_t tx = 2u * (uint32_t)g.rt.rows_tile * sw + 2u * b_tile_bytes;
-    uint32_t it = 0;
+    RingPos sp(g.stages);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = t / g.n_tiles; const int n0 = (t - mt * g.n_tiles) * g.BN;
       int a0, f0; tile_coords(g.rt, mt, a0, f0);
-      for (int kb = 0; kb < g.kblocks; kb++, it++) {
-        const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+      for (int kb = 0; kb < g.kblocks; kb++, sp.advance()) {
+        const int s = sp.idx;
+        mbar_wait(empty_bar(s), sp.phase ^ 1u);
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
         if (elect_one()) {
           mbar_expect_tx(full_bar(s), tx);
@@ -288,15 +334,15 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
     const uint32_t idesc = make_idesc(g.BN, false);
     const uint64_t dbase = sdesc_base(0, sw);
-    uint32_t it = 0; int lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
-      const int buf = lt % g.acc_sets; const uint32_t aph = (uint32_t)((lt / g.acc_sets) & 1);
-      mbar_wait(acce_bar(buf), aph ^ 1u);                 // epilogue has drained this accumulator set
+    RingPos sp(g.stages), ap(g.acc_sets);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ap.advance()) {
+      const int buf = ap.idx;
+      mbar_wait(acce_bar(buf), ap.phase ^ 1u);            // epilogue has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + (uint32_t)(buf * 2 * g.BN), acc2 = acc + (uint32_t)g.BN;
-      for (int kb = 0; kb < g.kblocks; kb++, it++) {
-        const int s = (int)(it % (uint32_t)g.stages); const uint32_t ph = (it / (uint32_t)g.stages) & 1u;
-        mbar_wait(full_bar(s), ph);
+      for (int kb = 0; kb < g.kblocks; kb++, sp.advance()) {
+        const int s = sp.idx;
+        mbar_wait(full_bar(s), sp.phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
         const uint64_t ah = sdesc_at(dbase, st), al = sdesc_at(dbase, st + a_tile_bytes);
@@ -321,17 +367,19 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const int row_local = lq * 32 + lane;
     const int eg = (warp - 2) >> 2;                  // epilogue group: tiles with (local tile index & 1) == eg
     const int et = (threadIdx.x - 64) & 127;        // 0..127 within the epilogue group
-    float* bias_s = bias_all + eg * 256;
+    float* bias_s = bias_all + eg * 256;             // [4][256]
     // local row -> (frame-in-tile, row-group-in-tile, row-in-group)
     const int grp = row_local / g.rt.RbH, b_in = row_local - grp * g.rt.RbH;
     const int fl = grp / g.rt.Ab, al = grp - fl * g.rt.Ab;
     // Each accumulator set (and its barriers) must be served by ONE group, phase after phase (parity waits):
-    // with an even number of sets the tile parity picks the group; with a single set group 0 serves every tile.
-    const int egmask = (g.acc_sets & 1) ? 0 : 1;
+    // the launch gives 1, 2 or 4 groups, a divisor of the number of sets; local tile lt belongs to group lt % groups.
+    const int egmask = (int)((blockDim.x - 64) >> 7) - 1;
     int lt = 0, n0_staged = -1;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
+    RingPos ap(g.acc_sets); TileIter ti(g.rt);           // (ti: the n_tiles == 1 fast path; tap mode always)
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++, ap.advance(), ti.advance()) {
       if ((lt & egmask) != eg) continue;
-      const int mt = t / g.n_tiles; const int n0 = (t - mt * g.n_tiles) * g.BN;
+      int mt = t, n0 = 0;
+      if (g.n_tiles > 1) { mt = t / g.n_tiles; n0 = (t - mt * g.n_tiles) * g.BN; }
       if (n0 != n0_staged) {                        // (bias0 + bias1 + bias2)[n % bias_mod] for this tile's columns (0 without bias)
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");          // previous tile's readers are done
         for (int c = et; c < g.BN; c += 128) {
@@ -345,8 +393,9 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
         n0_staged = n0;
       }
-      const int buf = lt % g.acc_sets; const uint32_t aph = (uint32_t)((lt / g.acc_sets) & 1);
-      int a0, f0; tile_coords(g.rt, mt, a0, f0);
+      const int buf = ap.idx; const uint32_t aph = ap.phase;
+      int a0, f0;
+      if (g.n_tiles > 1) tile_coords(g.rt, mt, a0, f0); else { a0 = ti.ta * g.rt.Ab; f0 = ti.fb * g.rt.FB; }
       const long long f = f0 + fl; const int a = a0 + al;
       const bool row_ok = (row_local < g.rt.rows_tile) && (b_in < g.rt.Rb) && (f < g.rt.frames) && (a < g.rt.Ra);
       float* cp = nullptr; uint16_t* chp = nullptr;
@@ -489,10 +538,11 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
     const uint32_t tx = 2u * (2u * (uint32_t)g.rt.rows_tile * 128u + (uint32_t)d_boxes * (uint32_t)g.rt.rows_tile * (uint32_t)g.d_sw);
-    for (int i = 0; i < ntl; i++) {
-      const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
+    RingPos sp(g.stages);
+    for (int i = 0; i < ntl; i++, sp.advance()) {
+      const int s = sp.idx;
       int a0, f0; tile_coords(g.rt, t_begin + i, a0, f0);
-      mbar_wait(empty_bar(s), ph ^ 1u);
+      mbar_wait(empty_bar(s), sp.phase ^ 1u);
       const uint32_t st = sbase + (uint32_t)s * stage_bytes;
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), tx);
@@ -514,9 +564,10 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     const int ksteps = g.rows_al >> 4;
     const uint64_t abase = sdesc_base(a_region, 128), dbase = sdesc_base(d_region, (uint32_t)g.d_sw);
     const uint32_t acc2 = tmem_base + (uint32_t)g.BN;
-    for (int i = 0; i < ntl; i++) {
-      const int s = i % g.stages; const uint32_t ph = (uint32_t)((i / g.stages) & 1);
-      mbar_wait(full_bar(s), ph);
+    RingPos sp(g.stages);
+    for (int i = 0; i < ntl; i++, sp.advance()) {
+      const int s = sp.idx;
+      mbar_wait(full_bar(s), sp.phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t st = sbase + (uint32_t)s * stage_bytes;
       const uint64_t ah0 = sdesc_at(abase, st), al0 = sdesc_at(abase, st + a_plane);
