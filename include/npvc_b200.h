@@ -12,6 +12,9 @@
  *     from the architecture), uploaded on the first device call and freed by npvc_destroy().
  *   - every call takes the CUDA stream (cudaStream_t passed as void*) to enqueue on; nothing
  *     synchronises the device; nothing runs on the legacy default stream unless stream == NULL.
+ *     npvc_loss_fwd_bwd may fork part of its backward pass (the weight gradients) onto an internal
+ *     non-blocking stream; that work is ordered after / before the caller's stream by events, so the
+ *     call keeps plain stream semantics (and can be captured in a CUDA graph).
  *   - return value: 0 = ok, non-zero = error; npvc_last_error() gives the thread-local message.
  *   - there is NO CPU fallback: with no usable GPU every compute entry returns NPVC_ERR_CUDA.
  *   - parameters travel as ONE flat fp32 buffer `theta` = concatenation of the TF variables in
