@@ -97,6 +97,32 @@ def test_workspace_sizes(arch):
     assert h.workspace_bytes(200, True) > b
 
 
+def test_tensor_path_plan_features(arch, monkeypatch):
+    """Plan-level features of the tensor path: operand planes, tap metadata of the conv-shaped views, the
+    parity-split dgrad of the 8-channel transposed conv (interleaved views, padded gradient frame), the
+    speaker term inside the merge GEMM."""
+    monkeypatch.setenv("NPVC_UMMA", "1")
+    plan = lib.Handle(arch).plan()
+    ops = {o["name"]: o for o in plan["ops"]}
+    bufs = {b["name"]: b for b in plan["bufs"]}
+    for name in ("a_e0", "a_g2", "dc_e1", "dc_g2", "zs", "hm", "dhm", "dhz", "dxh"):
+        assert bufs[name]["split"] == 1 and bufs[name]["per_frame"] % 8 == 0, name        # 16-byte aligned lo plane
+    for name in ("c_e0", "da_g2", "xh", "mu"):
+        assert bufs[name]["split"] == 0, name
+    assert ops["conv_e1"]["tap"] == [7, 16, 3] and ops["convT_g2"]["tap"] == [3, 16, 1]
+    assert ops["dgrad_g1"]["tap"] == [7, 16, 3] and ops["dgrad_e1"]["tap"] == [3, 32, 1]
+    assert ops["convT_g3"]["tap"] == [0, 0, 0] and "dgrad_g2" not in ops
+    ev, od = ops["dgrad_g2_even"], ops["dgrad_g2_odd"]
+    assert ev["tap"] == od["tap"] == [4, 16, 3] and ev["K"] == od["K"] == 56
+    assert (ev["A"]["R"], od["A"]["R"]) == (86, 85) and ev["A"]["rs"] == od["A"]["rs"] == 48
+    assert (ev["A"]["off"], od["A"]["off"]) == (0, 24) and (ev["C"]["off"], od["C"]["off"]) == (0, 16) and ev["C"]["rs"] == 32
+    # the last 16-element tap of the last row stays inside the frame's own plane (zeros), never a neighbour's bits
+    last = ev["A"]["off"] + (ev["A"]["R"] - 1) * ev["A"]["rs"] + ev["tap"][0] * ev["tap"][1]
+    assert last <= bufs["dc_g2"]["per_frame"] == 4144
+    # merge: K = z + padded one-hot columns, no table / segmented-sum ops left
+    assert ops["merge"]["K"] == 128 + 16 and ops["wgrad_merge_z"]["K"] == 144 and "segsum_dhm" not in ops and "zcat" in ops
+
+
 def test_bad_architecture_raises_value_error(arch):
     bad = dict(arch); bad["encoder"] = dict(arch["encoder"]); bad["encoder"]["output"] = [16, 32, 64, 128, 255]
     with pytest.raises(ValueError):
