@@ -206,6 +206,7 @@ TapGeom tap_geometry(const Op& o, long long frames) {
   r.frames = (int)frames; r.m_tiles = (int)(((frames + r.FB - 1) / r.FB) * r.TA);
   const int bres = T * 2 * t.b_tile_al, stage = t.P * 2 * 128 * t.sw;
   t.stages = (225 * 1024 - 6144 - bres) / stage; if (t.stages > 8) t.stages = 8;
+  if (const char* ts = getenv("NPVC_TAP_STAGES")) { int v = atoi(ts); if (v >= 2 && v < t.stages) t.stages = v; }   // (experiments: leave shared memory to co-resident kernels)
   t.ok = t.stages >= 2;
   return t;
 }
