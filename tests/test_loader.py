@@ -116,3 +116,22 @@ def test_main_and_convert_drivers_end_to_end(tmp_path, arch, monkeypatch):
     assert conv.shape == (90, analyzer.FEAT_DIM) and np.isfinite(conv).all() and (conv[:, -1] == analyzer.SPEAKERS.index("TM3")).all()
     src = np.fromfile(str(tmp_path / 'dataset' / 'vcc2016' / 'bin' / 'Testing Set' / 'SF1' / '100001.bin'), np.float32).reshape(-1, analyzer.FEAT_DIM)
     assert np.array_equal(conv[:, 513:1026], src[:, 513:1026]) and np.array_equal(conv[:, 1027], src[:, 1027])     # ap, en pass through
+
+
+def test_trainer_writes_reference_summary_tags(tmp_path):
+    """trainer/vae.py status + summaries without a GPU: the training.log line format of the reference
+    (trainer/vae.py:31-52) and the TensorBoard scalar tags of model/vae.py:132-133."""
+    import importlib
+    T = importlib.import_module("trainer.vae").VAETrainer
+    arch = {"training": {"lr": 1e-4, "beta1": 0.5, "beta2": 0.999, "max_iter": 1}}
+    dirs = {"logdir": str(tmp_path / "train")}
+    tr = T({"G": 0.0}, arch, None, dirs)
+    tr.global_step = 7
+    msg = tr._refresh_status()
+    assert msg.startswith("Iter 00007: log P(x|z, y) = ") and "D_KL(z) = " in msg
+    assert "Iter 00007" in open(os.path.join(dirs["logdir"], "training.log")).read()
+    if tr._write_summaries([1.0, 2.5, -3.5]):
+        from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+        acc = EventAccumulator(dirs["logdir"]); acc.Reload()
+        assert set(acc.Tags()["scalars"]) == {"KL-div", "logPx"}
+        assert acc.Scalars("KL-div")[0].value == 2.5 and acc.Scalars("logPx")[0].step == 7

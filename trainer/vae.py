@@ -78,6 +78,28 @@ class VAETrainer(object):
             hd.flush()
         return msg
 
+    # -- TensorBoard scalars (model/vae.py:132-133: 'KL-div', 'logPx'; Supervisor's summary thread) -------
+    def _write_summaries(self, losses=None):
+        """Event file in the logdir with the reference's scalar tags, at the trainer's global step.
+        Best effort: without the tensorboard package this is a no-op."""
+        if not (self.dirs and self.dirs.get('logdir')):
+            return False
+        if getattr(self, '_tb', None) is None:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+            except Exception:
+                self._tb = False
+                return False
+            self._tb = SummaryWriter(self.dirs['logdir'])
+        if self._tb is False:
+            return False
+        if losses is None:
+            losses = self._state['losses'].tolist() if self._state else [float('nan')] * 3
+        self._tb.add_scalar('KL-div', losses[1], self.global_step)
+        self._tb.add_scalar('logPx', losses[2], self.global_step)
+        self._tb.flush()
+        return True
+
     def save(self, path=None):
         """Checkpoint: the variables under their TF names + Adam slots + global_step (the
         reference's Supervisor autosave, trainer/vae.py:78-84, as one torch file)."""
@@ -88,21 +110,24 @@ class VAETrainer(object):
         return path
 
     # -- hot loop (trainer/vae.py:73-99) ----------------------------------------------------
-    def train(self, nIter=None, machine=None, summary_op=None, status_secs=60, save_secs=300):
+    def train(self, nIter=None, machine=None, summary_op=None, status_secs=60, save_secs=300, summary_secs=120):
         if machine is not None:
             self.machine = machine
         if self.machine is None:
             raise ValueError('VAETrainer needs the machine: pass `machine=` or a loss from machine.loss()')
         rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
-        t_status = t_save = time.time()
+        t_status = t_save = t_summary = time.time()
         for step in range(self.arch['training']['max_iter'] if nIter is None else min(nIter, self.arch['training']['max_iter'])):
             self.opt['g']()
             now = time.time()
             if rank0 and now - t_status >= status_secs:
                 self._refresh_status(); t_status = now
+            if rank0 and now - t_summary >= summary_secs:
+                self._write_summaries(); t_summary = now
             if rank0 and self.dirs and self.dirs.get('logdir') and now - t_save >= save_secs:
                 self.save(); t_save = now
         torch.cuda.synchronize()
         if rank0 and self.dirs and self.dirs.get('logdir'):
             self._refresh_status()
+            self._write_summaries()
             self.save()
