@@ -39,6 +39,10 @@ struct npvc_handle {
   PFN_tmapEncodeTiled encode = nullptr;
   struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile, sw; CUtensorMap tAh, tAl, tBh, tBl; };
   std::map<int, TMaps> tmaps;        // per-op tensor-map cache
+  std::map<int, TMaps> tmaps_pair;   // same, CTA-pair launches (B boxes of BN / 2 rows)
+  int umma_pair = 0;                 // NPVC_PAIR=1: wide dense layers as cta_group::2 CTA pairs (opt-in until measured on a B200)
+  std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the width rule)
+  bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
   int64_t umma_launches = 0;
   int ln_bulk = 1;                   // NPVC_LN_BULK=0: shared-memory Layernorm backward for large frames (A/B comparisons)
   int wgrad_smem_kb = 225;           // NPVC_WGRAD_SMEM_KB
@@ -251,14 +255,67 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
   g.stages = tg.stages;
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_fwd) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    h->attr_fwd = true;
   }
   const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 4096;
   unsigned grid = (unsigned)(rt.m_tiles < h->sm_count ? rt.m_tiles : h->sm_count);
   umma_fwd_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  h->launches++; h->umma_launches++;
+  return NPVC_OK;
+}
+
+// CTA-pair form of the window-mode forward kernel (umma_gemm.cuh, PAIR): clusters of 2 CTAs, each staging its own
+// 128-row A tile and half of the B tile per k-block for one 256 x BN cta_group::2 MMA.
+bool pair_wanted(const npvc_handle* h, const Op& o, int BN, int m_tiles) {
+  if (!h->umma_pair || m_tiles < 2 || o.K <= 32 || (BN & 15)) return false;
+  if (!h->pair_ops.empty()) return ("," + h->pair_ops + ",").find("," + o.name + ",") != std::string::npos;
+  return BN >= 128;
+}
+int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, const RowTiling& rt) {
+  npvc_handle* h = c.h; cudaStream_t st = c.st;
+  const int sw = 128, bk = 64;
+  const void* a_base = resolve(c, o.A.ref);
+  uint16_t* arena16 = reinterpret_cast<uint16_t*>(c.ws + h->plan.aw16_off);
+  uint16_t* b_hi = arena16 + o.bu_hi; uint16_t* b_lo = arena16 + o.bu_lo;
+  auto it = h->tmaps_pair.find(op_index);
+  if (it == h->tmaps_pair.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != rt.frames || it->second.bn != BN) {
+    npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = rt.frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = sw;
+    int rc = make_view_maps(h, c, o.A, o.K, rt, bk, sw, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
+    cuuint64_t gdB[2] = {(cuuint64_t)o.kpad, (cuuint64_t)o.N};
+    cuuint64_t gsB[1] = {(cuuint64_t)o.kpad * 2};
+    cuuint32_t bxB[2] = {(cuuint32_t)bk, (cuuint32_t)(BN / 2)};         // each CTA of the pair loads half of the N tile
+    cuuint32_t es[2] = {1, 1};
+    for (int w = 0; w < 2; w++) {
+      CUresult r = h->encode(w ? &tm.tBl : &tm.tBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w ? b_lo : b_hi, gdB, gsB, bxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(pair B) failed for " + o.name + " code " + std::to_string((int)r));
+    }
+    h->tmaps_pair[op_index] = tm; it = h->tmaps_pair.find(op_index);
+  }
+  UmmaArgs g; memset(&g, 0, sizeof g);
+  g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + bk - 1) / bk; g.rt = rt; g.n_tiles = n_tiles; g.sw = sw;
+  const int stage_bytes = 2 * 128 * sw + BN * sw;                        // A hi / lo + this CTA's half of B hi / lo
+  g.acc_sets = 512 / (2 * BN) >= 4 ? 4 : (512 / (2 * BN) >= 2 ? 2 : 1);
+  int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
+  int stages = (225 * 1024 - 6144) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
+  g.stages = stages;
+  g.C = dview(c, o.C);
+  g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
+  if (!h->attr_pair) {
+    CUDA_TRY(cudaFuncSetAttribute(umma_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    h->attr_pair = true;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 4096;
+  const long long pair_tiles = (long long)((rt.m_tiles + 1) / 2) * n_tiles;
+  const long long pairs = pair_tiles < h->sm_count / 2 ? pair_tiles : h->sm_count / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3((unsigned)(64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups)));
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_fwd_pair_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -272,6 +329,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   }
   int n_tiles = 1; const int BN = pick_bn(o.N, &n_tiles);
   const RowTiling rt = make_tiling(o.A.R, frames, 128);
+  if (pair_wanted(h, o, BN, rt.m_tiles)) return launch_umma_pair(c, o, op_index, BN, n_tiles, rt);
   // k-block: 64 bf16 (128-byte swizzled rows) when >= 4 such stages fit, else 32 (64-byte rows): the
   // same bytes in flight at twice the pipeline granularity (wide N tiles are L2-latency-bound otherwise)
   int sw = 128;
@@ -305,10 +363,9 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   g.stages = stages;
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_fwd) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    h->attr_fwd = true;
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 4096;   // + bias_s[256]
   long long total = rt.m_tiles * n_tiles;
@@ -374,10 +431,9 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   g.tiles_per_split = (int)((rt.m_tiles + S - 1) / S);
   S = (rt.m_tiles + g.tiles_per_split - 1) / g.tiles_per_split;
   g.out = resolve(c, o.B); g.ld = o.ldb;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_wgrad) {
     CUDA_TRY(cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    h->attr_wgrad = true;
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 1) + 16;
   dim3 grid((unsigned)m_tiles_k, (unsigned)n_tiles, (unsigned)S);
@@ -519,8 +575,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
                  (size_t)(4 * o.L + 5 * o.Cn) * sizeof(float) <= 100 * 1024) {
         // large frames: double-buffered bulk-async frame stream (3 blocks / SM at L = 4104)
         const size_t sm = (size_t)(4 * o.L + 5 * o.Cn) * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(ln_bwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set = true; }
+        if (!h->attr_ln_bulk) { CUDA_TRY(cudaFuncSetAttribute(ln_bwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); h->attr_ln_bulk = true; }
         int per_sm = (int)((220 * 1024) / (sm + 1024)); if (per_sm > 3) per_sm = 3; if (per_sm < 1) per_sm = 1;
         long long blocks = (long long)h->sm_count * per_sm; if (blocks > c.n) blocks = c.n;
         ln_bwd_bulk_kernel<<<(unsigned)blocks, 256, sm, st>>>(g);
@@ -669,6 +724,8 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
   if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
+  if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
+  if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty()) h->umma_pair = 1; }
   if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
   if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }
   const char* ea = getenv("NPVC_UMMA_OPS");

@@ -118,8 +118,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // instruction descriptor: D fp32, A/B bf16, M = 128, N = bn; mn_major: both operands MN-major
-__device__ __forceinline__ uint32_t make_idesc(int bn, bool mn_major) {
-  uint32_t d = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int bn, bool mn_major, int m = BM) {
+  uint32_t d = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
   if (mn_major) d |= (1u << 15) | (1u << 16);
   return d;
 }
@@ -164,6 +164,47 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ uint64_t sdesc_base(uint32_t lbo, uint32_t sw) { return make_sdesc(0u, lbo, sw); }
 __device__ __forceinline__ uint64_t sdesc_at(uint64_t base, uint32_t saddr) { return base | (uint64_t)((saddr & 0x3FFFF) >> 4); }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster (the two SMs of a TPC) run ONE 256 x BN MMA.  Each CTA
+// stages its own 128 A rows and HALF of the B tile (BN / 2 rows); the leader (cluster rank 0) issues the MMAs,
+// which read both CTAs' shared memory at the same offsets and write each CTA's 128 accumulator rows into its
+// own TMEM.  Per CTA the B fill per MAC halves.  PTX forms as in CUTLASS (SM100_TMA_2SM_LOAD, SM100_MMA_*_2x1SM,
+// umma_arrive_multicast_2x1SM, ClusterBarrier::arrive(cta_id)).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {      // same offset in CTA `rank` of the cluster
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a pair: data lands in the executing CTA, the transaction bytes are counted on `bar`, a
+// shared::cluster address (the leader's full barrier)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // The MMAs of one tile in tap mode, taps and phases known at compile time: every descriptor is the stage's
 // base descriptor plus a constant (the MMA warp's serial instruction stream paces the few-tap layers).
 //   a0d / b0d: descriptors of phase tile 0 (hi plane) of the stage / of tap 0's resident weight tile (hi)
@@ -195,17 +236,22 @@ __device__ __forceinline__ void issue_taps(uint32_t acc, uint32_t acc2, uint64_t
 //   warps 2-9   two epilogue groups of 4 warps (TMEM -> registers -> bias -> fp32 or split store): group 0 takes
 //               the CTA's even tiles, group 1 the odd ones, overlapped with the next tiles' mainloops through
 //               the accf / acce barriers (small-K layers are bound by the per-tile epilogue latency)
+// PAIR (window mode only; launched as clusters of 2 CTAs): the two CTAs of a cluster work on two adjacent M tiles
+//   and the same N tile as ONE 256 x BN cta_group::2 MMA -- each CTA stages its own A tile and half of the B
+//   tile, the leader (cluster rank 0) issues the MMAs and commits to both CTAs' barriers, every CTA drains its
+//   own 128 accumulator rows.  B bytes per CTA and MAC halve, which buys pipeline stages for the wide-N layers.
 // =============================================================================================
+template <bool PAIR>
 __global__ void __launch_bounds__(576, 1)
-umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
+umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
   using namespace umma;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sw = (uint32_t)g.sw;
   const int bk = g.sw >> 1, ksteps = bk >> 4;
-  const uint32_t a_tile_bytes = (uint32_t)BM * sw, b_tile_bytes = (uint32_t)g.BN * sw;
-  const bool tap = g.tapT > 0;
+  const uint32_t a_tile_bytes = (uint32_t)BM * sw, b_tile_bytes = (uint32_t)(PAIR ? g.BN >> 1 : g.BN) * sw;   // (PAIR: this CTA's half of the B tile)
+  const bool tap = !PAIR && g.tapT > 0;        // (the pair form exists in window mode only)
   // tap mode: [resident weights: tapT x (hi, lo) tiles][stages x tapP x (hi, lo) A tiles]
   const uint32_t bres_bytes = tap ? (uint32_t)g.tapT * 2u * (uint32_t)g.b_tile_al : 0u;
   const uint32_t stage_bytes = tap ? (uint32_t)g.tapP * 2u * a_tile_bytes : 2u * a_tile_bytes + 2u * b_tile_bytes;
@@ -221,21 +267,33 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   float* bias_all = reinterpret_cast<float*>(gen_base + (tmem_slot - sbase) + 16);    // [2][256] effective bias of each epilogue group's current N tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = g.rt.m_tiles * g.n_tiles;
+  // PAIR: a "tile" of the loops below is a pair tile (M tiles 2 * pm + rank of the two CTAs, one N tile); the pair
+  // (cluster) index and count take the place of blockIdx.x / gridDim.x
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int total_tiles = PAIR ? ((g.rt.m_tiles + 1) >> 1) * g.n_tiles : g.rt.m_tiles * g.n_tiles;
+#define NPVC_TILE0 (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)
+#define NPVC_TILE_STEP (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
     for (int s = 0; s < g.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 4; b++) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+    // (PAIR: the leader's acce barriers collect the epilogue warps of both CTAs)
+    for (int b = 0; b < 4; b++) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), PAIR ? 8 : 4); }
     mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {       // the MMA warps of both CTAs allocate the same columns in both SMs' TMEM
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();        // barriers of both CTAs initialised before any remote arrive / TMA signal
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
 
@@ -311,16 +369,30 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
-    const uint32_t tx = 2u * (uint32_t)g.rt.rows_tile * sw + 2u * b_tile_bytes;
+    // (PAIR: the leader's full barrier counts the bytes of both CTAs' loads)
+    const uint32_t tx = (PAIR ? 2u : 1u) * (2u * (uint32_t)g.rt.rows_tile * sw + 2u * b_tile_bytes);
     RingPos sp(g.stages);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t / g.n_tiles; const int n0 = (t - mt * g.n_tiles) * g.BN;
+    for (int t = NPVC_TILE0; t < total_tiles; t += NPVC_TILE_STEP) {
+      int mt = t / g.n_tiles; int n0 = (t - mt * g.n_tiles) * g.BN;
+      if constexpr (PAIR) {
+        mt = 2 * mt + (int)rank; if (mt >= g.rt.m_tiles) mt = g.rt.m_tiles - 1;     // odd tile count: the idle half re-reads the last tile (never stored)
+        n0 += (int)rank * (g.BN >> 1);
+      }
       int a0, f0; tile_coords(g.rt, mt, a0, f0);
       for (int kb = 0; kb < g.kblocks; kb++, sp.advance()) {
         const int s = sp.idx;
         mbar_wait(empty_bar(s), sp.phase ^ 1u);
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
-        if (elect_one()) {
+        if constexpr (PAIR) {
+          const uint32_t lead_full = mapa_rank(full_bar(s), 0u);
+          if (elect_one()) {
+            if (rank == 0u) mbar_expect_tx(full_bar(s), tx);
+            tma_load_4d_pair(st, &tmAh, lead_full, kb * bk, 0, a0, f0);
+            tma_load_4d_pair(st + a_tile_bytes, &tmAl, lead_full, kb * bk, 0, a0, f0);
+            tma_load_2d_pair(st + 2u * a_tile_bytes, &tmBh, lead_full, kb * bk, n0);
+            tma_load_2d_pair(st + 2u * a_tile_bytes + b_tile_bytes, &tmBl, lead_full, kb * bk, n0);
+          }
+        } else if (elect_one()) {
           mbar_expect_tx(full_bar(s), tx);
           tma_load_4d(st, &tmAh, full_bar(s), kb * bk, 0, a0, f0);
           tma_load_4d(st + a_tile_bytes, &tmAl, full_bar(s), kb * bk, 0, a0, f0);
@@ -330,12 +402,18 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         __syncwarp();
       }
     }
+    if constexpr (PAIR) {
+      // producer tail: every stage this CTA filled has been consumed (its multicast commit has arrived here)
+      // before the CTA may leave the cluster
+      // (a slot that was never filled passes at once: the parity waited for is that of its "previous" phase)
+      for (int i = 0; i < g.stages; i++, sp.advance()) mbar_wait(empty_bar(sp.idx), sp.phase ^ 1u);
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
-    const uint32_t idesc = make_idesc(g.BN, false);
+    const uint32_t idesc = make_idesc(g.BN, false, PAIR ? 2 * BM : BM);
     const uint64_t dbase = sdesc_base(0, sw);
     RingPos sp(g.stages), ap(g.acc_sets);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ap.advance()) {
+    for (int t = (PAIR && rank != 0u) ? total_tiles : NPVC_TILE0; t < total_tiles; t += NPVC_TILE_STEP, ap.advance()) {   // (PAIR: the leader issues for both CTAs)
       const int buf = ap.idx;
       mbar_wait(acce_bar(buf), ap.phase ^ 1u);            // epilogue has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -347,7 +425,19 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         const uint32_t st = sbase + (uint32_t)s * stage_bytes;
         const uint64_t ah = sdesc_at(dbase, st), al = sdesc_at(dbase, st + a_tile_bytes);
         const uint64_t bh = sdesc_at(dbase, st + 2u * a_tile_bytes), bl = sdesc_at(dbase, st + 2u * a_tile_bytes + b_tile_bytes);
-        if (elect_one()) {
+        if constexpr (PAIR) {
+          if (elect_one()) {
+            for (int k4 = 0; k4 < ksteps; k4++) {
+              const uint64_t o = (uint64_t)(k4 * 2);
+              const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
+              mma_bf16_pair(acc, ah + o, bh + o, idesc, first);
+              mma_bf16_pair(acc2, al + o, bh + o, idesc, first);
+              mma_bf16_pair(acc2, ah + o, bl + o, idesc, 1u);
+            }
+            umma_commit_pair(empty_bar(s));             // frees the stage in both CTAs
+            if (kb == g.kblocks - 1) umma_commit_pair(accf_bar(buf));
+          }
+        } else if (elect_one()) {
           for (int k4 = 0; k4 < ksteps; k4++) {             // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr >> 4) field
             const uint64_t o = (uint64_t)(k4 * 2);
             const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
@@ -376,10 +466,12 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const int egmask = (int)((blockDim.x - 64) >> 7) - 1;
     int lt = 0, n0_staged = -1;
     RingPos ap(g.acc_sets); TileIter ti(g.rt);           // (ti: the n_tiles == 1 fast path; tap mode always)
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++, ap.advance(), ti.advance()) {
+    for (int t = NPVC_TILE0; t < total_tiles; t += NPVC_TILE_STEP, lt++, ap.advance(), ti.advance()) {
       if ((lt & egmask) != eg) continue;
       int mt = t, n0 = 0;
-      if (g.n_tiles > 1) { mt = t / g.n_tiles; n0 = (t - mt * g.n_tiles) * g.BN; }
+      if (PAIR || g.n_tiles > 1) { mt = t / g.n_tiles; n0 = (t - mt * g.n_tiles) * g.BN; }
+      bool tile_ok = true;
+      if constexpr (PAIR) { mt = 2 * mt + (int)rank; tile_ok = mt < g.rt.m_tiles; if (!tile_ok) mt = g.rt.m_tiles - 1; }
       if (n0 != n0_staged) {                        // (bias0 + bias1 + bias2)[n % bias_mod] for this tile's columns (0 without bias)
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");          // previous tile's readers are done
         for (int c = et; c < g.BN; c += 128) {
@@ -395,9 +487,9 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       }
       const int buf = ap.idx; const uint32_t aph = ap.phase;
       int a0, f0;
-      if (g.n_tiles > 1) tile_coords(g.rt, mt, a0, f0); else { a0 = ti.ta * g.rt.Ab; f0 = ti.fb * g.rt.FB; }
+      if (PAIR || g.n_tiles > 1) tile_coords(g.rt, mt, a0, f0); else { a0 = ti.ta * g.rt.Ab; f0 = ti.fb * g.rt.FB; }
       const long long f = f0 + fl; const int a = a0 + al;
-      const bool row_ok = (row_local < g.rt.rows_tile) && (b_in < g.rt.Rb) && (f < g.rt.frames) && (a < g.rt.Ra);
+      const bool row_ok = (!PAIR || tile_ok) && (row_local < g.rt.rows_tile) && (b_in < g.rt.Rb) && (f < g.rt.frames) && (a < g.rt.Ra);
       float* cp = nullptr; uint16_t* chp = nullptr;
       int n_lo = 0, n_hi = 0; bool al16 = false;      // this row's valid columns [n_lo, n_hi); 16-byte aligned chunks
       if (row_ok) {
@@ -469,16 +561,24 @@ umma_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       // this accumulator set may be overwritten by the MMA warp now
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(acce_bar(buf));
+      if constexpr (PAIR) { if (lane == 0) mbar_arrive_cluster(mapa_rank(acce_bar(buf), 0u)); }   // the leader's barrier
+      else if (lane == 0) mbar_arrive(acce_bar(buf));
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();        // both CTAs have drained their accumulators and seen every commit
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
   }
 }
+// the single-CTA form (every layer) and the CTA-pair form (opt-in for the wide dense layers, engine.cu)
+#undef NPVC_TILE0
+#undef NPVC_TILE_STEP
+#define umma_fwd_kernel umma_fwd_kernel_t<false>
+#define umma_fwd_pair_kernel umma_fwd_kernel_t<true>
 
 // =============================================================================================
 // (W) weight-gradient kernel, 192 threads, grid = (K tiles of 128, N tiles, row-tile splits):
