@@ -257,3 +257,24 @@ def test_plugin_surface_trains(arch, tmp_path):
     z = machine.encode(image)
     xh = machine.decode(z, label)
     assert z.shape == (64, 128) and xh.shape == (64, 513, 1, 1) and machine.generate == machine.decode
+
+
+def test_cta_pair_form_is_bit_identical_to_single_cta(arch, monkeypatch):
+    """The cta_group::2 form of the forward kernel (two CTAs, one 256 x BN MMA; umma_gemm.cuh PAIR) against the
+    single-CTA form on every layer wide enough for it, at cfg2 size: per-frame outputs must be bit-identical
+    (same products, same accumulation order), gradients equal up to the atomics' summation order."""
+    from vae_npvc_b200.engine import Engine
+    n = 16384
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = (torch.rand(n, 513, generator=g) * 2 - 1).cuda(); y = torch.randint(0, 10, (n,), generator=g).cuda()
+    eps = torch.randn(n, 128, generator=g).cuda()
+    monkeypatch.setenv("NPVC_PAIR", "0"); single = Engine(arch, "cuda:0")
+    monkeypatch.setenv("NPVC_PAIR", "2"); pair = Engine(arch, "cuda:0")       # every BN >= 128 layer
+    monkeypatch.delenv("NPVC_PAIR")
+    theta = single.init_theta(0, 0.1)
+    g1 = torch.empty_like(theta); g2 = torch.empty_like(theta)
+    o1 = single.loss_fwd_bwd(theta, x, y, eps, grad=g1)
+    o2 = pair.loss_fwd_bwd(theta, x, y, eps, grad=g2)
+    for k in ("z", "mu", "lv", "xh"):
+        assert torch.equal(o1[k], o2[k]), k
+    assert torch.isfinite(g2).all() and rel(g2, g1.cpu().numpy()) < 1e-5

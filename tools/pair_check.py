@@ -3,7 +3,8 @@ and through an engine created with NPVC_PAIR / NPVC_PAIR_OPS, outputs and gradie
 per-step times of both printed.  Every line is flushed as it is produced (a trap in the pair kernel ends the
 process: what was printed before it tells how far it got).
 
-    python tools/pair_check.py [n_frames] [ops]      # ops: comma-separated op names, or "wide" (every BN >= 128 layer)
+    python tools/pair_check.py [n_frames] [ops]      # ops: comma-separated op names, "wide" (every BN >= 128 layer)
+                                                     #      or "default" (the library's shape rule)
 """
 import os
 import sys
@@ -29,11 +30,14 @@ def main():
     y = torch.randint(0, 10, (n,), generator=g).cuda()
     eps = torch.randn(n, 128, generator=g).cuda()
 
-    base = Engine(arch, "cuda:0")
+    os.environ["NPVC_PAIR"] = "0"
+    base = Engine(arch, "cuda:0")                      # single-CTA form everywhere
     if ops == "wide":
-        os.environ["NPVC_PAIR"] = "1"
+        os.environ["NPVC_PAIR"] = "2"                  # every BN >= 128 layer
+    elif ops == "default":
+        os.environ["NPVC_PAIR"] = "1"                  # the library's own shape rule
     else:
-        os.environ["NPVC_PAIR_OPS"] = ops
+        os.environ["NPVC_PAIR"] = "1"; os.environ["NPVC_PAIR_OPS"] = ops
     pair = Engine(arch, "cuda:0")
     os.environ.pop("NPVC_PAIR", None); os.environ.pop("NPVC_PAIR_OPS", None)
     theta = base.init_theta(0, perturb=0.1)

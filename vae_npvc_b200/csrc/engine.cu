@@ -40,8 +40,8 @@ struct npvc_handle {
   struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile, sw; CUtensorMap tAh, tAl, tBh, tBl; };
   std::map<int, TMaps> tmaps;        // per-op tensor-map cache
   std::map<int, TMaps> tmaps_pair;   // same, CTA-pair launches (B boxes of BN / 2 rows)
-  int umma_pair = 0;                 // NPVC_PAIR=1: wide dense layers as cta_group::2 CTA pairs (opt-in until measured on a B200)
-  std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the width rule)
+  int umma_pair = 1;                 // NPVC_PAIR=0: no cta_group::2 CTA pairs; 2: every BN >= 128 layer (A/B comparisons)
+  std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the shape rule)
   bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
   int64_t umma_launches = 0;
   int ln_bulk = 1;                   // NPVC_LN_BULK=0: shared-memory Layernorm backward for large frames (A/B comparisons)
@@ -268,10 +268,15 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
 
 // CTA-pair form of the window-mode forward kernel (umma_gemm.cuh, PAIR): clusters of 2 CTAs, each staging its own
 // 128-row A tile and half of the B tile per k-block for one 256 x BN cta_group::2 MMA.
+// Default rule = the shapes measured faster on a B200 (profiles/r1i_pair_check_*.txt, 16,384 frames): wide N tiles
+// (BN >= 128: the B fill dominates and halves), long reductions (>= 8 k-blocks: G3 forward 0.268 -> 0.189 ms,
+// G3 dgrad 0.276 -> 0.253, E4 0.076 -> 0.071, merge dgrad 0.034 -> 0.030; the 3-k-block merge GEMM got slower)
+// and enough M tiles to fill the 74 pairs (small batches keep the single-CTA form, which is bit-identical per frame).
 bool pair_wanted(const npvc_handle* h, const Op& o, int BN, int m_tiles) {
   if (!h->umma_pair || m_tiles < 2 || o.K <= 32 || (BN & 15)) return false;
   if (!h->pair_ops.empty()) return ("," + h->pair_ops + ",").find("," + o.name + ",") != std::string::npos;
-  return BN >= 128;
+  if (h->umma_pair >= 2) return BN >= 128;
+  return BN >= 128 && o.K > 7 * 64 && m_tiles >= 64;
 }
 int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, const RowTiling& rt) {
   npvc_handle* h = c.h; cudaStream_t st = c.st;
@@ -725,7 +730,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
-  if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty()) h->umma_pair = 1; }
+  if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty() && !h->umma_pair) h->umma_pair = 1; }
   if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
   if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }
   const char* ea = getenv("NPVC_UMMA_OPS");
