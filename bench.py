@@ -135,8 +135,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * n / fps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 ConvVAE 10-speaker fwd+bwd+Adam (frame-major [N,513])", "frames_per_step_sample": n,
-                   "note": "CPU restatement of the reference graph (PyTorch/oneDNN fp32), not TF 1.2.1"},
+        # the native arm's workload (same frame shape, speakers, fwd+bwd+Adam); each CPU step is a bounded sample of it
+        "config": {"workload": "cfg2: ConvVAE (architecture-vae-vcc2016) 10-speaker, %d frames/GPU/step (64x256), fwd+bwd+Adam" % args.frames,
+                   "frames_per_gpu_per_step": args.frames, "frames_per_step_sample": n,
+                   "note": "CPU restatement of the reference graph (PyTorch/oneDNN fp32), not TF 1.2.1; a step = %d frames of the workload" % n},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d frames/step x %d steps (cfg2 shapes, N bounded for CPU time)" % (n, args.steps)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
