@@ -196,7 +196,11 @@ class FrameLoader(object):
             rec = self.host[slot].to(self.dev, non_blocking=True)
             x, y = self.engine.unpack_records(rec, SP_DIM, self.norm[0], self.norm[1])
             done = torch.cuda.Event(); done.record(self.stream)
-        torch.cuda.current_stream().wait_event(done)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(done)
+        # allocated on the loader's stream, consumed on the caller's: the caching allocator must not hand the
+        # blocks back to the loader's stream while the training step still reads them
+        x.record_stream(cur); y.record_stream(cur)
         done.synchronize()                  # the pinned slot may be refilled once the H2D copy is done
         self.free.release()
         if self.fmt == 'NCHW':

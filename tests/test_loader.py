@@ -135,3 +135,49 @@ def test_trainer_writes_reference_summary_tags(tmp_path):
         acc = EventAccumulator(dirs["logdir"]); acc.Reload()
         assert set(acc.Tags()["scalars"]) == {"KL-div", "logPx"}
         assert acc.Scalars("KL-div")[0].value == 2.5 and acc.Scalars("logPx")[0].step == 7
+
+
+def test_trainer_checkpoint_resume_roundtrip(tmp_path):
+    """save -> restore (trainer/vae.py:78-84 Supervisor autosave / restore-on-start, util/wrapper.py:32-62 `load`):
+    the variables under their TF names, the Adam slots and global_step come back; the newest
+    ``model.ckpt-<step>`` of the logdir is the one taken; shape mismatches are refused.  No GPU needed: the
+    machine is a stand-in exposing what the trainer touches (theta, variables())."""
+    import importlib
+    import torch
+    tv = importlib.import_module("trainer.vae")
+
+    class Machine(object):
+        def __init__(self, seed):
+            g = torch.Generator().manual_seed(seed)
+            self.theta = torch.randn(10, generator=g)
+
+        def variables(self):
+            return {"Encoder/dense/kernel": self.theta[:6].view(2, 3), "Encoder/dense/bias": self.theta[6:]}
+
+    arch = {"training": {"lr": 1e-4, "beta1": 0.5, "beta2": 0.999, "max_iter": 1}}
+    dirs = {"logdir": str(tmp_path / "train"), "restore_from": str(tmp_path / "train")}
+    assert tv.latest_checkpoint(dirs["logdir"]) is None
+    m1 = Machine(1)
+    t1 = tv.VAETrainer({"G": 0.0}, arch, None, dirs); t1.machine = m1
+    assert t1.restore() is None                                   # nothing to restore yet
+    st = t1._ensure_state(m1)
+    st["m"].fill_(0.25); st["v"].fill_(0.5)
+    t1.global_step = 9; t1.save()
+    t1.global_step = 120; m1.theta.mul_(2.0); st["m"].fill_(0.75); t1.save()
+    assert tv.latest_checkpoint(dirs["logdir"]).endswith("model.ckpt-120")      # numeric, not lexicographic, order
+
+    m2 = Machine(2)
+    t2 = tv.VAETrainer({"G": 0.0}, arch, None, dirs); t2.machine = m2
+    assert t2.restore() == 120 and t2.global_step == 120
+    assert torch.equal(m2.theta, m1.theta) and torch.equal(t2._state["m"], st["m"]) and torch.equal(t2._state["v"], st["v"])
+    m3 = Machine(3)
+    t3 = tv.VAETrainer({"G": 0.0}, arch, None, dirs); t3.machine = m3
+    assert t3.restore(ckpt="model.ckpt-9") == 9 and float(t3._state["m"][0]) == 0.25
+    assert torch.allclose(m3.theta * 2.0, m1.theta)
+
+    class Other(Machine):
+        def variables(self):
+            return {"Encoder/dense/kernel": self.theta[:6].view(3, 2), "Encoder/dense/bias": self.theta[6:]}
+    t4 = tv.VAETrainer({"G": 0.0}, arch, None, dirs); t4.machine = Other(4)
+    with pytest.raises(ValueError):
+        t4.restore()

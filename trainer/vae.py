@@ -9,12 +9,25 @@ gradient is all-reduced once per step over NCCL before the replicate
 """
 import logging
 import os
+import re
 import time
 
 import torch
 import torch.distributed as dist
 
 from vae_npvc_b200.parallel import allreduce_flat_grad_, broadcast_params_, world_info
+
+
+def latest_checkpoint(logdir):
+    """Newest ``model.ckpt-<step>`` in `logdir` (what ``tf.train.get_checkpoint_state`` resolves in
+    ``util/wrapper.py:39-60``), or None."""
+    best, best_step = None, -1
+    if logdir and os.path.isdir(logdir):
+        for f in os.listdir(logdir):
+            m = re.fullmatch(r'model\.ckpt-(\d+)', f)
+            if m and int(m.group(1)) > best_step:
+                best, best_step = os.path.join(logdir, f), int(m.group(1))
+    return best
 
 
 class VAETrainer(object):
@@ -109,6 +122,37 @@ class VAETrainer(object):
                     'adam_m': st['m'].cpu(), 'adam_v': st['v'].cpu(), 'global_step': self.global_step}, path)
         return path
 
+    def restore(self, logdir=None, ckpt=None, machine=None):
+        """Resume from a checkpoint written by ``save`` (the Supervisor's restore-on-start of
+        ``trainer/vae.py:78-84``; ``load`` of ``util/wrapper.py:32-62``): `ckpt` names a file inside `logdir`,
+        otherwise the newest ``model.ckpt-<step>`` there is taken.  Restores the variables, the Adam slots
+        and ``global_step``; returns the step, or None when there is nothing to restore."""
+        machine = machine if machine is not None else self.machine
+        logdir = logdir or (self.dirs or {}).get('restore_from') or (self.dirs or {}).get('logdir')
+        path = os.path.join(logdir, ckpt) if (ckpt and logdir) else latest_checkpoint(logdir)
+        if not path or not os.path.exists(path):
+            return None
+        ck = torch.load(path, map_location='cpu')
+        views = machine.variables()
+        missing = sorted(set(views) - set(ck['variables']))
+        if missing:
+            raise ValueError('checkpoint {} lacks variables: {}'.format(path, ', '.join(missing[:4])))
+        for name, v in views.items():
+            t = ck['variables'][name]
+            if tuple(t.shape) != tuple(v.shape):
+                raise ValueError('checkpoint {}: {} has shape {}, the architecture wants {}'.format(
+                    path, name, tuple(t.shape), tuple(v.shape)))
+            v.copy_(t.to(v.device))
+        if hasattr(machine, 'engine') and hasattr(machine.engine, '_packed_for'):
+            machine.engine._packed_for = None          # the variables changed behind the operand packs
+        self.machine = machine
+        st = self._ensure_state(machine)
+        if 'adam_m' in ck and 'adam_v' in ck:
+            st['m'].copy_(ck['adam_m'].to(st['m'].device)); st['v'].copy_(ck['adam_v'].to(st['v'].device))
+        self.global_step = int(ck.get('global_step', 0))
+        self.logger.info('Restored {} (global step {})'.format(path, self.global_step))
+        return self.global_step
+
     # -- hot loop (trainer/vae.py:73-99) ----------------------------------------------------
     def train(self, nIter=None, machine=None, summary_op=None, status_secs=60, save_secs=300, summary_secs=120):
         if machine is not None:
@@ -116,6 +160,10 @@ class VAETrainer(object):
         if self.machine is None:
             raise ValueError('VAETrainer needs the machine: pass `machine=` or a loss from machine.loss()')
         rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+        if self.global_step == 0 and self.dirs and (self.dirs.get('restore_from') or self.dirs.get('logdir')):
+            # tf.train.Supervisor restores the newest checkpoint of its logdir before the first step; every
+            # rank reads the same file, so the replicas stay identical
+            self.restore(ckpt=getattr(self.args, 'ckpt', None))
         t_status = t_save = t_summary = time.time()
         for step in range(self.arch['training']['max_iter'] if nIter is None else min(nIter, self.arch['training']['max_iter'])):
             self.opt['g']()
