@@ -21,6 +21,8 @@
  *     tf.trainable_variables() creation order, each in its TF layout (npvc_param_table()).
  *     Gradients / Adam moments use the same flat layout (one NCCL all-reduce bucket).
  *   - frames are frame-major: x[n,513] == NCHW [n,1,513,1] (analyzer.py:116-122).
+ *   - labels are not range-checked on the device: a label outside [0, y_dim) selects no embedding row, i.e.
+ *     contributes a zero speaker term (what tf.nn.embedding_lookup returns on a GPU), never an out-of-bounds access.
  */
 #ifndef NPVC_B200_H
 #define NPVC_B200_H
