@@ -122,7 +122,8 @@ int npvc_decode(npvc_handle* h, const float* d_theta, const float* d_z, const in
  * forward, KL + Gaussian log-density, backward.  Outputs z, mu, lv [n,z], xh [n,513],
  * d_losses[3] = {G, D_KL, logP}, d_grad[param_count] = d G / d theta (overwritten).
  * Any of d_z/d_mu/d_lv/d_xh may be NULL.  d_grad == NULL: forward + losses only.
- * loss_scale_n: the frame count the means are taken over (n for single GPU). */
+ * The loss means (and the gradient) are taken over the n frames of this call; data-parallel ranks
+ * average their gradients afterwards (all-reduce SUM, then grad_scale = 1/world in npvc_adam_step). */
 int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, const int64_t* d_y,
                       const float* d_eps, int64_t n, float* d_z, float* d_mu, float* d_lv,
                       float* d_xh, float* d_losses, float* d_grad, int32_t repack,
