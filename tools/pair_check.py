@@ -3,8 +3,10 @@ and through an engine created with NPVC_PAIR / NPVC_PAIR_OPS, outputs and gradie
 per-step times of both printed.  Every line is flushed as it is produced (a trap in the pair kernel ends the
 process: what was printed before it tells how far it got).
 
-    python tools/pair_check.py [n_frames] [ops]      # ops: comma-separated op names, "wide" (every BN >= 128 layer)
-                                                     #      or "default" (the library's shape rule)
+    python tools/pair_check.py [n_frames] [ops] [wgrad]   # ops: comma-separated op names, "wide" (every BN >= 128 layer)
+                                                          #      or "default" (the library's shape rule)
+                                                          # wgrad: 1 | 2 = NPVC_WGRAD_PAIR for the second engine (the
+                                                          #      cta_group::2 weight-gradient kernel; 2: 256-column N tiles)
 """
 import os
 import sys
@@ -24,6 +26,7 @@ def say(*a):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     ops = sys.argv[2] if len(sys.argv) > 2 else "convT_g3"
+    wgrad = sys.argv[3] if len(sys.argv) > 3 else ""
     arch = vcc2016_vae_arch()
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(n, 513, generator=g) * 2 - 1).cuda()
@@ -38,8 +41,11 @@ def main():
         os.environ["NPVC_PAIR"] = "1"                  # the library's own shape rule
     else:
         os.environ["NPVC_PAIR"] = "1"; os.environ["NPVC_PAIR_OPS"] = ops
+    if wgrad:
+        os.environ["NPVC_WGRAD_PAIR"] = wgrad
     pair = Engine(arch, "cuda:0")
-    os.environ.pop("NPVC_PAIR", None); os.environ.pop("NPVC_PAIR_OPS", None)
+    for k in ("NPVC_PAIR", "NPVC_PAIR_OPS", "NPVC_WGRAD_PAIR"):
+        os.environ.pop(k, None)
     theta = base.init_theta(0, perturb=0.1)
 
     def run(eng, grad):
@@ -80,7 +86,7 @@ def main():
         return {q["name"]: q["ms"] / iters for q in p}
     pb, pp = op_ms(base, gb), op_ms(pair, gp)
     for name in sorted(pb, key=lambda k: -pb[k]):
-        if abs(pb[name] - pp.get(name, 0.0)) > 0.01 * pb[name] + 0.002 or name in ops.split(","):
+        if abs(pb[name] - pp.get(name, 0.0)) > 0.01 * pb[name] + 0.002 or name in ops.split(",") or (wgrad and name.startswith("wgrad")):
             say("  %-16s base %.4f ms  pair %.4f ms" % (name, pb[name], pp.get(name, float("nan"))))
     say("sum of ops: base %.4f  pair %.4f" % (sum(pb.values()), sum(pp.values())))
 

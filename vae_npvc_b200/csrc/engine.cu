@@ -42,7 +42,9 @@ struct npvc_handle {
   std::map<int, TMaps> tmaps_pair;   // same, CTA-pair launches (B boxes of BN / 2 rows)
   int umma_pair = 1;                 // NPVC_PAIR=0: no cta_group::2 CTA pairs; 2: every BN >= 128 layer (A/B comparisons)
   std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the shape rule)
-  bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
+  int wgrad_pair = 0;                // NPVC_WGRAD_PAIR=1|2: cta_group::2 form of the weight-gradient kernel for N >= 128 (2: 256-column
+                                     // N tiles); opt-in: compiled and reviewed, NOT yet run on a GPU (round-2 experiment)
+  bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
   int64_t umma_launches = 0;
   int ln_bulk = 1;                   // NPVC_LN_BULK=0: shared-memory Layernorm backward for large frames (A/B comparisons)
   int wgrad_smem_kb = 225;           // NPVC_WGRAD_SMEM_KB
@@ -387,7 +389,13 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   const long long frames = c.n;
   // N tile: 16 / 32 columns in one 32B / 64B-swizzled box, else 64-column boxes (128B swizzle)
   int BN, n_tiles = 1, d_sw;
-  if (o.N <= 16) { BN = 16; d_sw = 32; }
+  const bool pair = h->wgrad_pair > 0 && o.N >= 128 && o.K > 128;      // (>= 2 K tiles, whole 64-column boxes per CTA)
+  if (pair) {
+    d_sw = 128;
+    const int t128 = (o.N + 127) / 128, t256 = (o.N + 255) / 256;
+    if (h->wgrad_pair >= 2 || 256 * t256 <= 128 * t128) { BN = 256; n_tiles = t256; } else { BN = 128; n_tiles = t128; }
+  }
+  else if (o.N <= 16) { BN = 16; d_sw = 32; }
   else if (o.N <= 32) { BN = 32; d_sw = 64; }
   else {
     d_sw = 128; BN = 64; long long best = -1;
@@ -398,12 +406,12 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   }
   const int m_tiles_k = (o.K + 127) / 128;
   // rows per stage: keep >= 3 stages in shared memory
-  const int per_row = 512 + 4 * BN;
+  const int per_row = pair ? 512 + 2 * BN : 512 + 4 * BN;          // (pair: each CTA stages half of the dC columns)
   const int budget = h->wgrad_smem_kb * 1024;       // < 227 KB leaves shared memory for a co-resident Layernorm block (side-stream overlap)
   int row_target = ((budget - 5 * 1024) / 3 / per_row) / 16 * 16; if (row_target > 128) row_target = 128; if (row_target < 16) row_target = 16;
   const RowTiling rt = make_tiling(o.A.R, frames, row_target);
   const void* a_base = resolve(c, o.A.ref); const void* d_base = resolve(c, o.C.ref);
-  auto it = h->tmaps.find(op_index);
+  auto it = h->tmaps.find(op_index);        // (the boxes do not depend on the pair form; BN and rows_tile are part of the key)
   if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != d_base || it->second.frames != frames || it->second.bn != BN ||
       it->second.rows_tile != rt.rows_tile) {
     npvc_handle::TMaps tm; tm.a = a_base; tm.b = d_base; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = 128;
@@ -414,7 +422,7 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.rt = rt; g.n_tiles = n_tiles; g.d_sw = d_sw;
   g.rows_al = (rt.rows_tile + 15) / 16 * 16;
-  const int d_boxes = (BN + d_sw / 2 - 1) / (d_sw / 2);
+  const int d_boxes = pair ? BN / 128 : (BN + d_sw / 2 - 1) / (d_sw / 2);      // per CTA
   const int d_region = (g.rows_al * d_sw + 1023) / 1024 * 1024;
   const int stage_bytes = 2 * (2 * g.rows_al * 128) + 2 * d_boxes * d_region;
   int tc = 32; while (tc < 2 * BN) tc *= 2; g.tmem_cols = tc;
@@ -422,7 +430,8 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   g.stages = stages;
   // split the reduction so that tiles * S fills whole waves of SMs, each CTA keeping enough row
   // tiles to amortise its 128 x BN atomic epilogue
-  const long long tiles = (long long)m_tiles_k * n_tiles;
+  const int grid_x = pair ? 2 * ((m_tiles_k + 1) / 2) : m_tiles_k;
+  const long long tiles = (long long)grid_x * n_tiles;
   const long long min_tiles = (512 + rt.rows_tile - 1) / rt.rows_tile;     // >= 512 rows per CTA
   long long maxS = rt.m_tiles / min_tiles; if (maxS < 1) maxS = 1; if (maxS > 4096) maxS = 4096;
   const double slots = (double)h->sm_count;
@@ -441,7 +450,20 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
     h->attr_wgrad = true;
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 1) + 16;
-  dim3 grid((unsigned)m_tiles_k, (unsigned)n_tiles, (unsigned)S);
+  dim3 grid((unsigned)grid_x, (unsigned)n_tiles, (unsigned)S);
+  if (pair) {
+    if (!h->attr_wgrad_pair) {
+      CUDA_TRY(cudaFuncSetAttribute(umma_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      h->attr_wgrad_pair = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_wgrad_pair_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
+    h->launches++; h->umma_launches++;
+    return NPVC_OK;
+  }
   umma_wgrad_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
@@ -730,6 +752,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
+  if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);
   if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty() && !h->umma_pair) h->umma_pair = 1; }
   if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
   if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }

@@ -588,14 +588,18 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 //   warp 1      TMEM allocator + MMA issuer
 //   warps 2-5   RED.ADD epilogue after the last row tile of this CTA's split
 // =============================================================================================
+// PAIR (clusters of 2 CTAs along x = two adjacent K tiles, same N tile and split): one 256 x BN cta_group::2 MMA per
+//   K step; each CTA stages its own 128 A columns and HALF of the dC columns (BN / 2, whole boxes), the leader
+//   issues and commits to both CTAs, each CTA adds its own 128 accumulator rows.  Opt-in (engine.cu) until measured.
+template <bool PAIR>
 __global__ void __launch_bounds__(192, 1)
-umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                  const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDl, UmmaArgs g) {
+umma_wgrad_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                    const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDl, UmmaArgs g) {
   using namespace umma;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int dw = g.d_sw >> 1;                                   // dC columns per box
-  const int d_boxes = (g.BN + dw - 1) / dw;
+  const int d_boxes = PAIR ? (g.BN / dw) >> 1 : (g.BN + dw - 1) / dw;      // dC boxes THIS CTA stages (PAIR: its half of the N tile)
   const uint32_t a_region = (uint32_t)g.rows_al * 128u;         // one 64-column A box (rows_al % 16 == 0 -> 1024-aligned)
   const uint32_t d_region = ((uint32_t)g.rows_al * (uint32_t)g.d_sw + 1023u) & ~1023u;
   const uint32_t a_plane = 2u * a_region, d_plane = (uint32_t)d_boxes * d_region;
@@ -609,6 +613,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * g.BN;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                       // (== blockIdx.x & 1)
   const int t_begin = (int)blockIdx.z * g.tiles_per_split;
   int t_end = t_begin + g.tiles_per_split; if (t_end > g.rt.m_tiles) t_end = g.rt.m_tiles;
   if (t_begin >= t_end) return;                       // uniform per CTA
@@ -627,18 +632,50 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)g.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - sbase));
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
-    const uint32_t tx = 2u * (2u * (uint32_t)g.rt.rows_tile * 128u + (uint32_t)d_boxes * (uint32_t)g.rt.rows_tile * (uint32_t)g.d_sw);
+    const uint32_t tx = (PAIR ? 2u : 1u) * 2u * (2u * (uint32_t)g.rt.rows_tile * 128u + (uint32_t)d_boxes * (uint32_t)g.rt.rows_tile * (uint32_t)g.d_sw);
     RingPos sp(g.stages);
+    if constexpr (PAIR) {
+      // the K tile past the last one (odd tile count) re-reads the last tile; its rows are never added (k >= K)
+      int m0l = m0; if (m0l >= g.K) m0l -= BM;
+      const int n0l = n0 + (int)rank * (g.BN >> 1);
+      for (int i = 0; i < ntl; i++, sp.advance()) {
+        const int s = sp.idx;
+        int a0, f0; tile_coords(g.rt, t_begin + i, a0, f0);
+        mbar_wait(empty_bar(s), sp.phase ^ 1u);
+        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        const uint32_t lead_full = mapa_rank(full_bar(s), 0u);
+        if (elect_one()) {
+          if (rank == 0u) mbar_expect_tx(full_bar(s), tx);
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            tma_load_4d_pair(st + (uint32_t)b * a_region, &tmAh, lead_full, m0l + 64 * b, 0, a0, f0);
+            tma_load_4d_pair(st + a_plane + (uint32_t)b * a_region, &tmAl, lead_full, m0l + 64 * b, 0, a0, f0);
+          }
+          for (int b = 0; b < d_boxes; b++) {
+            tma_load_4d_pair(st + 2u * a_plane + (uint32_t)b * d_region, &tmDh, lead_full, n0l + dw * b, 0, a0, f0);
+            tma_load_4d_pair(st + 2u * a_plane + d_plane + (uint32_t)b * d_region, &tmDl, lead_full, n0l + dw * b, 0, a0, f0);
+          }
+        }
+        __syncwarp();
+      }
+      for (int i = 0; i < g.stages; i++, sp.advance()) mbar_wait(empty_bar(sp.idx), sp.phase ^ 1u);   // producer tail (see the forward kernel)
+    } else
     for (int i = 0; i < ntl; i++, sp.advance()) {
       const int s = sp.idx;
       int a0, f0; tile_coords(g.rt, t_begin + i, a0, f0);
@@ -660,12 +697,12 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
-    const uint32_t idesc = make_idesc(g.BN, true);
+    const uint32_t idesc = make_idesc(g.BN, true, PAIR ? 2 * BM : BM);
     const int ksteps = g.rows_al >> 4;
     const uint64_t abase = sdesc_base(a_region, 128), dbase = sdesc_base(d_region, (uint32_t)g.d_sw);
     const uint32_t acc2 = tmem_base + (uint32_t)g.BN;
     RingPos sp(g.stages);
-    for (int i = 0; i < ntl; i++, sp.advance()) {
+    for (int i = (PAIR && rank != 0u) ? ntl : 0; i < ntl; i++, sp.advance()) {      // (PAIR: the leader issues for both CTAs)
       const int s = sp.idx;
       mbar_wait(full_bar(s), sp.phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -673,7 +710,19 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       const uint64_t ah0 = sdesc_at(abase, st), al0 = sdesc_at(abase, st + a_plane);
       const uint64_t dh0 = sdesc_at(dbase, st + 2u * a_plane), dl0 = sdesc_at(dbase, st + 2u * a_plane + d_plane);
       const uint64_t astep = (uint64_t)((16u * 128u) >> 4), dstep = (uint64_t)((16u * (uint32_t)g.d_sw) >> 4);   // 16 view rows per MMA
-      if (elect_one()) {
+      if constexpr (PAIR) {
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps; ks++) {
+            const uint64_t ah = ah0 + astep * ks, al = al0 + astep * ks, dh = dh0 + dstep * ks, dl = dl0 + dstep * ks;
+            const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+            mma_bf16_pair(tmem_base, ah, dh, idesc, first);
+            mma_bf16_pair(acc2, al, dh, idesc, first);
+            mma_bf16_pair(acc2, ah, dl, idesc, 1u);
+          }
+          umma_commit_pair(empty_bar(s));
+          if (i == ntl - 1) umma_commit_pair(accum_bar);
+        }
+      } else if (elect_one()) {
         for (int ks = 0; ks < ksteps; ks++) {
           const uint64_t ah = ah0 + astep * ks, al = al0 + astep * ks, dh = dh0 + dstep * ks, dl = dl0 + dstep * ks;
           const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
@@ -709,11 +758,15 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
   }
 }
+#define umma_wgrad_kernel umma_wgrad_kernel_t<false>
+#define umma_wgrad_pair_kernel umma_wgrad_kernel_t<true>
 
 }  // namespace npvc
