@@ -162,3 +162,43 @@ def test_alternative_architectures(alt_arch, umma, monkeypatch):
         assert rel(out[k], ref[k]) < tol, k
     assert rel(out["grad"], R.flatten_params(alt_arch, ref["grads"], np.float64)) < tol
     assert h.param_count() == R.n_params(alt_arch)
+
+
+def _random_arch(rs):
+    """A valid random architecture inside the plan's documented limits (kernel >= stride, channel counts that are
+    multiples of 4, a stride-1 kernel > 3 as the last generator layer): random depths, strides 1..4, even / odd
+    kernels (asymmetric SAME pads and crops), channel counts that need padding."""
+    n_gen = rs.randint(2, 4)
+    strides = [int(rs.choice([2, 3, 4])) for _ in range(n_gen - 1)] + [1]
+    gen_h = int(rs.randint(3, 12))
+    in_h = gen_h * int(np.prod(strides))
+    gk = [[int(s + rs.randint(0, 6)), 1] for s in strides[:-1]]
+    gk += [[int(rs.choice([5, 6, 2 * in_h - 1, in_h // 2 * 2 + 1, in_h + 4])), 1]]
+    gout = [int(rs.choice([4, 8, 12, 16, 24, 32])) for _ in range(n_gen - 1)] + [1]
+    n_enc = rs.randint(1, 4)
+    es = [int(rs.choice([1, 2, 3, 4])) for _ in range(n_enc)]
+    return {"hwc": [in_h, 1, 1], "z_dim": int(rs.choice([4, 8, 12, 32])), "y_dim": int(rs.randint(1, 7)),
+            "encoder": {"kernel": [[int(s + rs.randint(0, 6)), 1] for s in es], "stride": [[s, 1] for s in es],
+                        "output": [int(rs.choice([4, 8, 12, 16, 24, 32, 64])) for _ in range(n_enc)]},
+            "generator": {"hwc": [gen_h, 1, int(rs.choice([3, 5, 8, 16, 33]))], "kernel": gk,
+                          "stride": [[s, 1] for s in strides], "output": gout}}
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_architectures(seed, monkeypatch):
+    """Plan generality: the launch plan of a random architecture, executed by the numpy interpreter in both operand
+    formats (fp32 CUDA-core packs / bf16 hi-lo planes), against the oracle -- outputs and every gradient."""
+    arch = _random_arch(np.random.RandomState(seed))
+    P = R.init_params(arch, 0)
+    x, y, eps = R.make_inputs(arch, 3)
+    ref = R.forward(arch, P, x, y, eps, with_grads=True)
+    gref = R.flatten_params(arch, ref["grads"], np.float64)
+    for umma, tol in ((0, 1e-10), (1, 2e-4)):
+        monkeypatch.setenv("NPVC_UMMA", str(umma))
+        h = lib.Handle(arch)
+        tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx")}
+        out = PI.Interp(h.plan(), tables, R.flatten_params(arch, P, np.float64), 3, x, y, eps).loss_fwd_bwd()
+        for k in ("mu", "lv", "z", "xh"):
+            assert rel(out[k], ref[k]) < tol, (umma, k, arch)
+        assert rel(out["grad"], gref) < tol, (umma, arch)
+        assert h.param_count() == R.n_params(arch)
