@@ -130,6 +130,9 @@ def test_bad_architecture_raises_value_error(arch):
     bad2 = dict(arch); bad2["generator"] = dict(arch["generator"]); bad2["generator"]["output"] = [32, 16, 8]
     with pytest.raises(AssertionError):          # model/vae.py:37-39 _sanity_check
         lib.Handle(bad2)
+    with pytest.raises(ValueError):              # frames per internal pass are bounded (32-bit row / tile counts)
+        lib.Handle(arch, max_chunk=1 << 21)
+    assert lib.Handle(arch, max_chunk=1 << 20).workspace_bytes(1 << 22, True) == lib.Handle(arch, max_chunk=1 << 20).workspace_bytes(1 << 20, True)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -762,6 +762,8 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (!err.empty()) { delete h; return fail(NPVC_ERR_ARG, "unsupported architecture: " + err); }
   if (max_chunk > 0) h->max_chunk = max_chunk;
   else if (const char* mc = getenv("NPVC_MAX_CHUNK")) { long v = atol(mc); if (v > 0) h->max_chunk = v; }
+  // frames per internal pass: row counts, tile counts and TMA coordinates of a pass are 32-bit
+  if (h->max_chunk > ((int64_t)1 << 20)) { delete h; return fail(NPVC_ERR_ARG, "max_chunk > 1048576 frames per pass is not supported (larger calls are chunked by the library)"); }
   *out = h;
   return NPVC_OK;
 }
