@@ -5,8 +5,10 @@ process: what was printed before it tells how far it got).
 
     python tools/pair_check.py [n_frames] [ops] [wgrad]   # ops: comma-separated op names, "wide" (every BN >= 128 layer)
                                                           #      or "default" (the library's shape rule)
-                                                          # wgrad: 1 | 2 = NPVC_WGRAD_PAIR for the second engine (the
+                                                          # wgrad: 0 | 1 | 2 = NPVC_WGRAD_PAIR for the second engine (the
                                                           #      cta_group::2 weight-gradient kernel; 2: 256-column N tiles)
+    python tools/pair_check.py 16384 default 0 2          # 4th argument: NPVC_STREAMS for the second engine (two half-batches
+                                                          #      on two streams)
 """
 import os
 import sys
@@ -26,7 +28,8 @@ def say(*a):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     ops = sys.argv[2] if len(sys.argv) > 2 else "convT_g3"
-    wgrad = sys.argv[3] if len(sys.argv) > 3 else ""
+    wgrad = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] != "0" else ""
+    streams = sys.argv[4] if len(sys.argv) > 4 else ""
     arch = vcc2016_vae_arch()
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(n, 513, generator=g) * 2 - 1).cuda()
@@ -43,8 +46,10 @@ def main():
         os.environ["NPVC_PAIR"] = "1"; os.environ["NPVC_PAIR_OPS"] = ops
     if wgrad:
         os.environ["NPVC_WGRAD_PAIR"] = wgrad
+    if streams:
+        os.environ["NPVC_STREAMS"] = streams
     pair = Engine(arch, "cuda:0")
-    for k in ("NPVC_PAIR", "NPVC_PAIR_OPS", "NPVC_WGRAD_PAIR"):
+    for k in ("NPVC_PAIR", "NPVC_PAIR_OPS", "NPVC_WGRAD_PAIR", "NPVC_STREAMS"):
         os.environ.pop(k, None)
     theta = base.init_theta(0, perturb=0.1)
 

@@ -42,6 +42,9 @@ struct npvc_handle {
   std::map<int, TMaps> tmaps_pair;   // same, CTA-pair launches (B boxes of BN / 2 rows)
   int umma_pair = 1;                 // NPVC_PAIR=0: no cta_group::2 CTA pairs; 2: every BN >= 128 layer (A/B comparisons)
   std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the shape rule)
+  int streams = 1;                   // NPVC_STREAMS=2: a training pass runs as two half-batches on two streams (the Layernorm / loss kernels
+                                     // of one half overlap the GEMMs of the other); opt-in: NOT yet run on a GPU (round-2 experiment)
+  cudaStream_t st2 = nullptr; cudaEvent_t ev2_fork = nullptr, ev2_join = nullptr;
   int wgrad_pair = 0;                // NPVC_WGRAD_PAIR=1|2: cta_group::2 form of the weight-gradient kernel for N >= 128 (2: 256-column
                                      // N tiles); opt-in: compiled and reviewed, NOT yet run on a GPU (round-2 experiment)
   bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
@@ -71,16 +74,22 @@ struct Ctx {
   int64_t n;          // frames in this chunk
   int64_t n_total;    // frames the loss means span
   cudaStream_t st;
+  // two-stream passes (NPVC_STREAMS=2): `ws` is this chunk's activation set, `ws_sh` the set that holds what both
+  // sets share (operand packs, packed weight gradients, loss accumulators); nullptr = ws (the single-set layout)
+  float* ws_sh = nullptr;
+  int set = 0;        // activation set index (tensor-map cache key)
 };
+inline float* shared_ws(const Ctx& c) { return c.ws_sh ? c.ws_sh : c.ws; }
+inline int tmap_key(const Ctx& c, int op_index) { return op_index + (c.set << 20); }
 
 float* resolve(const Ctx& c, const Ref& r) {
   const Plan& p = c.h->plan;
   switch (r.space) {
-    case SP_WS: return c.ws + p.buf_offset(r.buf, c.chunk_cap, c.train);
+    case SP_WS: return (p.bufs[r.buf].per_frame == 0 ? shared_ws(c) : c.ws) + p.buf_offset(r.buf, c.chunk_cap, c.train);
     case SP_THETA: return const_cast<float*>(c.theta) + r.off;
     case SP_GRAD: return c.grad ? c.grad + r.off : nullptr;
-    case SP_AW: return c.ws + r.off;
-    case SP_ADW: return c.ws + p.buf_offset(p.buf_adw, c.chunk_cap, c.train) + r.off;
+    case SP_AW: return shared_ws(c) + r.off;
+    case SP_ADW: return shared_ws(c) + p.buf_offset(p.buf_adw, c.chunk_cap, c.train) + r.off;
     case SP_USER:
       if (r.buf == U_X) return const_cast<float*>(c.x);
       if (r.buf == U_EPS) return const_cast<float*>(c.eps);
@@ -221,9 +230,10 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
   npvc_handle* h = c.h; cudaStream_t st = c.st;
   const RowTiling& rt = tg.rt; const int BN = tg.BN, sw = tg.sw, C = o.tap_C;
   const void* a_base = resolve(c, o.A.ref);
-  uint16_t* arena16 = reinterpret_cast<uint16_t*>(c.ws + h->plan.aw16_off);
+  uint16_t* arena16 = reinterpret_cast<uint16_t*>(shared_ws(c) + h->plan.aw16_off);
   uint16_t* b_hi = arena16 + o.bu_hi; uint16_t* b_lo = arena16 + o.bu_lo;
-  auto it = h->tmaps.find(op_index);
+  const int key = tmap_key(c, op_index);
+  auto it = h->tmaps.find(key);
   if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != rt.frames || it->second.bn != BN || it->second.sw != -sw) {
     npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = rt.frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = -sw;   // (negative: tap-mode maps)
     // A: (column within the s*C wide position group, row-in-group incl. halo, row-group, frame); groups overlap by the halo
@@ -247,7 +257,7 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
                              swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(tap B) failed for " + o.name + " code " + std::to_string((int)r));
     }
-    h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
+    h->tmaps[key] = tm; it = h->tmaps.find(key);
   }
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = 1; g.rt = rt; g.n_tiles = 1; g.sw = sw;
@@ -284,9 +294,10 @@ int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, con
   npvc_handle* h = c.h; cudaStream_t st = c.st;
   const int sw = 128, bk = 64;
   const void* a_base = resolve(c, o.A.ref);
-  uint16_t* arena16 = reinterpret_cast<uint16_t*>(c.ws + h->plan.aw16_off);
+  uint16_t* arena16 = reinterpret_cast<uint16_t*>(shared_ws(c) + h->plan.aw16_off);
   uint16_t* b_hi = arena16 + o.bu_hi; uint16_t* b_lo = arena16 + o.bu_lo;
-  auto it = h->tmaps_pair.find(op_index);
+  const int key = tmap_key(c, op_index);
+  auto it = h->tmaps_pair.find(key);
   if (it == h->tmaps_pair.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != rt.frames || it->second.bn != BN) {
     npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = rt.frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = sw;
     int rc = make_view_maps(h, c, o.A, o.K, rt, bk, sw, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
@@ -299,7 +310,7 @@ int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, con
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(pair B) failed for " + o.name + " code " + std::to_string((int)r));
     }
-    h->tmaps_pair[op_index] = tm; it = h->tmaps_pair.find(op_index);
+    h->tmaps_pair[key] = tm; it = h->tmaps_pair.find(key);
   }
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + bk - 1) / bk; g.rt = rt; g.n_tiles = n_tiles; g.sw = sw;
@@ -344,9 +355,10 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   if (o.K <= 32) sw = 64;
   const int bk = sw / 2;
   const void* a_base = resolve(c, o.A.ref);
-  uint16_t* arena16 = reinterpret_cast<uint16_t*>(c.ws + h->plan.aw16_off);
+  uint16_t* arena16 = reinterpret_cast<uint16_t*>(shared_ws(c) + h->plan.aw16_off);
   uint16_t* b_hi = arena16 + o.bu_hi; uint16_t* b_lo = arena16 + o.bu_lo;
-  auto it = h->tmaps.find(op_index);
+  const int key = tmap_key(c, op_index);
+  auto it = h->tmaps.find(key);
   if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != b_hi || it->second.frames != frames || it->second.bn != BN || it->second.sw != sw) {
     npvc_handle::TMaps tm; tm.a = a_base; tm.b = b_hi; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = sw;
     int rc = make_view_maps(h, c, o.A, o.K, rt, bk, sw, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
@@ -359,7 +371,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
                              sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(NPVC_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed for " + o.name + " code " + std::to_string((int)r));
     }
-    h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
+    h->tmaps[key] = tm; it = h->tmaps.find(key);
   }
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + bk - 1) / bk; g.rt = rt; g.n_tiles = n_tiles; g.sw = sw;
@@ -411,13 +423,14 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   int row_target = ((budget - 5 * 1024) / 3 / per_row) / 16 * 16; if (row_target > 128) row_target = 128; if (row_target < 16) row_target = 16;
   const RowTiling rt = make_tiling(o.A.R, frames, row_target);
   const void* a_base = resolve(c, o.A.ref); const void* d_base = resolve(c, o.C.ref);
-  auto it = h->tmaps.find(op_index);        // (the boxes do not depend on the pair form; BN and rows_tile are part of the key)
+  const int key = tmap_key(c, op_index);
+  auto it = h->tmaps.find(key);             // (the boxes do not depend on the pair form; BN and rows_tile are part of the check)
   if (it == h->tmaps.end() || it->second.a != a_base || it->second.b != d_base || it->second.frames != frames || it->second.bn != BN ||
       it->second.rows_tile != rt.rows_tile) {
     npvc_handle::TMaps tm; tm.a = a_base; tm.b = d_base; tm.frames = frames; tm.bn = BN; tm.rows_tile = rt.rows_tile; tm.sw = 128;
     int rc = make_view_maps(h, c, o.A, o.K, rt, 64, 128, &tm.tAh, &tm.tAl, o.name); if (rc) return rc;
     rc = make_view_maps(h, c, o.C, o.N, rt, d_sw / 2, d_sw, &tm.tBh, &tm.tBl, o.name); if (rc) return rc;
-    h->tmaps[op_index] = tm; it = h->tmaps.find(op_index);
+    h->tmaps[key] = tm; it = h->tmaps.find(key);
   }
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.rt = rt; g.n_tiles = n_tiles; g.d_sw = d_sw;
@@ -503,7 +516,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
     }
     case OP_UNPACK: {
       long long n = p.n_params;
-      const float* adw = c.ws + p.buf_offset(p.buf_adw, c.chunk_cap, c.train);
+      const float* adw = shared_ws(c) + p.buf_offset(p.buf_adw, c.chunk_cap, c.train);
       unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(adw, h->d_unpack_ptr, h->d_unpack_idx, c.grad, n);
       h->launches++;
       if (h->n_heavy > 0) {
@@ -614,7 +627,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
     }
     case OP_SAMPLE: {
       const int z = o.i0, fpb = 8;
-      double* acc = reinterpret_cast<double*>(c.ws + p.buf_offset(p.buf_acc, c.chunk_cap, c.train));
+      double* acc = reinterpret_cast<double*>(shared_ws(c) + p.buf_offset(p.buf_acc, c.chunk_cap, c.train));
       sample_kl_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 2 * z, 0, st>>>(
           resolve(c, o.r0), c.eps, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), c.eps ? acc : nullptr, z, c.n, fpb);
       h->launches++; break;
@@ -626,7 +639,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       h->launches++; break;
     }
     case OP_RECON: {
-      double* acc = reinterpret_cast<double*>(c.ws + p.buf_offset(p.buf_acc, c.chunk_cap, c.train)) + 1;
+      double* acc = reinterpret_cast<double*>(shared_ws(c) + p.buf_offset(p.buf_acc, c.chunk_cap, c.train)) + 1;
       const int wpb = 8;
       recon_kernel<<<(unsigned)((c.n + wpb - 1) / wpb), wpb * 32, 0, st>>>(
           c.x, resolve(c, o.r1), c.grad ? resolve(c, o.r2) : nullptr, c.grad ? resolve(c, o.r3) : nullptr, acc,
@@ -753,6 +766,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);
+  if (const char* ns = getenv("NPVC_STREAMS")) h->streams = atoi(ns) >= 2 ? 2 : 1;
   if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty() && !h->umma_pair) h->umma_pair = 1; }
   if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
   if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }
@@ -771,6 +785,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
 void npvc_destroy(npvc_handle* h) {
   if (!h) return;
   if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+  if (h->st2) { cudaStreamDestroy(h->st2); cudaEventDestroy(h->ev2_fork); cudaEventDestroy(h->ev2_join); }
   if (h->tables_on_device) { cudaFree(h->d_pack_src); cudaFree(h->d_pack16_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); cudaFree(h->d_heavy); }
   delete h;
 }
@@ -791,10 +806,19 @@ int npvc_param_table(const npvc_handle* h, npvc_param_desc* out, int32_t max) {
   return NPVC_OK;
 }
 
+// Two-stream training passes (NPVC_STREAMS=2): frames per half-batch, 0 = the call runs as one stream of chunks
+static int64_t half_chunk(const npvc_handle* h, int64_t n) {
+  if (h->streams < 2 || n < 256) return 0;
+  const int64_t chunk = n < h->max_chunk ? n : h->max_chunk;
+  return ((chunk + 1) / 2 + 127) / 128 * 128;
+}
+static int64_t set_floats(const npvc_handle* h, int64_t cap2) { return (h->plan.ws_floats(cap2, true) + 63) / 64 * 64; }
+
 int64_t npvc_workspace_bytes(const npvc_handle* h, int64_t n, int32_t train) {
   if (!h || n < 0) return -1;
   int64_t chunk = n < h->max_chunk ? n : h->max_chunk;
   if (chunk < 1) chunk = 1;
+  if (train) { const int64_t cap2 = half_chunk(h, n); if (cap2) return 2 * set_floats(h, cap2) * 4; }   // two activation sets
   return h->plan.ws_floats(chunk, train != 0) * 4;
 }
 
@@ -917,8 +941,13 @@ int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, co
   if (!d_theta || !d_x || !d_y || !d_eps || n < 1) return fail(NPVC_ERR_ARG, "bad argument");
   rc = ensure_tables(h); if (rc) return rc;
   const Plan& p = h->plan; cudaStream_t st = (cudaStream_t)stream;
-  const int64_t cap = n < h->max_chunk ? n : h->max_chunk; const int z = p.arch.z_dim, H = p.arch.in_h;
+  const int64_t cap2 = h->profiling ? 0 : half_chunk(h, n);          // > 0: two half-batches on two streams
+  const int64_t cap = cap2 ? cap2 : (n < h->max_chunk ? n : h->max_chunk); const int z = p.arch.z_dim, H = p.arch.in_h;
   float* ws = (float*)d_ws;
+  if (cap2 && !h->st2) {
+    if (cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess) return fail(NPVC_ERR_CUDA, "cudaStreamCreate failed");
+    cudaEventCreateWithFlags(&h->ev2_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev2_join, cudaEventDisableTiming);
+  }
   CUDA_TRY(cudaMemsetAsync(ws + p.buf_offset(p.buf_acc, cap, true), 0, 8 * 4, st));
   if (d_grad) {
     CUDA_TRY(cudaMemsetAsync(d_grad, 0, (size_t)p.n_params * 4, st));
@@ -928,14 +957,27 @@ int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, co
     Ctx c{h, ws, cap, true, d_theta, nullptr, nullptr, nullptr, nullptr, 0, n, st};
     rc = run_phase(c, PH_PACK); if (rc) return rc;
   }
-  for (int64_t c0 = 0; c0 < n; c0 += cap) {
+  if (cap2) {      // the second stream starts behind the memsets / packs above
+    CUDA_TRY(cudaEventRecord(h->ev2_fork, st)); CUDA_TRY(cudaStreamWaitEvent(h->st2, h->ev2_fork, 0));
+  }
+  int chunk_index = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += cap, chunk_index++) {
     int64_t m = n - c0 < cap ? n - c0 : cap;
-    Ctx c{h, ws, cap, true, d_theta, d_grad, d_x + c0 * H, d_y + c0, d_eps + c0 * z, m, n, st};
+    // two-stream passes: odd chunks use the second activation set on the second stream; the operand packs, the packed
+    // weight gradients (RED.ADD), the flat gradient (atomics) and the loss sums (atomics) are shared by both sets
+    const int set = cap2 ? (chunk_index & 1) : 0;
+    float* wset = ws + (set ? set_floats(h, cap2) : 0);
+    const cudaStream_t cst = set ? h->st2 : st;
+    Ctx c{h, wset, cap, true, d_theta, d_grad, d_x + c0 * H, d_y + c0, d_eps + c0 * z, m, n, cst};
+    if (cap2) { c.ws_sh = ws; c.set = set; }
     for (int ph : {PH_ENC, PH_SAMPLE, PH_DEC, PH_LOSS}) { rc = run_phase(c, ph); if (rc) return rc; }
     if (d_grad) { rc = run_phase(c, PH_BWD); if (rc) return rc; }
     struct { float* dst; int buf; int w; } outs[4] = {{d_z, p.buf_z, z}, {d_mu, p.buf_mu, z}, {d_lv, p.buf_lv, z}, {d_xh, p.buf_xh, H}};
     for (auto& o : outs)
-      if (o.dst) CUDA_TRY(cudaMemcpyAsync(o.dst + c0 * o.w, ws + p.buf_offset(o.buf, cap, true), (size_t)m * o.w * 4, cudaMemcpyDeviceToDevice, st));
+      if (o.dst) CUDA_TRY(cudaMemcpyAsync(o.dst + c0 * o.w, wset + p.buf_offset(o.buf, cap, true), (size_t)m * o.w * 4, cudaMemcpyDeviceToDevice, cst));
+  }
+  if (cap2) {      // join: everything the second stream did happens-before what follows on the caller's stream
+    CUDA_TRY(cudaEventRecord(h->ev2_join, h->st2)); CUDA_TRY(cudaStreamWaitEvent(st, h->ev2_join, 0));
   }
   if (d_grad) {
     Ctx c{h, ws, cap, true, d_theta, d_grad, nullptr, nullptr, nullptr, 0, n, st};
