@@ -318,6 +318,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cfg2: ConvVAE (architecture-vae-vcc2016) 10-speaker, %d frames/GPU/step (64x256), fwd+bwd+Adam" % n,
                        "frames_per_gpu_per_step": n, "global_frames_per_step": n * world, "parallelism": "dp%d" % world,
+                       "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("NPVC_")},   # library A/B switches in effect ({} = defaults)
                        "l2": "per-step working set (%.1f GB activations) >> 126 MB L2; %d distinct input batches cycled"
                              % (machine.engine.handle.workspace_bytes(n, True) / 1e9, NPOOL)},
             "clocks": clocks,
