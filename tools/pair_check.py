@@ -3,12 +3,10 @@ and through an engine created with NPVC_PAIR / NPVC_PAIR_OPS, outputs and gradie
 per-step times of both printed.  Every line is flushed as it is produced (a trap in the pair kernel ends the
 process: what was printed before it tells how far it got).
 
-    python tools/pair_check.py [n_frames] [ops] [wgrad]   # ops: comma-separated op names, "wide" (every BN >= 128 layer)
-                                                          #      or "default" (the library's shape rule)
-                                                          # wgrad: 0 | 1 | 2 = NPVC_WGRAD_PAIR for the second engine (the
-                                                          #      cta_group::2 weight-gradient kernel; 2: 256-column N tiles)
-    python tools/pair_check.py 16384 default 0 2          # 4th argument: NPVC_STREAMS for the second engine (two half-batches
-                                                          #      on two streams)
+    python tools/pair_check.py [n_frames] [ops] [NPVC_X=v ...]
+        ops: comma-separated op names for the pair form, "wide" (every BN >= 128 layer) or "default" (the library's rule)
+        NPVC_X=v: further switches for the second engine only, e.g. NPVC_WGRAD_PAIR=2 (cta_group::2 weight-gradient
+        kernel, 256-column N tiles), NPVC_STREAMS=2 (two half-batches on two streams), NPVC_PAIR_TRIM=1
 """
 import os
 import sys
@@ -28,8 +26,8 @@ def say(*a):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     ops = sys.argv[2] if len(sys.argv) > 2 else "convT_g3"
-    wgrad = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] != "0" else ""
-    streams = sys.argv[4] if len(sys.argv) > 4 else ""
+    extra = dict(a.split("=", 1) for a in sys.argv[3:])
+    wgrad = extra.get("NPVC_WGRAD_PAIR", "")
     arch = vcc2016_vae_arch()
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(n, 513, generator=g) * 2 - 1).cuda()
@@ -44,12 +42,9 @@ def main():
         os.environ["NPVC_PAIR"] = "1"                  # the library's own shape rule
     else:
         os.environ["NPVC_PAIR"] = "1"; os.environ["NPVC_PAIR_OPS"] = ops
-    if wgrad:
-        os.environ["NPVC_WGRAD_PAIR"] = wgrad
-    if streams:
-        os.environ["NPVC_STREAMS"] = streams
+    os.environ.update(extra)
     pair = Engine(arch, "cuda:0")
-    for k in ("NPVC_PAIR", "NPVC_PAIR_OPS", "NPVC_WGRAD_PAIR", "NPVC_STREAMS"):
+    for k in ["NPVC_PAIR", "NPVC_PAIR_OPS"] + list(extra):
         os.environ.pop(k, None)
     theta = base.init_theta(0, perturb=0.1)
 
@@ -62,7 +57,7 @@ def main():
     gb = torch.empty_like(theta); ob = run(base, gb)
     say("base ok  losses", ob["losses"].tolist(), "%.2fs" % (time.time() - t0))
     gp = torch.empty_like(theta); op = run(pair, gp)
-    say("pair ok  losses", op["losses"].tolist(), "ops =", ops)
+    say("pair ok  losses", op["losses"].tolist(), "ops =", ops, extra)
 
     def rel(a, b):
         return float((a - b).abs().max() / (b.abs().max() + 1e-30))

@@ -45,6 +45,8 @@ struct npvc_handle {
   int streams = 1;                   // NPVC_STREAMS=2: a training pass runs as two half-batches on two streams (the Layernorm / loss kernels
                                      // of one half overlap the GEMMs of the other); opt-in: NOT yet run on a GPU (round-2 experiment)
   cudaStream_t st2 = nullptr; cudaEvent_t ev2_fork = nullptr, ev2_join = nullptr;
+  int pair_trim = 0;                 // NPVC_PAIR_TRIM=1: the pair form skips the all-zero K steps of the last k-block (opt-in, not yet run on a GPU)
+  bool attr_pair_trim = false;
   int wgrad_pair = 0;                // NPVC_WGRAD_PAIR=1|2: cta_group::2 form of the weight-gradient kernel for N >= 128 (2: 256-column
                                      // N tiles); opt-in: compiled and reviewed, NOT yet run on a GPU (round-2 experiment)
   bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
@@ -333,6 +335,13 @@ int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, con
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (h->pair_trim && (o.K % bk) != 0) {
+    if (!h->attr_pair_trim) {
+      CUDA_TRY(cudaFuncSetAttribute(umma_fwd_pair_trim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      h->attr_pair_trim = true;
+    }
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_fwd_pair_trim_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
+  } else
   CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_fwd_pair_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
   h->launches++; h->umma_launches++;
   return NPVC_OK;
@@ -766,6 +775,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);
+  if (const char* pt = getenv("NPVC_PAIR_TRIM")) h->pair_trim = atoi(pt);
   if (const char* ns = getenv("NPVC_STREAMS")) h->streams = atoi(ns) >= 2 ? 2 : 1;
   if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty() && !h->umma_pair) h->umma_pair = 1; }
   if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
