@@ -45,6 +45,8 @@ struct npvc_handle {
   int streams = 1;                   // NPVC_STREAMS=2: a training pass runs as two half-batches on two streams (the Layernorm / loss kernels
                                      // of one half overlap the GEMMs of the other); opt-in: NOT yet run on a GPU (round-2 experiment)
   cudaStream_t st2 = nullptr; cudaEvent_t ev2_fork = nullptr, ev2_join = nullptr;
+  int bn_cap = 256, bn_cap_k = 1 << 30;   // NPVC_BN_CAP=128 [NPVC_BN_CAP_K=k]: N tiles <= 128 columns for window-mode layers with K <= k
+                                     // (two accumulator sets in TMEM: epilogue / mainloop overlap for the short-K layers); opt-in experiment
   int pair_trim = 0;                 // NPVC_PAIR_TRIM=1: the pair form skips the all-zero K steps of the last k-block (opt-in, not yet run on a GPU)
   bool attr_pair_trim = false;
   int wgrad_pair = 0;                // NPVC_WGRAD_PAIR=1|2: cta_group::2 form of the weight-gradient kernel for N >= 128 (2: 256-column
@@ -159,13 +161,16 @@ void launch_wgrad(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
 }
 
 // ---- tcgen05 path ---------------------------------------------------------------------------
-int pick_bn(int N, int* n_tiles) {
-  if (N <= 256) { *n_tiles = 1; return (N + 15) / 16 * 16; }
-  int best_bn = 256, best_t = (N + 255) / 256; long long best_cost = (long long)best_bn * best_t;
-  const int t0 = (N + 255) / 256;
+// N tile of the window-mode forward kernel: the fewest padded columns among tile counts near N / cap (cap = 256, the
+// MMA limit; NPVC_BN_CAP=128 keeps 2 * 2 * BN <= 512 TMEM columns, i.e. two accumulator sets, so that the epilogue of a
+// short-K tile overlaps the next tile's mainloop -- an experiment, not yet measured)
+int pick_bn(int N, int cap, int* n_tiles) {
+  if (N <= cap) { *n_tiles = 1; return (N + 15) / 16 * 16; }
+  int best_bn = cap, best_t = (N + cap - 1) / cap; long long best_cost = (long long)best_bn * best_t;
+  const int t0 = (N + cap - 1) / cap;
   for (int t = t0; t <= t0 + 6; t++) {
     int bn = ((N + t - 1) / t + 15) / 16 * 16;
-    if (bn > 256) continue;
+    if (bn > cap) continue;
     long long cost = (long long)bn * t;
     if (cost < best_cost) { best_cost = cost; best_bn = bn; best_t = t; }
   }
@@ -354,7 +359,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
     const TapGeom tg = tap_geometry(o, frames);
     if (tg.ok) return launch_umma_tap(c, o, op_index, tg);
   }
-  int n_tiles = 1; const int BN = pick_bn(o.N, &n_tiles);
+  int n_tiles = 1; const int BN = pick_bn(o.N, (h->bn_cap < 256 && o.K <= h->bn_cap_k) ? h->bn_cap : 256, &n_tiles);
   const RowTiling rt = make_tiling(o.A.R, frames, 128);
   if (pair_wanted(h, o, BN, rt.m_tiles)) return launch_umma_pair(c, o, op_index, BN, n_tiles, rt);
   // k-block: 64 bf16 (128-byte swizzled rows) when >= 4 such stages fit, else 32 (64-byte rows): the
@@ -776,6 +781,8 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);
   if (const char* pt = getenv("NPVC_PAIR_TRIM")) h->pair_trim = atoi(pt);
+  if (const char* bc = getenv("NPVC_BN_CAP")) { int v = atoi(bc); if (v >= 64 && v <= 256 && v % 16 == 0) h->bn_cap = v; }
+  if (const char* bk = getenv("NPVC_BN_CAP_K")) { int v = atoi(bk); if (v > 0) h->bn_cap_k = v; }
   if (const char* ns = getenv("NPVC_STREAMS")) h->streams = atoi(ns) >= 2 ? 2 : 1;
   if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty() && !h->umma_pair) h->umma_pair = 1; }
   if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
