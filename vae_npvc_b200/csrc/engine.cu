@@ -715,8 +715,20 @@ int run_phase(Ctx& c, int phase) {
   return NPVC_OK;
 }
 
+void free_tables(npvc_handle* h) {
+  cudaFree(h->d_pack_src); cudaFree(h->d_pack16_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); cudaFree(h->d_heavy);   // (cudaFree(nullptr) is a no-op)
+  h->d_pack_src = h->d_pack16_src = h->d_unpack_ptr = h->d_unpack_idx = h->d_heavy = nullptr;
+  h->tables_on_device = false;
+}
+
+int upload_tables(npvc_handle* h);
 int ensure_tables(npvc_handle* h) {
   if (h->tables_on_device) return NPVC_OK;
+  const int rc = upload_tables(h);
+  if (rc) free_tables(h);            // a failed upload leaves nothing behind: the next call starts over
+  return rc;
+}
+int upload_tables(npvc_handle* h) {
   int dev = 0, cnt = 0;
   cudaError_t e = cudaGetDeviceCount(&cnt);
   if (e != cudaSuccess || cnt == 0) return fail(NPVC_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
@@ -803,7 +815,7 @@ void npvc_destroy(npvc_handle* h) {
   if (!h) return;
   if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
   if (h->st2) { cudaStreamDestroy(h->st2); cudaEventDestroy(h->ev2_fork); cudaEventDestroy(h->ev2_join); }
-  if (h->tables_on_device) { cudaFree(h->d_pack_src); cudaFree(h->d_pack16_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); cudaFree(h->d_heavy); }
+  if (h->tables_on_device) free_tables(h);
   delete h;
 }
 
