@@ -181,3 +181,19 @@ def test_trainer_checkpoint_resume_roundtrip(tmp_path):
     t4 = tv.VAETrainer({"G": 0.0}, arch, None, dirs); t4.machine = Other(4)
     with pytest.raises(ValueError):
         t4.restore()
+
+
+def test_convert_f0_follows_the_reference_chain(tmp_path):
+    """convert.py:51-57: three chained tf.where's, each on the UPDATED value -- log where f0 > 1, the Gaussian
+    transform where the log is > 1, exp where the transformed value is > 1 (so an f0 in (1, e] comes out as its
+    logarithm, as in the reference); unvoiced frames (f0 = 0) pass through."""
+    import convert
+    etc = tmp_path / "etc"; etc.mkdir()
+    np.array([5.0, 0.3], np.float32).tofile(str(etc / "SF1.npf")); np.array([4.5, 0.2], np.float32).tofile(str(etc / "TM3.npf"))
+    f0 = np.array([0.0, 0.5, 2.0, 100.0, 220.0], np.float32)
+    out = convert.convert_f0(f0, "SF1", "TM3", etc=str(etc))
+    lf = np.log(f0[3:].astype(np.float64))
+    want = np.exp((lf - 5.0) / np.float32(0.3) * np.float32(0.2) + 4.5)
+    assert out.dtype == np.float32 and out[0] == 0.0 and out[1] == 0.5
+    assert abs(out[2] - np.log(2.0)) < 1e-6                       # log(2) = 0.69 is not > 1: stays the logarithm
+    assert np.allclose(out[3:], want, rtol=1e-5)
