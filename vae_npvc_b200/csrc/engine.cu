@@ -361,7 +361,13 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   }
   int n_tiles = 1; const int BN = pick_bn(o.N, (h->bn_cap < 256 && o.K <= h->bn_cap_k) ? h->bn_cap : 256, &n_tiles);
   const RowTiling rt = make_tiling(o.A.R, frames, 128);
-  if (pair_wanted(h, o, BN, rt.m_tiles)) return launch_umma_pair(c, o, op_index, BN, n_tiles, rt);
+  if (pair_wanted(h, o, BN, rt.m_tiles)) {
+    const int rc = launch_umma_pair(c, o, op_index, BN, n_tiles, rt);
+    if (rc == NPVC_OK || h->umma_pair >= 2 || !h->pair_ops.empty()) return rc;     // (an explicit request reports its failure)
+    // the cluster launch was refused (a device / partition that cannot co-schedule two such CTAs): the single-CTA
+    // form of the same kernel computes bit-identical results -- use it from now on
+    cudaGetLastError(); h->umma_pair = 0;
+  }
   // k-block: 64 bf16 (128-byte swizzled rows) when >= 4 such stages fit, else 32 (64-byte rows): the
   // same bytes in flight at twice the pipeline granularity (wide N tiles are L2-latency-bound otherwise)
   int sw = 128;
