@@ -1,0 +1,217 @@
+"""Host launch logic of engine.cu without a GPU: the product's host objects run against a recording CUDA-runtime stub
+(tests/hoststub.py, tests/cuda_stub/) and every launch is checked against the invariants the kernels rely on --
+shared-memory and TMEM budgets, tile geometry, the cuTensorMapEncodeTiled rules, tensor extents inside the caller's
+workspace, bytes per TMA box == bytes the kernels expect per stage, fork / join structure of the internal streams --
+for the reference architecture, the alternative and random ones, small to full batch sizes and every library switch
+(including the ones that have not run on a GPU yet)."""
+import numpy as np
+import pytest
+
+import hoststub as HS
+from conftest import ALT_ARCHS
+from test_plan import _random_arch
+from vae_npvc_b200 import vcc2016_vae_arch
+
+SMEM_MAX = 227 * 1024
+BF16, SWZ_BYTES = 9, {1: 32, 2: 64, 3: 128}        # CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_{32,64,128}B
+
+
+def _rup(v, m):
+    return (v + m - 1) // m * m
+
+
+def check_tmap(t, rec, what):
+    """cuTensorMapEncodeTiled's documented requirements + the tensor lies inside the caller's workspace."""
+    assert t["dtype"] == BF16 and t["interleave"] == 0 and t["swizzle"] in SWZ_BYTES, what
+    assert t["base"] % 16 == 0, (what, "global address must be 16-byte aligned")
+    assert all(1 <= d <= 2 ** 32 for d in t["dims"]), (what, t["dims"])
+    assert all(s % 16 == 0 and 0 < s < 2 ** 40 for s in t["strides"]), (what, t["strides"])
+    assert all(1 <= b <= 256 for b in t["box"]) and all(e == 1 for e in t["estrides"]), (what, t["box"])
+    inner = t["box"][0] * 2
+    assert inner % 16 == 0 and inner <= SWZ_BYTES[t["swizzle"]], (what, "inner box bytes vs swizzle span", t["box"], t["swizzle"])
+    last = t["base"] + t["dims"][0] * 2 + sum((d - 1) * s for d, s in zip(t["dims"][1:], t["strides"]))
+    assert rec.ws_lo <= t["base"] and last <= rec.ws_hi, (what, "tensor extent leaves the workspace", last - rec.ws_hi)
+
+
+def box_bytes(t):
+    return 2 * int(np.prod(t["box"]))
+
+
+def check_recording(rec, n):
+    assert rec.rc == 0, rec.err
+    assert rec.launch_count >= len(rec.launches) > 0
+    for L in rec.launches:
+        name, u = L["name"], L["umma"]
+        assert all(g >= 1 for g in L["grid"]) and 1 <= L["block"][0] <= 1024 and L["smem"] <= SMEM_MAX, L
+        assert L["grid"][1] <= 65535 and L["grid"][2] <= 65535, L
+        if L["cluster_x"] > 1:
+            assert L["cluster_x"] == 2 and L["grid"][0] % 2 == 0, L
+        if u is None:
+            continue
+        tm = [rec.tmaps[i] for i in L["tmap"]]
+        assert all(i >= 0 for i in L["tmap"]), (name, "kernel launched without encoded tensor maps")
+        for i, t in enumerate(tm):
+            check_tmap(t, rec, (name, i, u["K"], u["N"]))
+        pair = "ILb1" in name
+        assert pair == (L["cluster_x"] == 2), name
+        assert u["frames"] >= 1 and u["m_tiles"] >= 1 and u["rows_tile"] <= 128 and u["rows_tile"] == u["RbH"] * u["Ab"] * u["FB"], u
+        tc = u["tmem_cols"]
+        assert tc in (32, 64, 128, 256, 512), u
+        if "umma_fwd_kernel_t" in name:
+            BN, sw, st = u["BN"], u["sw"], u["stages"]
+            assert BN % 16 == 0 and 16 <= BN <= 256 and u["acc_sets"] in (1, 2, 4) and tc >= u["acc_sets"] * 2 * BN, u
+            groups = (L["block"][0] - 64) // 128
+            assert L["block"][0] == 64 + 128 * groups and groups in (1, 2, 4) and groups <= u["acc_sets"] and u["acc_sets"] % groups == 0, (L["block"], u)
+            assert u["n_tiles"] * BN >= u["N"] and (u["n_tiles"] - 1) * BN < u["N"], u
+            assert tm[0]["rank"] == 4 and tm[1]["rank"] == 4 and tm[2]["rank"] == 2 and tm[3]["rank"] == 2
+            if u["tapT"] > 0:                                     # tap mode
+                assert not pair and sw == 2 * u["tapC"] and sw in (32, 64, 128) and st >= 2 and u["n_tiles"] == 1, u
+                assert u["b_tile_al"] % 1024 == 0 and u["b_tile_al"] >= BN * sw, u
+                ring = u["tapT"] * 2 * u["b_tile_al"] + st * u["tapP"] * 2 * 128 * sw
+                assert box_bytes(tm[0]) == u["rows_tile"] * sw and box_bytes(tm[2]) == BN * sw, (u, tm[0]["box"], tm[2]["box"])
+                assert L["grid"][0] <= 148 and L["grid"][0] <= u["m_tiles"]
+            else:                                                 # window mode (single CTA or CTA pair)
+                assert sw in (64, 128) and st >= 1 and u["kblocks"] == -(-u["K"] // (sw // 2)), u
+                bt = (BN // 2 if pair else BN) * sw
+                ring = st * (2 * 128 * sw + 2 * bt)
+                assert box_bytes(tm[0]) == u["rows_tile"] * sw and box_bytes(tm[2]) == bt, (u, tm[0]["box"], tm[2]["box"])
+                if pair:
+                    assert sw == 128 and bt % 1024 == 0 and u["m_tiles"] >= 2 and L["grid"][0] <= 148, u
+                    assert L["grid"][0] // 2 <= -(-u["m_tiles"] // 2) * u["n_tiles"], (L["grid"], u)
+                else:
+                    assert L["grid"][0] <= min(148, u["m_tiles"] * u["n_tiles"]), (L["grid"], u)
+            # 1024-byte alignment slack + ring + barriers + TMEM slot + bias staging of up to 4 epilogue groups
+            assert L["smem"] >= 1023 + ring + 8 * (2 * st + 10) + 16 + 4096, (name, L["smem"], ring, u)
+            assert tm[0]["box"] == tm[1]["box"] and tm[2]["box"] == tm[3]["box"]
+        else:                                                     # weight-gradient kernel
+            BN, dsw, st, ral = u["BN"], u["d_sw"], u["stages"], u["rows_al"]
+            assert dsw in (32, 64, 128) and 16 <= BN <= 256 and BN % 16 == 0 and tc >= 2 * BN, u
+            assert ral % 16 == 0 and ral >= u["rows_tile"] and ral - u["rows_tile"] < 16 and st >= 1, u
+            dw = dsw // 2
+            if pair:
+                assert dsw == 128 and BN % (2 * dw) == 0, u
+                d_boxes = BN // dw // 2
+            else:
+                d_boxes = -(-BN // dw)
+            stage = 2 * (2 * ral * 128) + 2 * d_boxes * _rup(ral * dsw, 1024)
+            assert L["smem"] >= 1023 + st * stage + 8 * (2 * st + 1) + 8 + 4, (name, L["smem"], st, stage, u)
+            gx, gy, gz = L["grid"]
+            assert gx * 128 >= u["K"] and (gx - (2 if pair else 1)) * 128 < u["K"], (L["grid"], u)
+            assert gy * BN >= u["N"] and (gy - 1) * BN < u["N"] and gz * u["tiles_per_split"] >= u["m_tiles"] > (gz - 1) * u["tiles_per_split"], (L["grid"], u)
+            assert box_bytes(tm[0]) == u["rows_tile"] * 128 and box_bytes(tm[2]) == u["rows_tile"] * dsw, (u, tm[0]["box"], tm[2]["box"])
+            assert all(t["rank"] == 4 for t in tm) and u["out_ptr"] >= rec.ws_lo and u["out_ptr"] < rec.ws_hi
+    check_streams(rec)
+
+
+def check_streams(rec, caller=0):
+    """Everything issued on an internal stream happens-before the end of the call on the caller's stream (event record /
+    wait edges, transitively), and nothing on an internal stream starts before the call's first operation."""
+    clock, snap, last = {}, {}, {}                          # clock[s][t] = last seq of stream t that stream s has observed
+    for o in sorted(rec.ops, key=lambda o: o["seq"]):
+        s = o["stream"]
+        c = clock.setdefault(s, {})
+        if o["kind"] == 1:                                  # event record: what the stream has done / seen so far
+            e = dict(c); e[s] = o["seq"]
+            snap[o["event"]] = e
+        elif o["kind"] == 2:                                # stream wait
+            assert o["event"] in snap, "wait on an event that was never recorded"
+            for k, v in snap[o["event"]].items():
+                c[k] = max(c.get(k, -1), v)
+        else:                                               # launch / memset / memcpy
+            if s != caller:
+                assert caller in c, "internal stream %#x ran without a fork from the caller's stream" % s
+            last[s] = o["seq"]
+        c[s] = o["seq"]
+    seen = clock.get(caller, {})
+    for s, q in last.items():
+        if s != caller:
+            assert seen.get(s, -1) >= q, "work on internal stream %#x is not joined into the caller's stream" % s
+
+
+SWITCHES = {
+    "default": {},
+    "single_cta": {"NPVC_PAIR": "0"},
+    "pair_wide": {"NPVC_PAIR": "2"},
+    "pair_trim": {"NPVC_PAIR": "2", "NPVC_PAIR_TRIM": "1"},
+    "wgrad_pair": {"NPVC_WGRAD_PAIR": "1"},
+    "wgrad_pair_256": {"NPVC_WGRAD_PAIR": "2"},
+    "two_streams": {"NPVC_STREAMS": "2"},
+    "bn_cap": {"NPVC_BN_CAP": "128"},
+    "everything": {"NPVC_PAIR": "2", "NPVC_PAIR_TRIM": "1", "NPVC_WGRAD_PAIR": "2", "NPVC_STREAMS": "2", "NPVC_BN_CAP": "128"},
+    "window_only": {"NPVC_UMMA_TAP": "0"},
+    "no_overlap": {"NPVC_OVERLAP": "0"},
+}
+
+
+@pytest.mark.parametrize("switch", sorted(SWITCHES))
+@pytest.mark.parametrize("n", [1, 37, 64, 300, 4096, 16384])
+def test_reference_architecture_launches(n, switch):
+    check_recording(HS.record_loss_fwd_bwd(vcc2016_vae_arch(), n, SWITCHES[switch]), n)
+
+
+@pytest.mark.parametrize("switch", ["default", "everything"])
+@pytest.mark.parametrize("name", sorted(ALT_ARCHS))
+def test_alternative_architecture_launches(name, switch):
+    for n in (3, 29, 2048):
+        check_recording(HS.record_loss_fwd_bwd(ALT_ARCHS[name], n, SWITCHES[switch]), n)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_architecture_launches(seed):
+    arch = _random_arch(np.random.RandomState(seed))
+    for n, sw in ((5, "default"), (1000, "default"), (1000, "everything")):
+        check_recording(HS.record_loss_fwd_bwd(arch, n, SWITCHES[sw]), n)
+
+
+def test_chunked_and_repeated_calls():
+    """Calls larger than max_chunk run as chunks (the tensor-map cache must follow the changing frame count of the last
+    chunk), a second call reuses the cached maps, forward-only calls launch no backward work."""
+    arch = vcc2016_vae_arch()
+    r = HS.record_loss_fwd_bwd(arch, 40, max_chunk=16)
+    check_recording(r, 40)
+    frames = sorted({L["umma"]["frames"] for L in r.launches if L["umma"]})
+    assert frames == [8, 16]
+    r1 = HS.record_loss_fwd_bwd(arch, 16384)
+    r2 = HS.record_loss_fwd_bwd(arch, 16384, calls=2)
+    assert r2.rc == 0 and r2.tmaps == [], "a repeated call on the same buffers must hit the tensor-map cache"
+    key = lambda L: (L["name"], L["grid"], L["block"], L["smem"], L["cluster_x"], L["stream"] != 0)
+    assert [key(L) for L in r2.launches] == [key(L) for L in r1.launches]
+    r3 = HS.record_loss_fwd_bwd(arch, 64, with_grad=False)
+    check_recording(r3, 64)
+    assert not any("wgrad" in L["name"] or "ln_bwd" in L["name"] or "unpack" in L["name"] for L in r3.launches)
+    r4 = HS.record_loss_fwd_bwd(arch, 40000, {"NPVC_STREAMS": "2"}, max_chunk=16384)      # 5 half-batch chunks on alternating streams
+    check_recording(r4, 40000)
+    assert len({L["stream"] for L in r4.launches}) == 3                                    # caller, second stream, wgrad side stream
+
+
+def test_default_rule_pairs_only_the_measured_shapes():
+    """pair_wanted (engine.cu): at cfg2 size the CTA-pair form runs G3 forward / dgrad, E4, heads, E4 dgrad and the merge
+    dgrad (BN >= 128, >= 8 k-blocks, >= 64 M tiles); small batches keep the single-CTA form."""
+    arch = vcc2016_vae_arch()
+    big = HS.record_loss_fwd_bwd(arch, 16384)
+    pairs = sorted((L["umma"]["K"], L["umma"]["N"]) for L in big.launches if L["cluster_x"] == 2)
+    assert pairs == sorted([(4104, 513), (513, 4104), (896, 256), (768, 256), (768, 384), (1672, 128)]), pairs
+    small = HS.record_loss_fwd_bwd(arch, 64)
+    assert not any(L["cluster_x"] == 2 for L in small.launches)
+
+
+def test_refused_cluster_launch_falls_back_to_the_single_cta_form():
+    arch = vcc2016_vae_arch()
+    r = HS.record_loss_fwd_bwd(arch, 16384, fail_cluster=1)
+    check_recording(r, 16384)
+    assert not any(L["cluster_x"] == 2 for L in r.launches)
+    ref = HS.record_loss_fwd_bwd(arch, 16384, {"NPVC_PAIR": "0"})
+    assert [(L["name"], L["grid"], L["block"], L["smem"]) for L in r.launches] == [(L["name"], L["grid"], L["block"], L["smem"]) for L in ref.launches]
+    r2 = HS.record_loss_fwd_bwd(arch, 16384, {"NPVC_PAIR": "2"}, fail_cluster=1)           # an explicit request reports the failure
+    assert r2.rc != 0
+
+
+@pytest.mark.parametrize("n", [1, 23, 700, 16384, 40000])
+def test_inference_path_launches(n):
+    """encode -> decode (convert.py path; cfg3 runs as 16,384-frame chunks plus a ragged last chunk): inference workspace
+    layout, no backward kernels."""
+    rec = HS.record_encode_decode(vcc2016_vae_arch(), n)
+    check_recording(rec, n)
+    assert not any(k in L["name"] for L in rec.launches for k in ("wgrad", "ln_bwd", "unpack", "recon", "adam"))
+    if n == 40000:
+        assert sorted({L["umma"]["frames"] for L in rec.launches if L["umma"]}) == [40000 - 2 * 16384, 16384]

@@ -5,15 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-namespace npvc {
+#include "launch_args.h"
 
-// Strided row view (see plan.h): element (row, k) lives at
-//   p + (row / R) * fs + (row % R) * rs + off + k,  valid (when pred) iff 0 <= (row%R)*rs+off+k < flen
-// split != 0 (plan.h, Buf::split): the buffer holds bf16 hi / lo planes per frame -- element e of frame f
-// is  hi[f*2*fs + e] + lo[f*2*fs + fs + e]  (bf16 units from p), the tensor-core operand format.
-struct DView {
-  float* p; long long fs; int R, rs, off, flen, pred, split;
-};
+namespace npvc {
 
 // ---- bf16 hi / lo planes ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t split_pack2(float a, float b, uint32_t& lo) {

@@ -1,0 +1,50 @@
+// Plain (host + device) argument structs of the kernels: no device code, so host-only tools (the recording CUDA
+// runtime stub of tests/cuda_stub) can decode what engine.cu launches.
+#pragma once
+#include <stdint.h>
+
+namespace npvc {
+
+// Strided row view (see plan.h): element (row, k) lives at
+//   p + (row / R) * fs + (row % R) * rs + off + k,  valid (when pred) iff 0 <= (row%R)*rs+off+k < flen
+// split != 0 (plan.h, Buf::split): the buffer holds bf16 hi / lo planes per frame -- element e of frame f
+// is  hi[f*2*fs + e] + lo[f*2*fs + fs + e]  (bf16 units from p), the tensor-core operand format.
+struct DView {
+  float* p; long long fs; int R, rs, off, flen, pred, split;
+};
+
+// Tiling of a view's rows into <= 128-row tiles of whole (frame, row-group) boxes:
+//   row-in-frame j = a * Rb + b  (b < Rb, a < Ra);  a tile = FB frames x Ab row-groups x Rb rows
+//   (FB > 1 only when Ra == 1).  Local row r = (fl * Ab + al) * Rb + b.
+struct RowTiling {
+  int Rb, Ra, Ab, FB, TA;     // TA = ceil(Ra / Ab) tiles per frame block
+  int RbH;                    // accumulator rows per row-group: Rb, or Rb + halo rows in tap mode (halo rows are discarded)
+  int rows_tile;              // RbH * Ab * FB
+  int frames, m_tiles;        // m_tiles = ceil(frames / FB) * TA
+};
+
+struct UmmaArgs {
+  int K, N;              // logical GEMM sizes (wgrad: dB is [K, N])
+  int BN;                // N tile
+  int kblocks;           // (F): ceil(K / bk)
+  int sw;                // (F): swizzle span = bytes of one operand row per k-block: 128 (bk = 64) or 64 (bk = 32)
+  int stages;
+  int tmem_cols;
+  RowTiling rt;
+  // (F)
+  int n_tiles, acc_sets;
+  // tap mode (conv-shaped views, tapT > 0): the tile's positions are loaded ONCE as tapP phase tiles of
+  // [rows + halo][tapC] (no window overlap); tap t = tapP * m + ph multiplies phase tile ph shifted by m
+  // rows (row-shifted K-major descriptor) with the resident weight tile of tap t.  sw = 2 * tapC bytes.
+  int tapT, tapC, tapP;
+  int b_tile_al;         // tap mode: bytes of one resident weight tile (BN * sw rounded up to 1024)
+  DView C;
+  const float* bias0; const float* bias1; const float* bias2; int bias_mod;
+  // (W)
+  int d_sw;              // swizzle span (bytes) of the dC boxes: 128 / 64 / 32 -> 64 / 32 / 16 columns per box
+  int rows_al;           // rows_tile rounded up to 16 (MMA K step)
+  int tiles_per_split;
+  float* out; int ld;
+};
+
+}  // namespace npvc
