@@ -215,3 +215,23 @@ def test_inference_path_launches(n):
     assert not any(k in L["name"] for L in rec.launches for k in ("wgrad", "ln_bwd", "unpack", "recon", "adam"))
     if n == 40000:
         assert sorted({L["umma"]["frames"] for L in rec.launches if L["umma"]}) == [40000 - 2 * 16384, 16384]
+
+
+def test_two_stream_sets_are_disjoint_and_share_the_packs():
+    """NPVC_STREAMS=2: the half-batch on the second stream works in the second activation set (upper half of the
+    workspace), the caller's half in the first; both read the same weight packs (first set) and both halves cover
+    the batch."""
+    rec = HS.record_loss_fwd_bwd(vcc2016_vae_arch(), 16384, {"NPVC_STREAMS": "2"})
+    check_recording(rec, 16384)
+    half = rec.ws_lo + (rec.ws_hi - rec.ws_lo) // 2
+    fwd = [L for L in rec.launches if "umma_fwd_kernel_t" in L["name"]]
+    streams = sorted({L["stream"] for L in fwd})
+    assert streams[0] == 0 and len(streams) == 2
+    for L in fwd:
+        a, b = rec.tmaps[L["tmap"][0]], rec.tmaps[L["tmap"][2]]
+        assert b["base"] < half, "weight packs live in the first set"
+        assert (a["base"] >= half) == (L["stream"] != 0), "activation operands must come from the stream's own set"
+        assert (L["umma"]["c_ptr"] >= half) == (L["stream"] != 0), "outputs must go to the stream's own set"
+        assert L["umma"]["frames"] == 8192
+    per_stream = {s: [L["umma"]["K"] for L in fwd if L["stream"] == s] for s in streams}
+    assert per_stream[streams[0]] == per_stream[streams[1]]          # the same op sequence on both halves
