@@ -7,6 +7,7 @@
 # 3. cfg3 / cfg5 timings, launch list and ncu --set full of the pair kernel (G3 forward)
 mkdir -p gpurun_out; O=gpurun_out
 python -m pytest tests -m gpu -x -q > $O/r2a_gpu_tests.txt 2>&1; tail -3 $O/r2a_gpu_tests.txt
+NPVC_TEST_EXPERIMENTS=1 python -m pytest tests -m gpu -q -k experimental > $O/r2a_gpu_experiments.txt 2>&1; tail -15 $O/r2a_gpu_experiments.txt
 python bench.py --steps 20 --warmup 5 > $O/r2a_bench.json 2> $O/r2a_bench.err; cut -c1-400 $O/r2a_bench.json
 for sw in NPVC_WGRAD_PAIR=1 NPVC_WGRAD_PAIR=2 NPVC_STREAMS=2 NPVC_PAIR_TRIM=1 NPVC_BN_CAP=128 "NPVC_BN_CAP=128 NPVC_BN_CAP_K=1024"; do
   f=$O/r2a_switch_$(echo $sw | tr ' =' '__').txt
