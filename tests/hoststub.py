@@ -4,6 +4,7 @@ what engine.cu would have launched -- kernels, launch geometry, UmmaArgs, tensor
 comes back as Python dicts.  Nothing here is on a product path.
 """
 import ctypes as C
+import json
 import os
 import subprocess
 
@@ -141,6 +142,7 @@ def record_loss_fwd_bwd(arch, n, env=None, with_grad=True, max_chunk=0, fail_clu
                                        losses.ctypes.data, grad.ctypes.data if with_grad else None, 1, ws.ctypes.data, nbytes, None)
         rec = Recording(dll, ws.ctypes.data, ws.ctypes.data + nbytes, rc, dll.npvc_last_error().decode() if rc else "")
         rec.launch_count = int(dll.npvc_launch_count(h))
+        rec.plan, rec.train = json.loads(dll.npvc_plan_json(h).decode()), True
         return rec
     finally:
         dll.stub_fail_cluster_launches(0)
@@ -179,6 +181,19 @@ def record_encode_decode(arch, n, env=None, max_chunk=0):
         rc = rc or dll.npvc_decode(h, theta.ctypes.data, mu.ctypes.data, y.ctypes.data, n, xh.ctypes.data, ws.ctypes.data, nbytes, None)
         rec = Recording(dll, ws.ctypes.data, ws.ctypes.data + nbytes, rc, dll.npvc_last_error().decode() if rc else "")
         rec.launch_count = int(dll.npvc_launch_count(h))
+        rec.plan, rec.train = json.loads(dll.npvc_plan_json(h).decode()), False
         return rec
     finally:
         dll.npvc_destroy(h)
+
+
+def buffer_ranges(plan, chunk, train):
+    """[(name, first float, floats per frame, is-split)] of the per-frame workspace buffers for a pass over `chunk` frames
+    (Plan::buf_offset of plan.cpp restated: 64-float aligned buffers behind the operand-pack arena)."""
+    rup = lambda v: (v + 63) // 64 * 64
+    off, out = rup(plan["arena_w"]), []
+    for b in plan["bufs"]:
+        sz = 0 if (b["train_only"] and not train) else rup(b["fixed"] + b["per_frame"] * chunk)
+        out.append((b["name"], off, off + sz, b["per_frame"], b["split"]))
+        off += sz
+    return out

@@ -235,3 +235,52 @@ def test_two_stream_sets_are_disjoint_and_share_the_packs():
         assert L["umma"]["frames"] == 8192
     per_stream = {s: [L["umma"]["K"] for L in fwd if L["stream"] == s] for s in streams}
     assert per_stream[streams[0]] == per_stream[streams[1]]          # the same op sequence on both halves
+
+
+def _check_operand_rows_stay_in_their_plane(rec, chunk):
+    """The rule learned from the NaN * 0 bug: an A / dC operand box may never read bits from outside its own
+    frame's plane, not even to multiply them by a zero weight.  For every 4-D operand map: the bytes reachable inside
+    one frame -- (k extent) + (rows - 1) * row stride + (row groups - 1) * group stride -- measured from where the map
+    starts inside its bf16 plane, must end inside that plane.  (Columns beyond dims[0] are TMA zero fill and never read;
+    accumulator rows the epilogue discards may hold anything: rows are independent.)"""
+    bufs = HS.buffer_ranges(rec.plan, chunk, rec.train)
+    checked = 0
+    for L in rec.launches:
+        if not L["umma"]:
+            continue
+        for i in L["tmap"]:
+            t = rec.tmaps[i]
+            if t["rank"] != 4:
+                continue
+            pos = (t["base"] - rec.ws_lo) // 4                      # float index of the map's first element (hi or lo plane)
+            hit = [b for b in bufs if b[1] <= pos < b[2]]
+            assert len(hit) == 1 and hit[0][4], (L["name"], "operand map outside the split buffers", pos)
+            name, lo, hi, per_frame, _ = hit[0]
+            plane = per_frame * 2                                       # bytes of one bf16 plane of a frame
+            start = (t["base"] - rec.ws_lo - lo * 4) % (per_frame * 4) % plane
+            s_r, s_a, s_f = t["strides"]
+            assert s_f == per_frame * 4 or t["dims"][3] == 1, (name, "frame stride")
+            inner = t["dims"][0] * 2
+            u = L["umma"]
+            if u["tapT"] > 0 and "umma_fwd" in L["name"]:
+                # tap mode: the last halo row of a row group is read by the valid output rows only up to the phase of the last
+                # tap (T - 1 = P * m + pz); what lies behind it feeds the discarded halo accumulator rows alone
+                inner = ((u["tapT"] - 1) % u["tapP"] + 1) * u["tapC"] * 2
+            reach = inner + (t["dims"][1] - 1) * (s_r if t["dims"][1] > 1 else 0) + (t["dims"][2] - 1) * (s_a if t["dims"][2] > 1 else 0)
+            assert start + reach <= plane, (L["name"], name, "operand rows leave their plane by %d bytes" % (start + reach - plane), t)
+            checked += 1
+    return checked
+
+
+@pytest.mark.parametrize("switch", ["default", "pair_wide", "window_only", "bn_cap", "wgrad_pair_256"])
+def test_operand_boxes_never_leave_their_frame(switch):
+    arch = vcc2016_vae_arch()
+    for n in (8, 300, 16384):
+        rec = HS.record_loss_fwd_bwd(arch, n, SWITCHES[switch])
+        assert _check_operand_rows_stay_in_their_plane(rec, min(n, 16384)) > 40
+    for name in sorted(ALT_ARCHS):
+        rec = HS.record_loss_fwd_bwd(ALT_ARCHS[name], 29, SWITCHES[switch])
+        _check_operand_rows_stay_in_their_plane(rec, 29)
+    for seed in range(12):
+        rec = HS.record_loss_fwd_bwd(_random_arch(np.random.RandomState(seed)), 50, SWITCHES[switch])
+        _check_operand_rows_stay_in_their_plane(rec, 50)
