@@ -284,3 +284,38 @@ def test_operand_boxes_never_leave_their_frame(switch):
     for seed in range(12):
         rec = HS.record_loss_fwd_bwd(_random_arch(np.random.RandomState(seed)), 50, SWITCHES[switch])
         _check_operand_rows_stay_in_their_plane(rec, 50)
+
+
+def _check_epilogue_stores_stay_in_their_frame(rec, chunk):
+    """Forward / dgrad epilogues write row j of a frame at in-frame element j * rs + off, N columns wide: inside the
+    frame (or clipped to [0, flen) when the view is predicated), in a per-frame buffer of the workspace."""
+    bufs = HS.buffer_ranges(rec.plan, chunk, rec.train)
+    n = 0
+    for L in rec.launches:
+        u = L["umma"]
+        if not u or "umma_fwd" not in L["name"]:
+            continue
+        pos = (u["c_ptr"] - rec.ws_lo) // 4
+        hit = [b for b in bufs if b[1] <= pos < b[2]]
+        assert len(hit) == 1 and pos == hit[0][1], (L["name"], "output view does not start at a workspace buffer", pos)
+        name, lo, hi, per_frame, split = hit[0]
+        assert u["c_fs"] == per_frame and bool(u["c_split"]) == bool(split), (name, u)
+        for j in (0, u["c_R"] - 1):
+            inf = j * u["c_rs"] + u["c_off"]
+            if u["c_pred"]:
+                assert 0 < u["c_flen"] <= per_frame, (name, u)
+            else:
+                assert 0 <= inf and inf + u["N"] <= per_frame, (name, "row %d writes [%d, %d) of a %d-element frame" % (j, inf, inf + u["N"], per_frame))
+        n += 1
+    return n
+
+
+@pytest.mark.parametrize("switch", ["default", "pair_wide", "window_only", "bn_cap"])
+def test_epilogue_stores_stay_in_their_frame(switch):
+    for n in (8, 16384):
+        rec = HS.record_loss_fwd_bwd(vcc2016_vae_arch(), n, SWITCHES[switch])
+        assert _check_epilogue_stores_stay_in_their_frame(rec, n) >= 15
+    for name in sorted(ALT_ARCHS):
+        _check_epilogue_stores_stay_in_their_frame(HS.record_loss_fwd_bwd(ALT_ARCHS[name], 29, SWITCHES[switch]), 29)
+    for seed in range(12):
+        _check_epilogue_stores_stay_in_their_frame(HS.record_loss_fwd_bwd(_random_arch(np.random.RandomState(seed)), 50, SWITCHES[switch]), 50)
