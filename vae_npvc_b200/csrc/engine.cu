@@ -166,12 +166,12 @@ void launch_wgrad(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
 // short-K tile overlaps the next tile's mainloop -- an experiment, not yet measured)
 int pick_bn(int N, int cap, int* n_tiles) {
   if (N <= cap) { *n_tiles = 1; return (N + 15) / 16 * 16; }
-  int best_bn = cap, best_t = (N + cap - 1) / cap; long long best_cost = (long long)best_bn * best_t;
+  int best_bn = cap, best_t = (N + cap - 1) / cap; long long best_cost = (long long)best_bn * best_t + (cap < 256 ? 8LL * best_t : 0LL);
   const int t0 = (N + cap - 1) / cap;
   for (int t = t0; t <= t0 + 6; t++) {
     int bn = ((N + t - 1) / t + 15) / 16 * 16;
     if (bn > cap) continue;
-    long long cost = (long long)bn * t;
+    long long cost = (long long)bn * t + (cap < 256 ? 8LL * t : 0LL);     // (capped tiles: do not trade tile width for a few padded columns)
     if (cost < best_cost) { best_cost = cost; best_bn = bn; best_t = t; }
   }
   *n_tiles = best_t; return best_bn;
@@ -294,8 +294,9 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
 bool pair_wanted(const npvc_handle* h, const Op& o, int BN, int m_tiles) {
   if (!h->umma_pair || m_tiles < 2 || o.K <= 32 || (BN & 15)) return false;
   if (!h->pair_ops.empty()) return ("," + h->pair_ops + ",").find("," + o.name + ",") != std::string::npos;
-  if (h->umma_pair >= 2) return BN >= 128;
-  return BN >= 128 && o.K > 7 * 64 && m_tiles >= 64;
+  const int bn_min = h->bn_cap < 256 ? 96 : 128;          // (capped N tiles, an experiment: 112-column tiles still pair)
+  if (h->umma_pair >= 2) return BN >= bn_min;
+  return BN >= bn_min && o.K > 7 * 64 && m_tiles >= 64;
 }
 int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, const RowTiling& rt) {
   npvc_handle* h = c.h; cudaStream_t st = c.st;
@@ -425,7 +426,7 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   if (pair) {
     d_sw = 128;
     const int t128 = (o.N + 127) / 128, t256 = (o.N + 255) / 256;
-    if (h->wgrad_pair >= 2 || 256 * t256 <= 128 * t128) { BN = 256; n_tiles = t256; } else { BN = 128; n_tiles = t128; }
+    if ((h->wgrad_pair >= 2 && o.N > 128) || 256 * t256 <= 128 * t128) { BN = 256; n_tiles = t256; } else { BN = 128; n_tiles = t128; }
   }
   else if (o.N <= 16) { BN = 16; d_sw = 32; }
   else if (o.N <= 32) { BN = 32; d_sw = 64; }
