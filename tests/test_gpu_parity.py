@@ -281,8 +281,7 @@ def test_cta_pair_form_is_bit_identical_to_single_cta(arch, monkeypatch):
 
 
 EXPERIMENTS = {                    # library switches written without a GPU (DESIGN.md "Next"): run with NPVC_TEST_EXPERIMENTS=1
-    "wgrad_pair": {"NPVC_WGRAD_PAIR": "1"}, "wgrad_pair_256": {"NPVC_WGRAD_PAIR": "2"}, "two_streams": {"NPVC_STREAMS": "2"},
-    "pair_trim": {"NPVC_PAIR_TRIM": "1"}, "bn_cap": {"NPVC_BN_CAP": "128"},
+    "wgrad_pair": {"NPVC_WGRAD_PAIR": "1"}, "wgrad_pair_256": {"NPVC_WGRAD_PAIR": "2"},
 }
 
 

@@ -132,12 +132,9 @@ SWITCHES = {
     "default": {},
     "single_cta": {"NPVC_PAIR": "0"},
     "pair_wide": {"NPVC_PAIR": "2"},
-    "pair_trim": {"NPVC_PAIR": "2", "NPVC_PAIR_TRIM": "1"},
     "wgrad_pair": {"NPVC_WGRAD_PAIR": "1"},
     "wgrad_pair_256": {"NPVC_WGRAD_PAIR": "2"},
-    "two_streams": {"NPVC_STREAMS": "2"},
-    "bn_cap": {"NPVC_BN_CAP": "128"},
-    "everything": {"NPVC_PAIR": "2", "NPVC_PAIR_TRIM": "1", "NPVC_WGRAD_PAIR": "2", "NPVC_STREAMS": "2", "NPVC_BN_CAP": "128"},
+    "everything": {"NPVC_PAIR": "2", "NPVC_WGRAD_PAIR": "2"},
     "window_only": {"NPVC_UMMA_TAP": "0"},
     "no_overlap": {"NPVC_OVERLAP": "0"},
 }
@@ -179,9 +176,9 @@ def test_chunked_and_repeated_calls():
     r3 = HS.record_loss_fwd_bwd(arch, 64, with_grad=False)
     check_recording(r3, 64)
     assert not any("wgrad" in L["name"] or "ln_bwd" in L["name"] or "unpack" in L["name"] for L in r3.launches)
-    r4 = HS.record_loss_fwd_bwd(arch, 40000, {"NPVC_STREAMS": "2"}, max_chunk=16384)      # 5 half-batch chunks on alternating streams
+    r4 = HS.record_loss_fwd_bwd(arch, 40000, max_chunk=16384)                              # 2 full chunks + a ragged one
     check_recording(r4, 40000)
-    assert len({L["stream"] for L in r4.launches}) == 3                                    # caller, second stream, wgrad side stream
+    assert len({L["stream"] for L in r4.launches}) == 2                                    # caller, wgrad side stream
 
 
 def test_default_rule_pairs_only_the_measured_shapes():
@@ -215,26 +212,6 @@ def test_inference_path_launches(n):
     assert not any(k in L["name"] for L in rec.launches for k in ("wgrad", "ln_bwd", "unpack", "recon", "adam"))
     if n == 40000:
         assert sorted({L["umma"]["frames"] for L in rec.launches if L["umma"]}) == [40000 - 2 * 16384, 16384]
-
-
-def test_two_stream_sets_are_disjoint_and_share_the_packs():
-    """NPVC_STREAMS=2: the half-batch on the second stream works in the second activation set (upper half of the
-    workspace), the caller's half in the first; both read the same weight packs (first set) and both halves cover
-    the batch."""
-    rec = HS.record_loss_fwd_bwd(vcc2016_vae_arch(), 16384, {"NPVC_STREAMS": "2"})
-    check_recording(rec, 16384)
-    half = rec.ws_lo + (rec.ws_hi - rec.ws_lo) // 2
-    fwd = [L for L in rec.launches if "umma_fwd_kernel_t" in L["name"]]
-    streams = sorted({L["stream"] for L in fwd})
-    assert streams[0] == 0 and len(streams) == 2
-    for L in fwd:
-        a, b = rec.tmaps[L["tmap"][0]], rec.tmaps[L["tmap"][2]]
-        assert b["base"] < half, "weight packs live in the first set"
-        assert (a["base"] >= half) == (L["stream"] != 0), "activation operands must come from the stream's own set"
-        assert (L["umma"]["c_ptr"] >= half) == (L["stream"] != 0), "outputs must go to the stream's own set"
-        assert L["umma"]["frames"] == 8192
-    per_stream = {s: [L["umma"]["K"] for L in fwd if L["stream"] == s] for s in streams}
-    assert per_stream[streams[0]] == per_stream[streams[1]]          # the same op sequence on both halves
 
 
 def _check_operand_rows_stay_in_their_plane(rec, chunk):
@@ -272,7 +249,7 @@ def _check_operand_rows_stay_in_their_plane(rec, chunk):
     return checked
 
 
-@pytest.mark.parametrize("switch", ["default", "pair_wide", "window_only", "bn_cap", "wgrad_pair_256"])
+@pytest.mark.parametrize("switch", ["default", "pair_wide", "window_only", "wgrad_pair_256"])
 def test_operand_boxes_never_leave_their_frame(switch):
     arch = vcc2016_vae_arch()
     for n in (8, 300, 16384):
@@ -310,7 +287,7 @@ def _check_epilogue_stores_stay_in_their_frame(rec, chunk):
     return n
 
 
-@pytest.mark.parametrize("switch", ["default", "pair_wide", "window_only", "bn_cap"])
+@pytest.mark.parametrize("switch", ["default", "pair_wide", "window_only"])
 def test_epilogue_stores_stay_in_their_frame(switch):
     for n in (8, 16384):
         rec = HS.record_loss_fwd_bwd(vcc2016_vae_arch(), n, SWITCHES[switch])

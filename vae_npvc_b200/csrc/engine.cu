@@ -42,13 +42,6 @@ struct npvc_handle {
   std::map<int, TMaps> tmaps_pair;   // same, CTA-pair launches (B boxes of BN / 2 rows)
   int umma_pair = 1;                 // NPVC_PAIR=0: no cta_group::2 CTA pairs; 2: every BN >= 128 layer (A/B comparisons)
   std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the shape rule)
-  int streams = 1;                   // NPVC_STREAMS=2: a training pass runs as two half-batches on two streams (the Layernorm / loss kernels
-                                     // of one half overlap the GEMMs of the other); opt-in: NOT yet run on a GPU (round-2 experiment)
-  cudaStream_t st2 = nullptr; cudaEvent_t ev2_fork = nullptr, ev2_join = nullptr;
-  int bn_cap = 256, bn_cap_k = 1 << 30;   // NPVC_BN_CAP=128 [NPVC_BN_CAP_K=k]: N tiles <= 128 columns for window-mode layers with K <= k
-                                     // (two accumulator sets in TMEM: epilogue / mainloop overlap for the short-K layers); opt-in experiment
-  int pair_trim = 0;                 // NPVC_PAIR_TRIM=1: the pair form skips the all-zero K steps of the last k-block (opt-in, not yet run on a GPU)
-  bool attr_pair_trim = false;
   int wgrad_pair = 0;                // NPVC_WGRAD_PAIR=1|2: cta_group::2 form of the weight-gradient kernel for N >= 128 (2: 256-column
                                      // N tiles); opt-in: compiled and reviewed, NOT yet run on a GPU (round-2 experiment)
   bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
@@ -59,7 +52,6 @@ struct npvc_handle {
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int umma_groups = 4;               // NPVC_UMMA_GROUPS: epilogue groups of the forward kernel (1, 2 or 4; <= accumulator sets)
   int umma_tap = 1;                  // NPVC_UMMA_TAP=0: conv-shaped layers through the overlapping-window boxes (A/B comparisons)
-  int umma_min_stages = 0;           // NPVC_UMMA_MIN_STAGES (experiments): below this many 64-wide k-block stages use 32-wide ones (measured slower: more TMA row requests)
   bool profiling = false;
   struct Ev { int op; cudaEvent_t a, b; long long rows, frames; };
   std::vector<Ev> events;
@@ -78,13 +70,9 @@ struct Ctx {
   int64_t n;          // frames in this chunk
   int64_t n_total;    // frames the loss means span
   cudaStream_t st;
-  // two-stream passes (NPVC_STREAMS=2): `ws` is this chunk's activation set, `ws_sh` the set that holds what both
-  // sets share (operand packs, packed weight gradients, loss accumulators); nullptr = ws (the single-set layout)
-  float* ws_sh = nullptr;
-  int set = 0;        // activation set index (tensor-map cache key)
 };
-inline float* shared_ws(const Ctx& c) { return c.ws_sh ? c.ws_sh : c.ws; }
-inline int tmap_key(const Ctx& c, int op_index) { return op_index + (c.set << 20); }
+inline float* shared_ws(const Ctx& c) { return c.ws; }
+inline int tmap_key(const Ctx&, int op_index) { return op_index; }
 
 float* resolve(const Ctx& c, const Ref& r) {
   const Plan& p = c.h->plan;
@@ -161,9 +149,12 @@ void launch_wgrad(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
 }
 
 // ---- tcgen05 path ---------------------------------------------------------------------------
-// N tile of the window-mode forward kernel: the fewest padded columns among tile counts near N / cap (cap = 256, the
-// MMA limit; NPVC_BN_CAP=128 keeps 2 * 2 * BN <= 512 TMEM columns, i.e. two accumulator sets, so that the epilogue of a
-// short-K tile overlaps the next tile's mainloop -- an experiment, not yet measured)
+// N tile of the window-mode forward kernel: the fewest padded columns among tile counts near N / cap.  cap = 256 is
+// the MMA limit; bn_cap() lowers it to 128 for the short-K layers: 2 * 2 * BN <= 512 TMEM columns leave room for two
+// accumulator sets, so the epilogue of a tile overlaps the next tile's mainloop (measured on a B200,
+// profiles/r2a_switches.txt: E4 dgrad 0.099 -> 0.068 ms, E4 0.072 -> 0.064, E3 dgrad 0.078 -> 0.065, heads dgrad
+// 0.049 -> 0.044; the long-K G3 forward and the 4104-column G3 dgrad were faster with wide tiles and keep them)
+inline int bn_cap(const Op& o) { return (o.K <= 1024 && o.N <= 1024) ? 128 : 256; }
 int pick_bn(int N, int cap, int* n_tiles) {
   if (N <= cap) { *n_tiles = 1; return (N + 15) / 16 * 16; }
   int best_bn = cap, best_t = (N + cap - 1) / cap; long long best_cost = (long long)best_bn * best_t + (cap < 256 ? 8LL * best_t : 0LL);
@@ -228,7 +219,6 @@ TapGeom tap_geometry(const Op& o, long long frames) {
   r.frames = (int)frames; r.m_tiles = (int)(((frames + r.FB - 1) / r.FB) * r.TA);
   const int bres = T * 2 * t.b_tile_al, stage = t.P * 2 * 128 * t.sw;
   t.stages = (225 * 1024 - 6144 - bres) / stage; if (t.stages > 8) t.stages = 8;
-  if (const char* ts = getenv("NPVC_TAP_STAGES")) { int v = atoi(ts); if (v >= 2 && v < t.stages) t.stages = v; }   // (experiments: leave shared memory to co-resident kernels)
   t.ok = t.stages >= 2;
   return t;
 }
@@ -294,7 +284,7 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
 bool pair_wanted(const npvc_handle* h, const Op& o, int BN, int m_tiles) {
   if (!h->umma_pair || m_tiles < 2 || o.K <= 32 || (BN & 15)) return false;
   if (!h->pair_ops.empty()) return ("," + h->pair_ops + ",").find("," + o.name + ",") != std::string::npos;
-  const int bn_min = h->bn_cap < 256 ? 96 : 128;          // (capped N tiles, an experiment: 112-column tiles still pair)
+  const int bn_min = bn_cap(o) < 256 ? 96 : 128;          // (capped N tiles of 112 columns still pair)
   if (h->umma_pair >= 2) return BN >= bn_min;
   return BN >= bn_min && o.K > 7 * 64 && m_tiles >= 64;
 }
@@ -341,13 +331,6 @@ int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, con
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (h->pair_trim && (o.K % bk) != 0) {
-    if (!h->attr_pair_trim) {
-      CUDA_TRY(cudaFuncSetAttribute(umma_fwd_pair_trim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      h->attr_pair_trim = true;
-    }
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_fwd_pair_trim_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
-  } else
   CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_fwd_pair_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
   h->launches++; h->umma_launches++;
   return NPVC_OK;
@@ -360,7 +343,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
     const TapGeom tg = tap_geometry(o, frames);
     if (tg.ok) return launch_umma_tap(c, o, op_index, tg);
   }
-  int n_tiles = 1; const int BN = pick_bn(o.N, (h->bn_cap < 256 && o.K <= h->bn_cap_k) ? h->bn_cap : 256, &n_tiles);
+  int n_tiles = 1; const int BN = pick_bn(o.N, bn_cap(o), &n_tiles);
   const RowTiling rt = make_tiling(o.A.R, frames, 128);
   if (pair_wanted(h, o, BN, rt.m_tiles)) {
     const int rc = launch_umma_pair(c, o, op_index, BN, n_tiles, rt);
@@ -369,10 +352,9 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
     // form of the same kernel computes bit-identical results -- use it from now on
     cudaGetLastError(); h->umma_pair = 0;
   }
-  // k-block: 64 bf16 (128-byte swizzled rows) when >= 4 such stages fit, else 32 (64-byte rows): the
-  // same bytes in flight at twice the pipeline granularity (wide N tiles are L2-latency-bound otherwise)
+  // k-block: 64 bf16 (128-byte swizzled rows); 32 (64-byte rows) only when K itself is that short
+  // (32-wide k-blocks for deeper pipelines measured 20 % slower: more TMA requests per byte)
   int sw = 128;
-  if ((225 * 1024 - 6144) / (2 * 128 * 128 + 2 * BN * 128) < h->umma_min_stages) sw = 64;
   if (o.K <= 32) sw = 64;
   const int bk = sw / 2;
   const void* a_base = resolve(c, o.A.ref);
@@ -793,16 +775,11 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   npvc_handle* h = new npvc_handle();
   const char* eu = getenv("NPVC_UMMA");            // "0" = CUDA-core GEMMs only (debug / A-B comparisons)
   h->use_umma = !(eu && eu[0] == '0');
-  if (const char* ms = getenv("NPVC_UMMA_MIN_STAGES")) h->umma_min_stages = atoi(ms);
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
   if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);
-  if (const char* pt = getenv("NPVC_PAIR_TRIM")) h->pair_trim = atoi(pt);
-  if (const char* bc = getenv("NPVC_BN_CAP")) { int v = atoi(bc); if (v >= 64 && v <= 256 && v % 16 == 0) h->bn_cap = v; }
-  if (const char* bk = getenv("NPVC_BN_CAP_K")) { int v = atoi(bk); if (v > 0) h->bn_cap_k = v; }
-  if (const char* ns = getenv("NPVC_STREAMS")) h->streams = atoi(ns) >= 2 ? 2 : 1;
   if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty() && !h->umma_pair) h->umma_pair = 1; }
   if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
   if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }
@@ -821,7 +798,6 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
 void npvc_destroy(npvc_handle* h) {
   if (!h) return;
   if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
-  if (h->st2) { cudaStreamDestroy(h->st2); cudaEventDestroy(h->ev2_fork); cudaEventDestroy(h->ev2_join); }
   if (h->tables_on_device) free_tables(h);
   delete h;
 }
@@ -842,19 +818,10 @@ int npvc_param_table(const npvc_handle* h, npvc_param_desc* out, int32_t max) {
   return NPVC_OK;
 }
 
-// Two-stream training passes (NPVC_STREAMS=2): frames per half-batch, 0 = the call runs as one stream of chunks
-static int64_t half_chunk(const npvc_handle* h, int64_t n) {
-  if (h->streams < 2 || n < 256) return 0;
-  const int64_t chunk = n < h->max_chunk ? n : h->max_chunk;
-  return ((chunk + 1) / 2 + 127) / 128 * 128;
-}
-static int64_t set_floats(const npvc_handle* h, int64_t cap2) { return (h->plan.ws_floats(cap2, true) + 63) / 64 * 64; }
-
 int64_t npvc_workspace_bytes(const npvc_handle* h, int64_t n, int32_t train) {
   if (!h || n < 0) return -1;
   int64_t chunk = n < h->max_chunk ? n : h->max_chunk;
   if (chunk < 1) chunk = 1;
-  if (train) { const int64_t cap2 = half_chunk(h, n); if (cap2) return 2 * set_floats(h, cap2) * 4; }   // two activation sets
   return h->plan.ws_floats(chunk, train != 0) * 4;
 }
 
@@ -977,13 +944,8 @@ int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, co
   if (!d_theta || !d_x || !d_y || !d_eps || n < 1) return fail(NPVC_ERR_ARG, "bad argument");
   rc = ensure_tables(h); if (rc) return rc;
   const Plan& p = h->plan; cudaStream_t st = (cudaStream_t)stream;
-  const int64_t cap2 = h->profiling ? 0 : half_chunk(h, n);          // > 0: two half-batches on two streams
-  const int64_t cap = cap2 ? cap2 : (n < h->max_chunk ? n : h->max_chunk); const int z = p.arch.z_dim, H = p.arch.in_h;
+  const int64_t cap = n < h->max_chunk ? n : h->max_chunk; const int z = p.arch.z_dim, H = p.arch.in_h;
   float* ws = (float*)d_ws;
-  if (cap2 && !h->st2) {
-    if (cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess) return fail(NPVC_ERR_CUDA, "cudaStreamCreate failed");
-    cudaEventCreateWithFlags(&h->ev2_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev2_join, cudaEventDisableTiming);
-  }
   CUDA_TRY(cudaMemsetAsync(ws + p.buf_offset(p.buf_acc, cap, true), 0, 8 * 4, st));
   if (d_grad) {
     CUDA_TRY(cudaMemsetAsync(d_grad, 0, (size_t)p.n_params * 4, st));
@@ -993,27 +955,15 @@ int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, co
     Ctx c{h, ws, cap, true, d_theta, nullptr, nullptr, nullptr, nullptr, 0, n, st};
     rc = run_phase(c, PH_PACK); if (rc) return rc;
   }
-  if (cap2) {      // the second stream starts behind the memsets / packs above
-    CUDA_TRY(cudaEventRecord(h->ev2_fork, st)); CUDA_TRY(cudaStreamWaitEvent(h->st2, h->ev2_fork, 0));
-  }
-  int chunk_index = 0;
-  for (int64_t c0 = 0; c0 < n; c0 += cap, chunk_index++) {
+  for (int64_t c0 = 0; c0 < n; c0 += cap) {
     int64_t m = n - c0 < cap ? n - c0 : cap;
-    // two-stream passes: odd chunks use the second activation set on the second stream; the operand packs, the packed
-    // weight gradients (RED.ADD), the flat gradient (atomics) and the loss sums (atomics) are shared by both sets
-    const int set = cap2 ? (chunk_index & 1) : 0;
-    float* wset = ws + (set ? set_floats(h, cap2) : 0);
-    const cudaStream_t cst = set ? h->st2 : st;
+    float* wset = ws; const cudaStream_t cst = st;
     Ctx c{h, wset, cap, true, d_theta, d_grad, d_x + c0 * H, d_y + c0, d_eps + c0 * z, m, n, cst};
-    if (cap2) { c.ws_sh = ws; c.set = set; }
     for (int ph : {PH_ENC, PH_SAMPLE, PH_DEC, PH_LOSS}) { rc = run_phase(c, ph); if (rc) return rc; }
     if (d_grad) { rc = run_phase(c, PH_BWD); if (rc) return rc; }
     struct { float* dst; int buf; int w; } outs[4] = {{d_z, p.buf_z, z}, {d_mu, p.buf_mu, z}, {d_lv, p.buf_lv, z}, {d_xh, p.buf_xh, H}};
     for (auto& o : outs)
       if (o.dst) CUDA_TRY(cudaMemcpyAsync(o.dst + c0 * o.w, wset + p.buf_offset(o.buf, cap, true), (size_t)m * o.w * 4, cudaMemcpyDeviceToDevice, cst));
-  }
-  if (cap2) {      // join: everything the second stream did happens-before what follows on the caller's stream
-    CUDA_TRY(cudaEventRecord(h->ev2_join, h->st2)); CUDA_TRY(cudaStreamWaitEvent(st, h->ev2_join, 0));
   }
   if (d_grad) {
     Ctx c{h, ws, cap, true, d_theta, d_grad, nullptr, nullptr, nullptr, 0, n, st};

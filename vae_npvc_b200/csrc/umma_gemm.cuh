@@ -207,9 +207,7 @@ __device__ __forceinline__ void issue_taps(uint32_t acc, uint32_t acc2, uint64_t
 //   tile, the leader (cluster rank 0) issues the MMAs and commits to both CTAs' barriers, every CTA drains its
 //   own 128 accumulator rows.  B bytes per CTA and MAC halve, which buys pipeline stages for the wide-N layers.
 // =============================================================================================
-// TRIM (with PAIR; opt-in until measured): the last k-block issues only the K steps that hold live columns (the rest
-//   of its box is TMA zero fill: K = 513 is 8 k-blocks + 1 column, whose block needs 1 of its 4 K steps).
-template <bool PAIR, bool TRIM = false>
+template <bool PAIR>
 __global__ void __launch_bounds__(576, 1)
 umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
@@ -394,9 +392,8 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         const uint64_t ah = sdesc_at(dbase, st), al = sdesc_at(dbase, st + a_tile_bytes);
         const uint64_t bh = sdesc_at(dbase, st + 2u * a_tile_bytes), bl = sdesc_at(dbase, st + 2u * a_tile_bytes + b_tile_bytes);
         if constexpr (PAIR) {
-          const int ks_n = (TRIM && kb == g.kblocks - 1) ? ((g.K - kb * bk + 15) >> 4) : ksteps;
           if (elect_one()) {
-            for (int k4 = 0; k4 < ks_n; k4++) {
+            for (int k4 = 0; k4 < ksteps; k4++) {
               const uint64_t o = (uint64_t)(k4 * 2);
               const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
               mma_bf16_pair(acc, ah + o, bh + o, idesc, first);
@@ -546,9 +543,8 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 // the single-CTA form (every layer) and the CTA-pair form (opt-in for the wide dense layers, engine.cu)
 #undef NPVC_TILE0
 #undef NPVC_TILE_STEP
-#define umma_fwd_kernel umma_fwd_kernel_t<false, false>
-#define umma_fwd_pair_kernel umma_fwd_kernel_t<true, false>
-#define umma_fwd_pair_trim_kernel umma_fwd_kernel_t<true, true>
+#define umma_fwd_kernel umma_fwd_kernel_t<false>
+#define umma_fwd_pair_kernel umma_fwd_kernel_t<true>
 
 // =============================================================================================
 // (W) weight-gradient kernel, 192 threads, grid = (K tiles of 128, N tiles, row-tile splits):
