@@ -193,7 +193,7 @@ def buffer_ranges(plan, chunk, train):
     rup = lambda v: (v + 63) // 64 * 64
     off, out = rup(plan["arena_w"]), []
     for b in plan["bufs"]:
-        sz = 0 if (b["train_only"] and not train) else rup(b["fixed"] + b["per_frame"] * chunk)
+        sz = 0 if ((b["train_only"] and not train) or b.get("elide")) else rup(b["fixed"] + b["per_frame"] * chunk)
         out.append((b["name"], off, off + sz, b["per_frame"], b["split"]))
         off += sz
     return out

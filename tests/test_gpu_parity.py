@@ -176,6 +176,66 @@ def test_full_size_properties(eng, arch):
         assert rel(out[k][sl], ref[k]) <= TOL_OUT, k
 
 
+def _oracle_chunked(arch, P32, x, y, eps, pos, chunk=1024):
+    """fp64 oracle outputs and gradient of the batch mean, accumulated over chunks of frames (the loss is a mean of
+    per-frame terms: grad = sum_c (n_c / n) grad_c); `pos` = the lrelu branches the implementation took."""
+    n = x.shape[0]
+    outs = {k: [] for k in ("z", "mu", "lv", "xh")}
+    gsum, G = None, 0.0
+    for c0 in range(0, n, chunk):
+        sl = slice(c0, min(n, c0 + chunk))
+        ref = R.forward(arch, P32, x[sl], y[sl], eps[sl], with_grads=True, lrelu_pos={k: v[sl] for k, v in pos.items()})
+        w = (sl.stop - sl.start) / n
+        g = R.flatten_params(arch, ref["grads"], np.float64) * w
+        gsum = g if gsum is None else gsum + g
+        G += float(ref["G"]) * w
+        for k in outs:
+            outs[k].append(ref[k])
+    return {k: np.concatenate(v) for k, v in outs.items()}, gsum, G
+
+
+@pytest.mark.parametrize("n,n_speakers", [(16384, None), (2048, 1)])
+def test_benchmark_sizes_against_the_oracle(eng, arch, n, n_speakers):
+    """The sizes the metric is quoted on, with the default routing of those sizes (CTA-pair tiles, split weight
+    gradients, fused first layer): cfg2 (64 x 256 frames, 10 speakers) and cfg1 (16 x 128 frames, one speaker).
+    Every output and all 44 gradient tensors against the fp64 oracle, which is run in chunks of 1024 frames."""
+    P = R.init_params(arch, 0)
+    x, y, eps, xd, yd, ed = _dev_inputs(eng, arch, n, seed=3, n_speakers=n_speakers)
+    theta = torch.tensor(R.flatten_params(arch, P), device=eng.device)
+    grad = torch.full_like(theta, float("nan"))
+    out = eng.loss_fwd_bwd(theta, xd, yd, ed, grad=grad)
+    torch.cuda.synchronize()
+    P32 = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in P.items()}
+    x32, e32 = x.astype(np.float32), eps.astype(np.float32)
+    pos = lrelu_branches(lambda name: eng.debug_buffer(name, n).cpu().numpy(), arch, P32, n)
+    ref, gref, G = _oracle_chunked(arch, P32, x32, y, e32, pos)
+    for k in ("z", "mu", "lv", "xh"):
+        assert rel(out[k], ref[k]) <= TOL_OUT, (k, rel(out[k], ref[k]))
+    assert abs(float(out["losses"][0]) - G) <= 1e-5 * abs(G)
+    g = grad.cpu().numpy().astype(np.float64)
+    assert np.isfinite(g).all()
+    worst = 0.0
+    for t in eng.table:
+        sl = slice(t["offset"], t["offset"] + t["size"])
+        den = np.abs(gref[sl]).max()
+        if den == 0:
+            assert np.abs(g[sl]).max() == 0, t["name"]
+        else:
+            e = np.abs(g[sl] - gref[sl]).max() / den
+            worst = max(worst, e)
+            assert e <= TOL_GRAD, (t["name"], e)
+    print("n=%d worst per-tensor gradient error %.2e" % (n, worst))
+
+
+def test_unfused_plan_matches_oracle(arch, monkeypatch):
+    """NPVC_FUSE=0: every plan op as its own kernel (the path shapes without a fused kernel take)."""
+    from vae_npvc_b200.engine import Engine
+    monkeypatch.setenv("NPVC_FUSE", "0")
+    e2 = Engine(arch, "cuda:0")
+    monkeypatch.delenv("NPVC_FUSE")
+    _check_against_oracle(e2, arch, 37)
+
+
 def test_cfg3_inference_size(eng, arch):
     """cfg3 (convert.py path): encode -> mu -> decode at N = 256*512 = 131,072 frames, processed in
     16,384-frame chunks inside the library; chunk boundaries must be invisible and a slice that

@@ -13,6 +13,7 @@
 #include <map>
 
 #include "kernels.cuh"
+#include "fused_e0.cuh"
 #include "plan.h"
 #include "umma_gemm.cuh"
 
@@ -93,13 +94,6 @@ DView dview(const Ctx& c, const View& v) {
   DView d; d.p = resolve(c, v.ref); d.fs = v.fs; d.R = v.R; d.rs = v.rs; d.off = v.off; d.flen = v.flen; d.pred = v.pred;
   d.split = v.split;
   return d;
-}
-// threads per frame of the register-resident Layernorm kernels (0: use the shared-memory kernels)
-int ln_group(int L, int Cn, int out_off, int out_flen) {
-  if (L % 8 || out_off % 8 || out_flen % 8 || Cn % 8 || Cn > 2048) return 0;     // a thread's 8 elements = 8 consecutive channels
-  for (int G = 32; G <= 256; G *= 2)
-    if (L <= 32 * G && (8 * G) % Cn == 0) return G;
-  return 0;
 }
 bool view_vec_ok(const DView& d) {
   return !d.pred && ((reinterpret_cast<uintptr_t>(d.p) & 15) == 0) && (d.fs % 4 == 0) && (d.rs % 4 == 0) && (d.off % 4 == 0);
@@ -485,6 +479,48 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   return NPVC_OK;
 }
 
+// ---- fused first encoder layer (fused_e0.cuh): `o` and `nx` are the two plan ops the kernel stands for --------------
+int launch_e0_fwd(Ctx& c, const Op& o, const Op& nx) {      // o: conv (OP_GEMM on the caller's frames), nx: its OP_LN_FWD
+  npvc_handle* h = c.h; const Plan& p = h->plan;
+  E0FwdArgs g;
+  g.x = c.x; g.W = resolve(c, o.B); g.bias = resolve(c, o.bias[0]); g.gamma = resolve(c, nx.gamma); g.beta = resolve(c, nx.beta);
+  g.c = c.train ? resolve(c, nx.in) : nullptr;             // inference never reads the raw conv output again
+  g.mean = resolve(c, nx.r0); g.rstd = resolve(c, nx.rstd); g.aout = resolve(c, nx.aout);
+  g.Hi = (int)o.A.fs; g.Ho = o.A.R; g.Co = o.N; g.k = o.K; g.s = o.A.rs; g.pl = -o.A.off;
+  g.out_flen = nx.out_flen; g.out_off = nx.out_off; g.out_split = p.bufs[nx.aout.buf].split; g.frames = c.n;
+  if (!g.x) return fail(NPVC_ERR_ARG, "frames (x) required");
+  const int G = ln_group(nx.L, nx.Cn, nx.out_off, nx.out_flen);
+  const long long fbs = (c.n + 256 / G - 1) / (256 / G);
+  long long blocks = (long long)h->sm_count * 8; if (blocks > fbs) blocks = fbs;
+  const size_t sm = (size_t)(E0_KT + 3) * g.Co * sizeof(float);
+  if (G == 32) e0_fwd_kernel<32><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  else if (G == 64) e0_fwd_kernel<64><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  else if (G == 128) e0_fwd_kernel<128><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  else e0_fwd_kernel<256><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  h->launches++;
+  return NPVC_OK;
+}
+int launch_e0_bwd(Ctx& c, const Op& o, const Op& nx) {      // o: OP_LN_BWD of the first layer, nx: its OP_WGRAD
+  npvc_handle* h = c.h;
+  E0BwdArgs g;
+  g.x = c.x; g.dy = resolve(c, o.in); g.cin = resolve(c, o.xhat); g.mean = resolve(c, o.r0); g.rstd = resolve(c, o.rstd);
+  g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta);
+  g.dW = resolve(c, nx.B); g.dgamma = resolve(c, o.dgamma); g.dbeta = resolve(c, o.dbeta); g.dbias = resolve(c, o.dbias);
+  g.Hi = (int)nx.A.fs; g.Ho = nx.A.R; g.Co = nx.N; g.k = nx.K; g.s = nx.A.rs; g.pl = -nx.A.off; g.frames = c.n;
+  if (!g.x) return fail(NPVC_ERR_ARG, "frames (x) required");
+  if (nx.ldb != nx.N) return fail(NPVC_ERR_ARG, "fused first-layer backward: packed weight gradient must be dense");
+  const int G = e0_bwd_group(o.L, o.Cn);
+  const long long fbs = (c.n + 256 / G - 1) / (256 / G);
+  long long blocks = (long long)h->sm_count * 2; if (blocks > fbs) blocks = fbs;
+  const size_t sm = (size_t)(E0_KT + 5) * g.Co * sizeof(float);
+  if (G == 32) e0_bwd_kernel<32><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  else if (G == 64) e0_bwd_kernel<64><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  else if (G == 128) e0_bwd_kernel<128><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  else e0_bwd_kernel<256><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  h->launches++;
+  return NPVC_OK;
+}
+
 bool umma_allowed(const npvc_handle* h, const Op& o) {
   if (!o.umma || !h->encode) return false;
   if (h->umma_allow.empty()) return true;
@@ -695,7 +731,13 @@ int run_phase(Ctx& c, int phase) {
       cudaEventRecord(h->ev_fork, main_st); cudaStreamWaitEvent(h->side, h->ev_fork, 0);
       c.st = h->side; forked = true;
     }
-    int rc = run_op(c, o, (int)i);
+    int rc;
+    if (o.fuse == FUSE_E0_FWD) {                     // this op and the next one as one kernel (plan.h, Op::fuse)
+      rc = launch_e0_fwd(c, o, ops[i + 1]); i++;
+    } else if (o.fuse == FUSE_E0_BWD) {
+      rc = launch_e0_bwd(c, o, ops[i + 1]); i++;
+    } else rc = run_op(c, o, (int)i);
+    if (rc == NPVC_OK && o.fuse) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = fail(NPVC_ERR_CUDA, "launch " + o.name + " (fused): " + cudaGetErrorString(e)); }
     c.st = main_st;
     if (h->profiling) { cudaEventRecord(ev.b, c.st); h->events.push_back(ev); }
     if (rc) return rc;
@@ -785,7 +827,8 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }
   const char* ea = getenv("NPVC_UMMA_OPS");
   if (ea) h->umma_allow = ea;
-  std::string err = build_plan(*arch, h->plan, h->use_umma);
+  const char* fz = getenv("NPVC_FUSE");            // "0" = every plan op as its own kernel (A/B comparisons, fallback-path tests)
+  std::string err = build_plan(*arch, h->plan, h->use_umma, !(fz && fz[0] == '0'));
   if (!err.empty()) { delete h; return fail(NPVC_ERR_ARG, "unsupported architecture: " + err); }
   if (max_chunk > 0) h->max_chunk = max_chunk;
   else if (const char* mc = getenv("NPVC_MAX_CHUNK")) { long v = atol(mc); if (v > 0) h->max_chunk = v; }

@@ -79,11 +79,25 @@ int umma_row_tile(int R) {
   return 0;
 }
 
+// a thread's 8 elements = 8 consecutive channels of one position, at most 4 such units per thread
+int ln_group(int L, int Cn, int out_off, int out_flen) {
+  if (L % 8 || out_off % 8 || out_flen % 8 || Cn % 8 || Cn > 2048) return 0;
+  for (int G = 32; G <= 256; G *= 2)
+    if (L <= 32 * G && (8 * G) % Cn == 0) return G;
+  return 0;
+}
+int e0_bwd_group(int L, int Co) {
+  if (L % 4 || Co % 4 || Co > 1024) return 0;
+  for (int G = 32; G <= 256; G *= 2)
+    if (L <= 16 * G && (4 * G) % Co == 0) return G;
+  return 0;
+}
+
 int64_t Plan::buf_offset(int b, int64_t chunk, bool train) const {
   int64_t off = rup64(arena_w, 64);
   for (int i = 0; i < (int)bufs.size(); i++) {
     const Buf& q = bufs[i];
-    int64_t sz = (q.train_only && !train) ? 0 : rup64(q.fixed + q.per_frame * chunk, 64);
+    int64_t sz = ((q.train_only && !train) || q.elide) ? 0 : rup64(q.fixed + q.per_frame * chunk, 64);
     if (i == b) return off;
     off += sz;
   }
@@ -91,7 +105,7 @@ int64_t Plan::buf_offset(int b, int64_t chunk, bool train) const {
 }
 int64_t Plan::ws_floats(int64_t chunk, bool train) const { return buf_offset((int)bufs.size(), chunk, train); }
 
-std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
+std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
   p = Plan();
   p.arch = a;
   Builder B(p);
@@ -401,6 +415,10 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     o.tap_T = l.k; o.tap_C = l.Ci; o.tap_s = l.s;
     o.C = B.view(B.ws(b_ce[e]), l.Ho, l.Ho * l.Co, l.Co, 0, l.Ho * l.Co);
     o.bias[0] = B.th(poff(P_eb[e])); o.bias_mod = l.Co;
+    // first layer: conv + Layernorm + lrelu as one CUDA-core kernel (fused_e0.cuh) when the register-resident
+    // Layernorm mapping applies
+    const bool fuse_fwd = fuse && e == 0 && l.Ci == 1 && l.k <= 8 && ln_group(l.Ho * l.Co, l.Co, ae_off[e], ae_flen[e]) > 0;
+    if (fuse_fwd) p.ops.back().fuse = FUSE_E0_FWD;
     snprintf(nm, sizeof nm, "ln_e%d", e);
     Op& q = B.op(OP_LN_FWD, PH_ENC, nm);
     q.in = B.ws(b_ce[e]); q.r0 = B.ws(b_me[e]); q.aout = B.ws(b_ae[e]); q.rstd = B.ws(b_re[e]);
@@ -523,6 +541,8 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
     q.gamma = B.th(poff(P_es[e])); q.beta = B.th(poff(P_eo[e]));
     q.dgamma = B.gr(poff(P_es[e])); q.dbeta = B.gr(poff(P_eo[e])); q.dbias = B.gr(poff(P_eb[e]));
     q.L = l.Ho * l.Co; q.Cn = l.Co; q.out_flen = dce_flen[e]; q.out_off = dce_off[e];
+    // first layer: no data gradient, so dc_e0 is read by the weight gradient alone -- one kernel keeps it in registers
+    if (fuse && e == 0 && l.Ci == 1 && l.k <= 8 && e0_bwd_group(l.Ho * l.Co, l.Co) > 0) { q.fuse = FUSE_E0_BWD; p.bufs[b_dce[e]].elide = 1; }
     snprintf(nm, sizeof nm, "wgrad_e%d", e);
     Op& w = B.op(OP_WGRAD, PH_BWD, nm);
     w.A = VA_e[e]; w.K = l.k * l.Ci; w.a_scalar = (e == 0); w.N = l.Co;
@@ -606,12 +626,12 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma) {
   for (size_t i = 0; i < p.bufs.size(); i++) {
     const Buf& q = p.bufs[i];
     js << (i ? "," : "") << "{\"name\":\"" << q.name << "\",\"per_frame\":" << q.per_frame << ",\"fixed\":" << q.fixed
-       << ",\"train_only\":" << q.train_only << ",\"split\":" << q.split << "}";
+       << ",\"train_only\":" << q.train_only << ",\"split\":" << q.split << ",\"elide\":" << q.elide << "}";
   }
   js << "],\"ops\":[";
   for (size_t i = 0; i < p.ops.size(); i++) {
     const Op& o = p.ops[i];
-    js << (i ? "," : "") << "{\"kind\":" << o.kind << ",\"phase\":" << o.phase << ",\"name\":\"" << o.name << "\",";
+    js << (i ? "," : "") << "{\"kind\":" << o.kind << ",\"phase\":" << o.phase << ",\"fuse\":" << o.fuse << ",\"name\":\"" << o.name << "\",";
     json_view(js, "A", o.A); js << ","; json_view(js, "C", o.C);
     js << ",\"K\":" << o.K << ",\"N\":" << o.N << ","; json_ref(js, "B", o.B);
     js << ",\"ldb\":" << o.ldb << ","; json_ref(js, "bias0", o.bias[0]); js << ","; json_ref(js, "bias1", o.bias[1]);

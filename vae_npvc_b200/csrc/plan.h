@@ -28,6 +28,13 @@ enum OpKind {
   OP_ZCAT = 13      // zs[f] = [z[f] (i0) | one-hot(y[f]) (i1)]  (r0 -> r1; fp32 or split planes)
 };
 
+// Op::fuse: the op and the NEXT op of the list are executed by one fused kernel (engine.cu); the plan keeps both
+// ops (they remain the definition of the arithmetic; tests/plan_interp.py runs them one by one).
+//   FUSE_E0_FWD  conv of the first encoder layer (one input channel, <= 8 taps) + its Layernorm / lrelu
+//   FUSE_E0_BWD  Layernorm backward of the first encoder layer + its weight gradient: the gradient w.r.t. the
+//                conv output is consumed in registers, its buffer is never materialised (Buf::elide)
+enum Fuse { FUSE_NONE = 0, FUSE_E0_FWD = 1, FUSE_E0_BWD = 2 };
+
 struct Ref {
   int space = SP_NONE;
   int buf = -1;        // SP_WS: buffer index; SP_USER: slot
@@ -54,10 +61,12 @@ struct Buf {
   // with value = hi + lo (hi = bf16(v), lo = bf16(v - hi)): the tensor-core operand format.  The
   // tensor path multiplies such operands as hi.hi + hi.lo + lo.hi in fp32 (bf16x3).
   int split = 0;
+  int elide = 0;           // no storage: every producer / consumer of the buffer runs inside a fused kernel (Op::fuse)
 };
 
 struct Op {
   int kind = 0, phase = 0;
+  int fuse = 0;          // Fuse
   std::string name;
   // GEMM / WGRAD
   View A, C;             // WGRAD: C is the dC view
@@ -116,7 +125,13 @@ constexpr int32_t PACK_INDEX_MASK = (1 << 29) - 1;
 
 // Returns empty string on success, else an error message.  use_umma: route GEMM-shaped ops to the
 // tcgen05 kernels: their A operands become split (bf16 hi / lo) buffers, their B operands bf16 packs.
-std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma);
+// fuse: mark the op pairs the engine runs as fused kernels (Op::fuse) and elide the buffers that only lived between them.
+std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse = true);
+
+// Threads per frame of the register-resident Layernorm kernels, units of 8 elements (0: not applicable)
+int ln_group(int L, int Cn, int out_off, int out_flen);
+// Threads per frame of the fused first-layer backward kernel, units of 4 elements (0: not applicable)
+int e0_bwd_group(int L, int Co);
 
 // Rows of one frame per tensor-core tile (0: the view cannot be tiled); see plan.cpp.
 int umma_row_tile(int R);
