@@ -129,12 +129,38 @@ int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, co
                       float* d_xh, float* d_losses, float* d_grad, int32_t repack,
                       void* d_ws, int64_t ws_bytes, void* stream);
 
+/* Device-resident state of a training loop (32 bytes of caller-owned device memory, zero-initialised except `seed`):
+ * what changes from step to step lives on the device, so the launch sequence of a whole training step is identical
+ * every step and can be captured once in a CUDA graph and replayed.
+ *   seed   key of the in-kernel N(0,1) sampler (Philox4x32-10 + Box-Muller)
+ *   draws  number of completed npvc_train_fwd_bwd passes = third counter word of the sampler
+ *   step   number of completed passes that produced a gradient = the t of the Adam update that follows */
+typedef struct npvc_step_state { uint64_t seed; int64_t draws; int64_t step; int64_t reserved; } npvc_step_state;
+
+/* npvc_loss_fwd_bwd with the tf.random_normal of GaussianSampleLayer (util/layers.py:154) drawn IN-KERNEL:
+ * eps[frame, d] = Normal(Philox4x32-10(key = seed, counter = (d, frame_offset + frame, draws))) -- a function of
+ * (seed, pass, frame, dim) only, independent of chunking; the backward regenerates it (no eps buffer exists).
+ * frame_offset: index of this call's first frame in the job's batch (data-parallel ranks pass rank * n to draw
+ * different noise from one seed).  On completion draws += 1 and, when d_grad != NULL, step += 1 (in stream order). */
+int npvc_train_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, const int64_t* d_y,
+                       npvc_step_state* d_state, int64_t frame_offset, int64_t n, float* d_z, float* d_mu,
+                       float* d_lv, float* d_xh, float* d_losses, float* d_grad, int32_t repack,
+                       void* d_ws, int64_t ws_bytes, void* stream);
+/* The draw alone: d_eps[n, z] = what npvc_train_fwd_bwd would use for these frames at the state's current `draws`. */
+int npvc_normal_draw(npvc_handle* h, const npvc_step_state* d_state, int64_t frame_offset, int64_t n,
+                     float* d_eps, void* stream);
+
 /* tf.train.AdamOptimizer.apply_gradients, TF form (trainer/vae.py:16-24):
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMAs; theta -= lr_t*m/(sqrt(v)+eps).  grad is multiplied
  * by grad_scale first (1/world_size after an all-reduce SUM).  step t >= 1. */
 int npvc_adam_step(npvc_handle* h, float* d_theta, const float* d_grad, float* d_m, float* d_v,
                    int64_t n_params, int64_t step, float lr, float beta1, float beta2, float eps,
                    float grad_scale, void* stream);
+
+/* npvc_adam_step with t = d_state->step read on the device (see npvc_step_state). */
+int npvc_adam_step_dev(npvc_handle* h, float* d_theta, const float* d_grad, float* d_m, float* d_v,
+                       int64_t n_params, const npvc_step_state* d_state, float lr, float beta1, float beta2,
+                       float eps, float grad_scale, void* stream);
 
 /* Tanhize.forward_process / backward_process (analyzer.py:82-87) over [n, dim] with per-bin
  * xmin/xmax [dim].  In-place allowed. */

@@ -34,8 +34,10 @@ class ConvVAE(object):
         # variables: one flat fp32 buffer, TF variable order / layouts (npvc_param_table)
         self.theta = self.engine.init_theta(seed)
         self.y_emb = self.variables()['y_embedding/y_emb']
-        self._rng = torch.Generator(device=self.device)
-        self._rng.manual_seed(seed + 1)
+        # the tf.random_normal of GaussianSampleLayer (util/layers.py:154) is drawn inside the sampler kernel; its
+        # seed and the pass / step counters live in 32 bytes of device memory (npvc_step_state)
+        self.state = self.engine.new_step_state(seed + 1)
+        self.frame_offset = 0        # data-parallel ranks: rank * frames-per-rank (distinct noise from one seed)
         self.generate = self.decode  # for VAE-GAN extension (model/vae.py:34)
 
     def _sanity_check(self):
@@ -59,10 +61,6 @@ class ConvVAE(object):
             y = torch.as_tensor(y)
         return y.to(self.device, torch.int64, non_blocking=True).reshape(-1).contiguous()
 
-    def _eps(self, n):
-        # the tf.random_normal of GaussianSampleLayer (util/layers.py:154), drawn on device
-        return torch.randn(n, self.arch['z_dim'], device=self.device, dtype=torch.float32, generator=self._rng)
-
     # -- reference API ---------------------------------------------------------------------
     def loss(self, x, y, eps=None):
         """model/vae.py:106-137.  Returns {'G': -logPx + D_KL, 'D_KL', 'logP'} (0-dim tensors)."""
@@ -70,18 +68,19 @@ class ConvVAE(object):
         if hasattr(x, 'dequeue'):                      # analyzer.read() queue handles
             x, y = x.dequeue(peek=True)
         xf, yl = self._frames(x), self._labels(y)
-        eps = self._eps(xf.shape[0]) if eps is None else eps
-        out = self.engine.loss_fwd_bwd(self.theta, xf, yl, eps, grad=None, outputs=False)
+        out = self.engine.loss_fwd_bwd(self.theta, xf, yl, eps, grad=None, outputs=False, state=self.state,
+                                       frame_offset=self.frame_offset)
         loss = LossDict(G=out['losses'][0], D_KL=out['losses'][1], logP=out['losses'][2])
         loss.machine, loss.feed = self, feed
         return loss
 
-    def loss_and_grad(self, x, y, grad, eps=None, outputs=False):
+    def loss_and_grad(self, x, y, grad, eps=None, outputs=False, losses=None):
         """Forward + backward into the flat `grad` buffer (what optimizer.minimize differentiates,
-        trainer/vae.py:24).  Returns the engine's output dict (losses = [G, D_KL, logP])."""
+        trainer/vae.py:24).  eps=None: the sampler draws in-kernel and the device step state advances.
+        Returns the engine's output dict (losses = [G, D_KL, logP])."""
         xf, yl = self._frames(x), self._labels(y)
-        eps = self._eps(xf.shape[0]) if eps is None else eps
-        return self.engine.loss_fwd_bwd(self.theta, xf, yl, eps, grad=grad, outputs=outputs)
+        return self.engine.loss_fwd_bwd(self.theta, xf, yl, eps, grad=grad, outputs=outputs, losses=losses,
+                                        state=self.state, frame_offset=self.frame_offset)
 
     def encode(self, x):
         """model/vae.py:139-141: z_mu only."""

@@ -35,18 +35,20 @@ ALT_ARCHS = {
     "odd_pads": {"hwc": [100, 1, 1], "z_dim": 12, "y_dim": 4,
                  "encoder": {"kernel": [[7, 1], [3, 1], [8, 1]], "stride": [[3, 1], [2, 1], [4, 1]], "output": [8, 4, 12]},
                  "generator": {"hwc": [25, 1, 6], "kernel": [[4, 1], [2, 1], [199, 1]], "stride": [[2, 1], [2, 1], [1, 1]], "output": [4, 8, 1]}},
-    # cfg5 (BASELINE.json configs[4]): the VAWGAN discriminator conv stack of architecture-vawgan-vcc2016.json:7-14
-    # (kernels 7 / 7 / 115, stride 3, 16 / 32 / 64 channels) run as the encoder of the path; the generator stack
-    # of that JSON is the ConvVAE one.  Only the conv stacks are specifiable: the VAWGAN model code is absent from
-    # the reference snapshot.
-    "vawgan_d_stack": {"hwc": [513, 1, 1], "z_dim": 128, "y_dim": 10,
-                       "encoder": {"kernel": [[7, 1], [7, 1], [115, 1]], "stride": [[3, 1], [3, 1], [3, 1]], "output": [16, 32, 64]},
-                       "generator": {"hwc": [19, 1, 81], "kernel": [[9, 1], [7, 1], [7, 1], [1025, 1]],
-                                     "stride": [[3, 1], [3, 1], [3, 1], [1, 1]], "output": [32, 16, 8, 1]}},
     "wide": {"hwc": [162, 1, 1], "z_dim": 32, "y_dim": 5,
              "encoder": {"kernel": [[7, 1], [7, 1], [5, 1]], "stride": [[3, 1], [3, 1], [2, 1]], "output": [16, 32, 64]},
              "generator": {"hwc": [18, 1, 33], "kernel": [[9, 1], [7, 1], [323, 1]], "stride": [[3, 1], [3, 1], [1, 1]], "output": [32, 16, 1]}},
 }
+
+
+def _add_package_archs():
+    # cfg5 (BASELINE.json configs[4]): the VAWGAN discriminator conv stack as the encoder of the path (vae_npvc_b200/arch.py)
+    from vae_npvc_b200.arch import vawgan_d_stack_arch
+    a = vawgan_d_stack_arch()
+    ALT_ARCHS["vawgan_d_stack"] = {k: a[k] for k in ("hwc", "z_dim", "y_dim", "encoder", "generator")}
+
+
+_add_package_archs()
 
 
 @pytest.fixture(params=sorted(ALT_ARCHS))

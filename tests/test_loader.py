@@ -150,6 +150,7 @@ def test_trainer_checkpoint_resume_roundtrip(tmp_path):
         def __init__(self, seed):
             g = torch.Generator().manual_seed(seed)
             self.theta = torch.randn(10, generator=g)
+            self.state = torch.zeros(4, dtype=torch.int64)       # npvc_step_state stand-in: {seed, draws, step, -}
 
         def variables(self):
             return {"Encoder/dense/kernel": self.theta[:6].view(2, 3), "Encoder/dense/bias": self.theta[6:]}
@@ -169,6 +170,7 @@ def test_trainer_checkpoint_resume_roundtrip(tmp_path):
     m2 = Machine(2)
     t2 = tv.VAETrainer({"G": 0.0}, arch, None, dirs); t2.machine = m2
     assert t2.restore() == 120 and t2.global_step == 120
+    assert m2.state.tolist()[1:3] == [120, 120]                   # the device-side counters follow the restored step
     assert torch.equal(m2.theta, m1.theta) and torch.equal(t2._state["m"], st["m"]) and torch.equal(t2._state["v"], st["v"])
     m3 = Machine(3)
     t3 = tv.VAETrainer({"G": 0.0}, arch, None, dirs); t3.machine = m3

@@ -133,3 +133,18 @@ def test_detrand_is_stable():
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.05
     nrm = detrand.normal(3, (20000,))
     assert abs(nrm.mean()) < 0.03 and abs(nrm.std() - 1) < 0.03
+
+
+def test_philox_known_answers():
+    """oracle/philox.py against the Random123 known-answer vectors of Philox4x32-10 (kat_vectors)."""
+    from oracle import philox
+    z = np.zeros(1, np.uint32); f = np.full(1, 0xFFFFFFFF, np.uint32)
+    assert [int(v[0]) for v in philox.philox4x32_10((z, z, z, z), (0, 0))] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert [int(v[0]) for v in philox.philox4x32_10((f, f, f, f), (0xFFFFFFFF, 0xFFFFFFFF))] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    pi = [np.full(1, v, np.uint32) for v in (0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344)]
+    assert [int(v[0]) for v in philox.philox4x32_10(pi, (0xA4093822, 0x299F31D0))] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    e = philox.normal_draw(7, 3, 1000, 2048, 128)
+    assert abs(e.mean()) < 0.01 and abs(e.std() - 1.0) < 0.01 and np.isfinite(e).all()
+    # a draw depends on (seed, pass, frame, dim) only
+    assert np.array_equal(philox.normal_draw(7, 3, 1500, 8, 128), e[500:508])
+    assert not np.array_equal(philox.normal_draw(7, 4, 1000, 8, 128), e[:8])

@@ -4,10 +4,11 @@ from importlib import import_module
 from vae_npvc_b200 import vcc2016_vae_arch
 arch = vcc2016_vae_arch()
 M = import_module('model.vae').ConvVAE(arch); T = import_module('trainer.vae').VAETrainer
-n=16384
+n=int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 g = torch.Generator().manual_seed(1)
 x = (torch.rand(n,513,generator=g)*2-1).cuda(); y = torch.randint(0,10,(n,),generator=g).cuda()
 tr = T(M.loss(x,y), arch, None, None)
+tr.use_graph = False          # per-op CUDA events need eager launches
 for i in range(3): tr.opt['g'](x,y)
 M.engine.handle.profile_enable(True)
 for i in range(5): tr.opt['g'](x,y)

@@ -52,32 +52,73 @@ class VAETrainer(object):
         self.lr, self.b1, self.b2 = tr['lr'], tr['beta1'], tr['beta2']
         self.global_step = 0
         self._state = None
+        self.rank, self.world = 0, 1
+        self.use_graph = os.environ.get('NPVC_GRAPH', '1') != "0"
         return {'g': self._train_step, 'global_step': lambda: self.global_step}
 
     def _ensure_state(self, machine):
         if self._state is None or self._state['machine'] is not machine:
             th = machine.theta
             self._state = dict(machine=machine, grad=torch.empty_like(th), m=torch.zeros_like(th), v=torch.zeros_like(th),
-                               losses=torch.zeros(3, device=th.device))
-            self.world = world_info()[1]
+                               losses=torch.zeros(3, device=th.device), graphs={})
+            self.rank, self.world = world_info()
             broadcast_params_(th, src=0)       # identical replicas: rank 0's initial variables
+            self._sync_step_state(machine)
         return self._state
 
+    def _sync_step_state(self, machine):
+        """The device-resident counters (npvc_step_state) follow `global_step` (after a restore)."""
+        state = getattr(machine, 'state', None)
+        if state is not None:
+            state[1] = self.global_step              # draws: the sampler's pass counter
+            state[2] = self.global_step              # step: the pass that follows makes it the t of its Adam update
+
+    def _eager_step(self, machine, st, x, y, eps=None):
+        out = machine.loss_and_grad(x, y, st['grad'], eps=eps, losses=st['losses'])
+        scale = allreduce_flat_grad_(st['grad'], self.world)      # one 3.76 MB bucket over NVLink
+        if eps is not None:                                       # caller-supplied draw: the pass did not advance the device counters
+            machine.state[2] += 1
+        machine.engine.adam_step(machine.theta, st['grad'], st['m'], st['v'], machine.state,
+                                 self.lr, self.b1, self.b2, 1e-8, scale)
+        return out['losses']
+
     def _train_step(self, x=None, y=None, eps=None):
-        """One ``sess.run(opt['g'])``: fwd + bwd (+ all-reduce) + Adam on one batch of frames."""
+        """One ``sess.run(opt['g'])``: fwd + bwd (+ all-reduce) + Adam on one batch of frames.
+
+        Nothing the host computes changes from step to step (the Adam step count and the sampler's counters live on
+        the device), so after two eager steps on a batch shape the whole step -- ~60 kernel launches, the side-stream
+        fork / join of the weight gradients, the all-reduce -- is captured ONCE in a CUDA graph and replayed: the
+        reference's regime of 16 frames per step (architecture-vae-vcc2016.json:23) is launch-bound otherwise.
+        ``NPVC_GRAPH=0`` keeps every step eager."""
         machine = self.machine
         st = self._ensure_state(machine)
         if x is None:
             x, y = self.loss.feed
             if hasattr(x, 'dequeue'):
                 x, y = x.dequeue()
-        out = machine.loss_and_grad(x, y, st['grad'], eps=eps)
-        scale = allreduce_flat_grad_(st['grad'], self.world)      # one 3.76 MB bucket over NVLink
         self.global_step += 1
-        machine.engine.adam_step(machine.theta, st['grad'], st['m'], st['v'], self.global_step,
-                                 self.lr, self.b1, self.b2, 1e-8, scale)
-        st['losses'] = out['losses']
-        return out['losses']
+        if eps is not None or not self.use_graph:
+            return self._eager_step(machine, st, x, y, eps)
+        xf, yl = machine._frames(x), machine._labels(y)
+        machine.frame_offset = self.rank * xf.shape[0]
+        key = (xf.shape[0],)
+        g = st['graphs'].get(key)
+        if g is None:
+            g = st['graphs'][key] = dict(seen=0, graph=None, x=torch.empty_like(xf), y=torch.empty_like(yl))
+        if g['graph'] is None:
+            g['seen'] += 1
+            if g['seen'] <= 2:                                   # warm-up: workspace, tensor maps, kernel attributes, NCCL
+                return self._eager_step(machine, st, xf, yl)
+            g['x'].copy_(xf); g['y'].copy_(yl)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                self._eager_step(machine, st, g['x'], g['y'])
+            g['graph'] = graph                                   # (the capture did not run the step)
+        g['x'].copy_(xf, non_blocking=True); g['y'].copy_(yl, non_blocking=True)
+        g['graph'].replay()
+        machine.engine._packed_for = None                        # theta changed behind the operand packs
+        return st['losses']
 
     # -- status line (trainer/vae.py:31-52) -------------------------------------------------
     def _refresh_status(self, sess=None):
@@ -116,10 +157,12 @@ class VAETrainer(object):
     def save(self, path=None):
         """Checkpoint: the variables under their TF names + Adam slots + global_step (the
         reference's Supervisor autosave, trainer/vae.py:78-84, as one torch file)."""
-        st = self._state
+        st = self._ensure_state(self.machine)        # (a trainer that has not stepped yet saves zero Adam slots)
         path = path or os.path.join(self.dirs['logdir'], 'model.ckpt-{}'.format(self.global_step))
+        tmp = '{}.tmp.{}'.format(path, os.getpid())
         torch.save({'variables': {k: v.cpu() for k, v in self.machine.variables().items()},
-                    'adam_m': st['m'].cpu(), 'adam_v': st['v'].cpu(), 'global_step': self.global_step}, path)
+                    'adam_m': st['m'].cpu(), 'adam_v': st['v'].cpu(), 'global_step': self.global_step}, tmp)
+        os.replace(tmp, path)                        # atomic: a crash mid-write never leaves a truncated newest checkpoint
         return path
 
     def restore(self, logdir=None, ckpt=None, machine=None):
@@ -128,6 +171,31 @@ class VAETrainer(object):
         otherwise the newest ``model.ckpt-<step>`` there is taken.  Restores the variables, the Adam slots
         and ``global_step``; returns the step, or None when there is nothing to restore."""
         machine = machine if machine is not None else self.machine
+        rank, world = world_info()
+        if world > 1:
+            return self._restore_distributed(logdir, ckpt, machine, rank)
+        return self._restore_local(logdir, ckpt, machine)
+
+    def _restore_distributed(self, logdir, ckpt, machine, rank):
+        """Data-parallel resume: rank 0 alone reads the file (ranks need no shared filesystem and cannot disagree on
+        which checkpoint is the newest); the variables, both Adam slots and global_step are then broadcast."""
+        step = self._restore_local(logdir, ckpt, machine) if rank == 0 else None
+        dev = machine.theta.device
+        flag = torch.tensor([-1 if step is None else int(step)], dtype=torch.int64, device=dev)
+        dist.broadcast(flag, src=0)
+        if int(flag.item()) < 0:
+            return None
+        self.machine = machine
+        st = self._ensure_state(machine)
+        for t in (machine.theta, st['m'], st['v']):
+            dist.broadcast(t, src=0)
+        self.global_step = int(flag.item())
+        self._sync_step_state(machine)
+        if hasattr(machine, 'engine') and hasattr(machine.engine, '_packed_for'):
+            machine.engine._packed_for = None
+        return self.global_step
+
+    def _restore_local(self, logdir, ckpt, machine):
         logdir = logdir or (self.dirs or {}).get('restore_from') or (self.dirs or {}).get('logdir')
         path = os.path.join(logdir, ckpt) if (ckpt and logdir) else latest_checkpoint(logdir)
         if not path or not os.path.exists(path):
@@ -150,6 +218,7 @@ class VAETrainer(object):
         if 'adam_m' in ck and 'adam_v' in ck:
             st['m'].copy_(ck['adam_m'].to(st['m'].device)); st['v'].copy_(ck['adam_v'].to(st['v'].device))
         self.global_step = int(ck.get('global_step', 0))
+        self._sync_step_state(machine)
         self.logger.info('Restored {} (global step {})'.format(path, self.global_step))
         return self.global_step
 
@@ -161,8 +230,8 @@ class VAETrainer(object):
             raise ValueError('VAETrainer needs the machine: pass `machine=` or a loss from machine.loss()')
         rank0 = not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
         if self.global_step == 0 and self.dirs and (self.dirs.get('restore_from') or self.dirs.get('logdir')):
-            # tf.train.Supervisor restores the newest checkpoint of its logdir before the first step; every
-            # rank reads the same file, so the replicas stay identical
+            # tf.train.Supervisor restores the newest checkpoint of its logdir before the first step; under
+            # torch.distributed rank 0 reads it and broadcasts variables, Adam slots and the step
             self.restore(ckpt=getattr(self.args, 'ckpt', None))
         t_status = t_save = t_summary = time.time()
         for step in range(self.arch['training']['max_iter'] if nIter is None else min(nIter, self.arch['training']['max_iter'])):

@@ -71,6 +71,8 @@ struct Ctx {
   int64_t n;          // frames in this chunk
   int64_t n_total;    // frames the loss means span
   cudaStream_t st;
+  const StepState* state = nullptr;   // in-kernel sampler (eps == nullptr): device-resident {seed, draws, step}
+  long long frame0 = 0;               // index of this chunk's first frame in the sampler's counter
 };
 inline float* shared_ws(const Ctx& c) { return c.ws; }
 inline int tmap_key(const Ctx&, int op_index) { return op_index; }
@@ -489,14 +491,15 @@ int launch_e0_fwd(Ctx& c, const Op& o, const Op& nx) {      // o: conv (OP_GEMM 
   g.Hi = (int)o.A.fs; g.Ho = o.A.R; g.Co = o.N; g.k = o.K; g.s = o.A.rs; g.pl = -o.A.off;
   g.out_flen = nx.out_flen; g.out_off = nx.out_off; g.out_split = p.bufs[nx.aout.buf].split; g.frames = c.n;
   if (!g.x) return fail(NPVC_ERR_ARG, "frames (x) required");
+  g.xp = e0_row_floats(g.Ho, g.s, g.pl, g.Hi);
   const int G = ln_group(nx.L, nx.Cn, nx.out_off, nx.out_flen);
   const long long fbs = (c.n + 256 / G - 1) / (256 / G);
-  long long blocks = (long long)h->sm_count * 8; if (blocks > fbs) blocks = fbs;
-  const size_t sm = (size_t)(E0_KT + 3) * g.Co * sizeof(float);
-  if (G == 32) e0_fwd_kernel<32><<<(unsigned)blocks, 256, sm, c.st>>>(g);
-  else if (G == 64) e0_fwd_kernel<64><<<(unsigned)blocks, 256, sm, c.st>>>(g);
-  else if (G == 128) e0_fwd_kernel<128><<<(unsigned)blocks, 256, sm, c.st>>>(g);
-  else e0_fwd_kernel<256><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  long long blocks = (long long)h->sm_count * 6; if (blocks > fbs) blocks = fbs;
+  const size_t sm = ((size_t)(E0_KT + 3) * g.Co + (size_t)(256 / G) * g.xp) * sizeof(float);
+  const bool v4 = nx.L / 8 > 3 * G;                       // units of 8 elements per thread: 3 or 4
+#define NPVC_E0_FWD(GG) do { if (v4) e0_fwd_kernel<GG, 4><<<(unsigned)blocks, 256, sm, c.st>>>(g); else e0_fwd_kernel<GG, 3><<<(unsigned)blocks, 256, sm, c.st>>>(g); } while (0)
+  if (G == 32) NPVC_E0_FWD(32); else if (G == 64) NPVC_E0_FWD(64); else if (G == 128) NPVC_E0_FWD(128); else NPVC_E0_FWD(256);
+#undef NPVC_E0_FWD
   h->launches++;
   return NPVC_OK;
 }
@@ -509,14 +512,15 @@ int launch_e0_bwd(Ctx& c, const Op& o, const Op& nx) {      // o: OP_LN_BWD of t
   g.Hi = (int)nx.A.fs; g.Ho = nx.A.R; g.Co = nx.N; g.k = nx.K; g.s = nx.A.rs; g.pl = -nx.A.off; g.frames = c.n;
   if (!g.x) return fail(NPVC_ERR_ARG, "frames (x) required");
   if (nx.ldb != nx.N) return fail(NPVC_ERR_ARG, "fused first-layer backward: packed weight gradient must be dense");
+  g.xp = e0_row_floats(g.Ho, g.s, g.pl, g.Hi);
   const int G = e0_bwd_group(o.L, o.Cn);
   const long long fbs = (c.n + 256 / G - 1) / (256 / G);
   long long blocks = (long long)h->sm_count * 2; if (blocks > fbs) blocks = fbs;
-  const size_t sm = (size_t)(E0_KT + 5) * g.Co * sizeof(float);
-  if (G == 32) e0_bwd_kernel<32><<<(unsigned)blocks, 256, sm, c.st>>>(g);
-  else if (G == 64) e0_bwd_kernel<64><<<(unsigned)blocks, 256, sm, c.st>>>(g);
-  else if (G == 128) e0_bwd_kernel<128><<<(unsigned)blocks, 256, sm, c.st>>>(g);
-  else e0_bwd_kernel<256><<<(unsigned)blocks, 256, sm, c.st>>>(g);
+  const size_t sm = ((size_t)(E0_KT + 5) * g.Co + (size_t)(256 / G) * g.xp) * sizeof(float);
+  const bool v4 = o.L / 4 > 3 * G;                        // units of 4 elements per thread: 3 or 4
+#define NPVC_E0_BWD(GG) do { if (v4) e0_bwd_kernel<GG, 4><<<(unsigned)blocks, 256, sm, c.st>>>(g); else e0_bwd_kernel<GG, 3><<<(unsigned)blocks, 256, sm, c.st>>>(g); } while (0)
+  if (G == 32) NPVC_E0_BWD(32); else if (G == 64) NPVC_E0_BWD(64); else if (G == 128) NPVC_E0_BWD(128); else NPVC_E0_BWD(256);
+#undef NPVC_E0_BWD
   h->launches++;
   return NPVC_OK;
 }
@@ -668,13 +672,13 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       const int z = o.i0, fpb = 8;
       double* acc = reinterpret_cast<double*>(shared_ws(c) + p.buf_offset(p.buf_acc, c.chunk_cap, c.train));
       sample_kl_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 2 * z, 0, st>>>(
-          resolve(c, o.r0), c.eps, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), c.eps ? acc : nullptr, z, c.n, fpb);
+          resolve(c, o.r0), c.eps, c.state, c.frame0, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), (c.eps || c.state) ? acc : nullptr, z, c.n, fpb);
       h->launches++; break;
     }
     case OP_SAMPLE_BWD: {
       const int z = o.i0, fpb = 16;
       sample_bwd_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 2 * z, 0, st>>>(
-          resolve(c, o.r0), c.eps, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), z, c.n, fpb, 1.0f / (float)c.n_total, p.bufs[o.r2.buf].split);
+          resolve(c, o.r0), c.eps, c.state, c.frame0, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), z, c.n, fpb, 1.0f / (float)c.n_total, p.bufs[o.r2.buf].split);
       h->launches++; break;
     }
     case OP_RECON: {
@@ -980,11 +984,12 @@ int npvc_decode(npvc_handle* h, const float* d_theta, const float* d_z, const in
   return NPVC_OK;
 }
 
-int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, const int64_t* d_y, const float* d_eps,
-                      int64_t n, float* d_z, float* d_mu, float* d_lv, float* d_xh, float* d_losses, float* d_grad,
-                      int32_t repack, void* d_ws, int64_t ws_bytes, void* stream) {
+static int loss_core(npvc_handle* h, const float* d_theta, const float* d_x, const int64_t* d_y, const float* d_eps,
+                     StepState* d_state, int64_t frame_offset,
+                     int64_t n, float* d_z, float* d_mu, float* d_lv, float* d_xh, float* d_losses, float* d_grad,
+                     int32_t repack, void* d_ws, int64_t ws_bytes, void* stream) {
   int rc = check_ws(h, n, true, ws_bytes, d_ws); if (rc) return rc;
-  if (!d_theta || !d_x || !d_y || !d_eps || n < 1) return fail(NPVC_ERR_ARG, "bad argument");
+  if (!d_theta || !d_x || !d_y || (!d_eps && !d_state) || n < 1) return fail(NPVC_ERR_ARG, "bad argument");
   rc = ensure_tables(h); if (rc) return rc;
   const Plan& p = h->plan; cudaStream_t st = (cudaStream_t)stream;
   const int64_t cap = n < h->max_chunk ? n : h->max_chunk; const int z = p.arch.z_dim, H = p.arch.in_h;
@@ -1001,7 +1006,8 @@ int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, co
   for (int64_t c0 = 0; c0 < n; c0 += cap) {
     int64_t m = n - c0 < cap ? n - c0 : cap;
     float* wset = ws; const cudaStream_t cst = st;
-    Ctx c{h, wset, cap, true, d_theta, d_grad, d_x + c0 * H, d_y + c0, d_eps + c0 * z, m, n, cst};
+    Ctx c{h, wset, cap, true, d_theta, d_grad, d_x + c0 * H, d_y + c0, d_eps ? d_eps + c0 * z : nullptr, m, n, cst};
+    if (!d_eps) { c.state = d_state; c.frame0 = frame_offset + c0; }
     for (int ph : {PH_ENC, PH_SAMPLE, PH_DEC, PH_LOSS}) { rc = run_phase(c, ph); if (rc) return rc; }
     if (d_grad) { rc = run_phase(c, PH_BWD); if (rc) return rc; }
     struct { float* dst; int buf; int w; } outs[4] = {{d_z, p.buf_z, z}, {d_mu, p.buf_mu, z}, {d_lv, p.buf_lv, z}, {d_xh, p.buf_xh, H}};
@@ -1012,12 +1018,40 @@ int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, co
     Ctx c{h, ws, cap, true, d_theta, d_grad, nullptr, nullptr, nullptr, 0, n, st};
     rc = run_phase(c, PH_FINAL); if (rc) return rc;
   }
-  if (d_losses) {
-    finalize_losses_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(ws + p.buf_offset(p.buf_acc, cap, true)), d_losses, 1.0 / (double)n);
+  if (d_losses || d_state) {
+    finalize_losses_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(ws + p.buf_offset(p.buf_acc, cap, true)), d_losses, 1.0 / (double)n,
+                                             d_state, d_grad ? 1 : 0);
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
   h->last_chunk = cap; h->last_train = true;
+  return NPVC_OK;
+}
+
+int npvc_loss_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, const int64_t* d_y, const float* d_eps,
+                      int64_t n, float* d_z, float* d_mu, float* d_lv, float* d_xh, float* d_losses, float* d_grad,
+                      int32_t repack, void* d_ws, int64_t ws_bytes, void* stream) {
+  if (!d_eps) return fail(NPVC_ERR_ARG, "bad argument (eps required: npvc_train_fwd_bwd draws it in-kernel)");
+  return loss_core(h, d_theta, d_x, d_y, d_eps, nullptr, 0, n, d_z, d_mu, d_lv, d_xh, d_losses, d_grad, repack, d_ws, ws_bytes, stream);
+}
+
+int npvc_train_fwd_bwd(npvc_handle* h, const float* d_theta, const float* d_x, const int64_t* d_y, npvc_step_state* d_state,
+                       int64_t frame_offset, int64_t n, float* d_z, float* d_mu, float* d_lv, float* d_xh, float* d_losses,
+                       float* d_grad, int32_t repack, void* d_ws, int64_t ws_bytes, void* stream) {
+  if (!d_state || frame_offset < 0) return fail(NPVC_ERR_ARG, "bad argument (device step state required)");
+  return loss_core(h, d_theta, d_x, d_y, nullptr, reinterpret_cast<StepState*>(d_state), frame_offset, n, d_z, d_mu, d_lv, d_xh, d_losses,
+                   d_grad, repack, d_ws, ws_bytes, stream);
+}
+
+int npvc_normal_draw(npvc_handle* h, const npvc_step_state* d_state, int64_t frame_offset, int64_t n, float* d_eps, void* stream) {
+  if (!h || !d_state || !d_eps || n < 0 || frame_offset < 0) return fail(NPVC_ERR_ARG, "bad argument");
+  int rc = ensure_tables(h); if (rc) return rc;
+  const int z = h->plan.arch.z_dim; const long long tot = n * z;
+  if (tot > 0) {
+    philox_normal_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const StepState*>(d_state), frame_offset, d_eps, z, n);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
   return NPVC_OK;
 }
 
@@ -1026,7 +1060,18 @@ int npvc_adam_step(npvc_handle* h, float* d_theta, const float* d_grad, float* d
   if (!h || !d_theta || !d_grad || !d_m || !d_v || step < 1) return fail(NPVC_ERR_ARG, "bad argument");
   int rc = ensure_tables(h); if (rc) return rc;
   double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) / (1.0 - std::pow((double)beta1, (double)step));
-  adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_theta, d_grad, d_m, d_v, n_params, (float)lr_t, beta1, beta2, eps, grad_scale);
+  adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_theta, d_grad, d_m, d_v, n_params, (float)lr_t, beta1, beta2, eps, grad_scale, nullptr);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return NPVC_OK;
+}
+
+int npvc_adam_step_dev(npvc_handle* h, float* d_theta, const float* d_grad, float* d_m, float* d_v, int64_t n_params,
+                       const npvc_step_state* d_state, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!h || !d_theta || !d_grad || !d_m || !d_v || !d_state) return fail(NPVC_ERR_ARG, "bad argument");
+  int rc = ensure_tables(h); if (rc) return rc;
+  adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_theta, d_grad, d_m, d_v, n_params, lr, beta1, beta2, eps, grad_scale,
+                                                                                    reinterpret_cast<const StepState*>(d_state));
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return NPVC_OK;

@@ -22,71 +22,84 @@ struct E0FwdArgs {
   const float* x; const float* W; const float* bias; const float* gamma; const float* beta;
   float* c;                     // raw conv output [frames][Ho * Co] (nullptr: inference, not kept)
   float* mean; float* rstd; float* aout;
-  int Hi, Ho, Co, k, s, pl, out_flen, out_off, out_split; long long frames;
+  int Hi, Ho, Co, k, s, pl, out_flen, out_off, out_split;
+  int xp;                       // floats of a staged input row: pl zeros | Hi inputs | zeros up to s (Ho - 1) + KT, rounded up to 4
+  long long frames;
 };
 struct E0BwdArgs {
   const float* x; const float* dy; const float* cin; const float* mean; const float* rstd;
   const float* gamma; const float* beta;
   float* dW;                    // [k][Co] packed weight gradient (accumulated)
   float* dgamma; float* dbeta; float* dbias;
-  int Hi, Ho, Co, k, s, pl; long long frames;
+  int Hi, Ho, Co, k, s, pl, xp; long long frames;
 };
 
-constexpr int E0_KT = 8;        // taps held per thread (weights beyond k are zero)
+constexpr int E0_KT = 8;        // taps per position (weights beyond k are zero)
+__host__ __device__ inline int e0_row_floats(int Ho, int s, int pl, int Hi) {
+  int need = s * (Ho - 1) + E0_KT; if (need < pl + Hi) need = pl + Hi;
+  return (need + 3) / 4 * 4;
+}
 
-template <int G>
-__global__ void __launch_bounds__(256) e0_fwd_kernel(E0FwdArgs g) {
-  constexpr int V = 4, FPB = 256 / G;
-  extern __shared__ __align__(16) float e0sm[];      // [KT][Co] weights | bias | gamma | beta
+// the frame with its SAME padding (zeros) in shared memory: the taps read it without predicates or address math
+__device__ __forceinline__ void e0_stage_x(float* xs, const float* xp, bool fok, int t, int G, int XP, int pl, int Hi) {
+  for (int i = t; i < XP; i += G) { const int xi = i - pl; xs[i] = (fok && xi >= 0 && xi < Hi) ? __ldg(xp + xi) : 0.f; }
+}
+
+// G threads per frame, V units of 8 consecutive channels per thread (L <= 8 G V)
+template <int G, int V>
+__global__ void __launch_bounds__(256, 3) e0_fwd_kernel(E0FwdArgs g) {
+  constexpr int FPB = 256 / G;
+  extern __shared__ __align__(16) float e0sm[];      // [KT][Co] weights | bias | gamma | beta | [FPB][xp] staged frames
   __shared__ float red[8];
-  const int Co = g.Co;
+  const int Co = g.Co, XP = g.xp;
   float* sw = e0sm; float* sb = sw + E0_KT * Co; float* sg = sb + Co; float* sbt = sg + Co;
   for (int i = threadIdx.x; i < E0_KT * Co; i += blockDim.x) sw[i] = (i < g.k * Co) ? g.W[i] : 0.f;
   for (int i = threadIdx.x; i < Co; i += blockDim.x) { sb[i] = g.bias[i]; sg[i] = g.gamma[i]; sbt[i] = g.beta[i]; }
-  __syncthreads();
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
+  float* xs = sbt + Co + grp * XP;
   const int cpb = Co >> 3;                             // 8-channel blocks per position (a power of two: divides G)
   const int cshift = 31 - __clz(cpb);
   const int c0 = (t & (cpb - 1)) << 3;                 // this thread's channels
   const int L = g.Ho * Co, L8 = L >> 3, off8 = g.out_off >> 3, F8 = g.out_flen >> 3;
   const float invL = 1.0f / (float)L;
+  const float2* w2 = reinterpret_cast<const float2*>(sw + c0);
   for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
     const long long f = fb * FPB + grp; const bool fok = f < g.frames;
-    const float* xp = g.x + f * g.Hi;
-    float v[V][8];
+    __syncthreads();                                   // (first pass: the weights; later: the previous frame's taps are done)
+    e0_stage_x(xs, g.x + f * g.Hi, fok, t, G, XP, g.pl, g.Hi);
+    __syncthreads();
+    float2 v[V][4];
     float s[1] = {0.f};
 #pragma unroll
     for (int i = 0; i < V; i++) {
       const int u = t + i * G;
-      if (fok && u < L8) {
-        const int i0 = g.s * (u >> cshift) - g.pl;     // first input position of the window (SAME padding: zeros outside)
-        { const float4 a = *reinterpret_cast<const float4*>(sb + c0), b = *reinterpret_cast<const float4*>(sb + c0 + 4);
-          v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w; }
+      if (u < L8) {
+        const float* xw = xs + g.s * (u >> cshift);   // window of output position u / cpb
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[i][q] = *reinterpret_cast<const float2*>(sb + c0 + 2 * q);
 #pragma unroll
         for (int kk = 0; kk < E0_KT; kk++) {
-          const int xi = i0 + kk;
-          const float xv = (kk < g.k && xi >= 0 && xi < g.Hi) ? __ldg(xp + xi) : 0.f;
-          const float4 a = *reinterpret_cast<const float4*>(sw + kk * Co + c0), b = *reinterpret_cast<const float4*>(sw + kk * Co + c0 + 4);
-          v[i][0] = fmaf(xv, a.x, v[i][0]); v[i][1] = fmaf(xv, a.y, v[i][1]); v[i][2] = fmaf(xv, a.z, v[i][2]); v[i][3] = fmaf(xv, a.w, v[i][3]);
-          v[i][4] = fmaf(xv, b.x, v[i][4]); v[i][5] = fmaf(xv, b.y, v[i][5]); v[i][6] = fmaf(xv, b.z, v[i][6]); v[i][7] = fmaf(xv, b.w, v[i][7]);
+          const float xv = xw[kk]; const float2 x2 = make_float2(xv, xv);
+#pragma unroll
+          for (int q = 0; q < 4; q++) v[i][q] = __ffma2_rn(x2, w2[(kk * Co >> 1) + q], v[i][q]);
         }
 #pragma unroll
-        for (int e = 0; e < 8; e++) s[0] += v[i][e];
+        for (int q = 0; q < 4; q++) s[0] += v[i][q].x + v[i][q].y;
       }
     }
     group_sum<G, 1>(s, red);
     const float mean = s[0] * invL;
-    float q[1] = {0.f};
+    float q2[1] = {0.f};
 #pragma unroll
     for (int i = 0; i < V; i++) {
-      if (fok && t + i * G < L8) {
+      if (t + i * G < L8) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) { const float d = v[i][e] - mean; q[0] = fmaf(d, d, q[0]); }
+        for (int q = 0; q < 4; q++) { const float d0 = v[i][q].x - mean, d1 = v[i][q].y - mean; q2[0] = fmaf(d0, d0, q2[0]); q2[0] = fmaf(d1, d1, q2[0]); }
       }
     }
-    group_sum<G, 1>(q, red);
-    const float rs = rsqrtf(q[0] * invL + NPVC_LN_EPS);
-    if (!fok) continue;                    // (no block-wide barrier after this point in the iteration)
+    group_sum<G, 1>(q2, red);
+    const float rs = rsqrtf(q2[0] * invL + NPVC_LN_EPS);
+    if (!fok) continue;                    // (every thread still reaches the barriers at the top of the next iteration)
     if (t == 0) { g.rstd[f] = rs; g.mean[f] = mean; }
     float gm[8], bt[8];
     { const float4 a = *reinterpret_cast<const float4*>(sg + c0), b = *reinterpret_cast<const float4*>(sg + c0 + 4);
@@ -97,10 +110,11 @@ __global__ void __launch_bounds__(256) e0_fwd_kernel(E0FwdArgs g) {
     for (int i = 0; i < V; i++) {
       const int u = t + i * G;
       if (u < L8) {
-        if (g.c) st8(g.c, f, L, 8 * u, v[i], 0);
+        const float r[8] = {v[i][0].x, v[i][0].y, v[i][1].x, v[i][1].y, v[i][2].x, v[i][2].y, v[i][3].x, v[i][3].y};
+        if (g.c) st8(g.c, f, L, 8 * u, r, 0);
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e] = lrelu_f(fmaf((v[i][e] - mean) * rs, gm[e], bt[e]));
+        for (int e = 0; e < 8; e++) o[e] = lrelu_f(fmaf((r[e] - mean) * rs, gm[e], bt[e]));
         st8(g.aout, f, g.out_flen, 8 * (u + off8), o, g.out_split);
       }
     }
@@ -108,42 +122,46 @@ __global__ void __launch_bounds__(256) e0_fwd_kernel(E0FwdArgs g) {
   }
 }
 
-template <int G>
+// G threads per frame, V units of 4 consecutive channels per thread (L <= 4 G V)
+template <int G, int V>
 __global__ void __launch_bounds__(256, 2) e0_bwd_kernel(E0BwdArgs g) {
-  constexpr int V = 4, FPB = 256 / G;
-  extern __shared__ __align__(16) float e0sm[];      // [3 Co] dgamma | dbeta | dbias sums, [KT Co] dW sums, gamma, beta
+  constexpr int FPB = 256 / G;
+  extern __shared__ __align__(16) float e0sm[];      // [3 Co] dgamma | dbeta | dbias sums, [KT Co] dW sums, gamma, beta, [FPB][xp] frames
   __shared__ float red[16];
-  const int Co = g.Co;
+  const int Co = g.Co, XP = g.xp;
   float* chs = e0sm; float* sdw = chs + 3 * Co; float* sgm = sdw + E0_KT * Co; float* sbt = sgm + Co;
   for (int i = threadIdx.x; i < (3 + E0_KT) * Co; i += blockDim.x) e0sm[i] = 0.f;
   for (int i = threadIdx.x; i < Co; i += blockDim.x) { sgm[i] = g.gamma[i]; sbt[i] = g.beta[i]; }
   __syncthreads();
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
+  float* xs = sbt + Co + grp * XP;
   const int qpp = Co >> 2;                             // channel quads per position (a power of two: divides G)
   const int qshift = 31 - __clz(qpp);
   const int c0 = (t & (qpp - 1)) << 2;
   const int L = g.Ho * Co, L4 = L >> 2;
   const float invL = 1.0f / (float)L;
-  float gm[4], bt[4], adg[4], adb[4], adc[4], dw[E0_KT][4];
+  float gm[4], bt[4], adg[4], adb[4], adc[4];
+  float2 dw[E0_KT][2];
 #pragma unroll
   for (int e = 0; e < 4; e++) { gm[e] = sgm[c0 + e]; bt[e] = sbt[c0 + e]; adg[e] = adb[e] = adc[e] = 0.f; }
 #pragma unroll
-  for (int kk = 0; kk < E0_KT; kk++)
-#pragma unroll
-    for (int e = 0; e < 4; e++) dw[kk][e] = 0.f;
+  for (int kk = 0; kk < E0_KT; kk++) dw[kk][0] = dw[kk][1] = make_float2(0.f, 0.f);
   for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
     const long long f = fb * FPB + grp; const bool fok = f < g.frames;
     float dx[V][4], xh[V][4];
     float rs = 0.f, mu = 0.f;
     if (fok) { rs = g.rstd[f]; mu = g.mean[f]; }
+    const float4* dyp = reinterpret_cast<const float4*>(g.dy + f * L) + t;
+    const float4* cp = reinterpret_cast<const float4*>(g.cin + f * L) + t;
 #pragma unroll
     for (int i = 0; i < V; i++) {
-      const int u = t + i * G;
-      if (fok && u < L4) {
-        const float4 a = *reinterpret_cast<const float4*>(g.dy + f * L + 4 * u), b = *reinterpret_cast<const float4*>(g.cin + f * L + 4 * u);
+      if (fok && t + i * G < L4) {
+        const float4 a = dyp[i * G], b = cp[i * G];
         dx[i][0] = a.x; dx[i][1] = a.y; dx[i][2] = a.z; dx[i][3] = a.w; xh[i][0] = b.x; xh[i][1] = b.y; xh[i][2] = b.z; xh[i][3] = b.w;
       }
     }
+    __syncthreads();                                   // the previous frame's taps are done with the staged rows
+    e0_stage_x(xs, g.x + f * g.Hi, fok, t, G, XP, g.pl, g.Hi);
     float s[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < V; i++) {
@@ -160,10 +178,10 @@ __global__ void __launch_bounds__(256, 2) e0_bwd_kernel(E0BwdArgs g) {
         }
       }
     }
+    __syncthreads();                                   // staged rows visible
     group_sum<G, 2>(s, red);
     if (!fok) continue;
     const float s1 = s[0] * invL, s2 = s[1] * invL;
-    const float* xp = g.x + f * g.Hi;
 #pragma unroll
     for (int i = 0; i < V; i++) {
       const int u = t + i * G;
@@ -171,13 +189,12 @@ __global__ void __launch_bounds__(256, 2) e0_bwd_kernel(E0BwdArgs g) {
         float o[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) { o[e] = rs * (dx[i][e] - s1 - xh[i][e] * s2); adc[e] += o[e]; }
-        const int i0 = g.s * (u >> qshift) - g.pl;
+        const float2 o01 = make_float2(o[0], o[1]), o23 = make_float2(o[2], o[3]);
+        const float* xw = xs + g.s * (u >> qshift);
 #pragma unroll
         for (int kk = 0; kk < E0_KT; kk++) {
-          const int xi = i0 + kk;
-          const float xv = (kk < g.k && xi >= 0 && xi < g.Hi) ? __ldg(xp + xi) : 0.f;
-#pragma unroll
-          for (int e = 0; e < 4; e++) dw[kk][e] = fmaf(xv, o[e], dw[kk][e]);
+          const float xv = xw[kk]; const float2 x2 = make_float2(xv, xv);
+          dw[kk][0] = __ffma2_rn(x2, o01, dw[kk][0]); dw[kk][1] = __ffma2_rn(x2, o23, dw[kk][1]);
         }
       }
     }
@@ -188,9 +205,10 @@ __global__ void __launch_bounds__(256, 2) e0_bwd_kernel(E0BwdArgs g) {
     atomicAdd(&chs[c0 + e], adg[e]); atomicAdd(&chs[Co + c0 + e], adb[e]); atomicAdd(&chs[2 * Co + c0 + e], adc[e]);
   }
 #pragma unroll
-  for (int kk = 0; kk < E0_KT; kk++)
-#pragma unroll
-    for (int e = 0; e < 4; e++) atomicAdd(&sdw[kk * Co + c0 + e], dw[kk][e]);
+  for (int kk = 0; kk < E0_KT; kk++) {
+    atomicAdd(&sdw[kk * Co + c0 + 0], dw[kk][0].x); atomicAdd(&sdw[kk * Co + c0 + 1], dw[kk][0].y);
+    atomicAdd(&sdw[kk * Co + c0 + 2], dw[kk][1].x); atomicAdd(&sdw[kk * Co + c0 + 3], dw[kk][1].y);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < Co; i += blockDim.x) {
     atomicAdd(&g.dgamma[i], chs[i]); atomicAdd(&g.dbeta[i], chs[Co + i]); atomicAdd(&g.dbias[i], chs[2 * Co + i]);

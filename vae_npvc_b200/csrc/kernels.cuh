@@ -1035,9 +1035,34 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_bulk_kernel(LnBwdArgs g) {
 }
 
 // =============================================================================================
-// sampler + KL  (util/layers.py:152-156,170-183); blockDim = 2z threads, thread = column
+// The N(0,1) draw of GaussianSampleLayer (util/layers.py:154, tf.random_normal) made in-kernel: counter-based
+// Philox4x32-10 (Salmon et al., SC'11 -- the generator family TF's RandomStandardNormal uses; TF's own stream is
+// not reproducible) keyed by the caller's seed, counter = (dim, frame index, pass counter), Box-Muller on two of
+// the four output words.  A draw depends only on (seed, pass, frame, dim): identical for any chunking, launch
+// geometry or rank layout, and the backward regenerates it instead of reading 512 B / frame back.
 // =============================================================================================
-__global__ void sample_kl_kernel(const float* hz, const float* eps, float* mu, float* lv, float* zout,
+struct StepState { unsigned long long seed; long long draws; long long step; long long reserved; };   // == npvc_step_state
+
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long draws, unsigned long long frame, uint32_t dim) {
+  uint32_t c0 = dim, c1 = (uint32_t)frame, c2 = (uint32_t)(frame >> 32), c3 = (uint32_t)draws;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(draws >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const float u1 = (float)((c0 >> 8) + 1u) * 5.9604644775390625e-8f;     // (0, 1], 24 bits
+  const float u2 = (float)(c1 >> 8) * 5.9604644775390625e-8f;            // [0, 1)
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// =============================================================================================
+// sampler + KL  (util/layers.py:152-156,170-183); blockDim = 2z threads, thread = column
+// eps != nullptr: the caller's draw; else st != nullptr: in-kernel Philox (frame index = frame0 + f); else no sampling
+// =============================================================================================
+__global__ void sample_kl_kernel(const float* hz, const float* eps, const StepState* st, long long frame0, float* mu, float* lv, float* zout,
                                  double* acc_kl, int z, long long frames, int frames_per_block) {
   __shared__ float red[40];
   const int col = threadIdx.x;
@@ -1053,10 +1078,16 @@ __global__ void sample_kl_kernel(const float* hz, const float* eps, float* mu, f
       float m = hz[f * 2 * z + d];
       float ev = expf(v);
       if (eps) zout[f * z + d] = fmaf(eps[f * z + d], sqrtf(ev), m);
+      else if (st) zout[f * z + d] = fmaf(philox_normal(st->seed, (unsigned long long)st->draws, (unsigned long long)(frame0 + f), (uint32_t)d), sqrtf(ev), m);
       kl += 0.5f * (-v + (ev + m * m) / NPVC_ONE_PLUS_EPS - 1.0f);
     }
   }
   if (acc_kl) { float t = block_sum(kl, red); if (threadIdx.x == 0) atomicAdd(acc_kl, (double)t); }
+}
+// the in-kernel draw alone (tests: statistics / reproducibility of the generator): out[n, z]
+__global__ void philox_normal_kernel(const StepState* st, long long frame0, float* out, int z, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * z) out[i] = philox_normal(st->seed, (unsigned long long)st->draws, (unsigned long long)(frame0 + i / z), (uint32_t)(i % z));
 }
 
 // GaussianSampleLayer alone (util/layers.py:152-156)
@@ -1066,7 +1097,7 @@ __global__ void sample_only_kernel(const float* mu, const float* lv, const float
 }
 
 // dz, eps, (mu|lv) -> (dmu|dlv); column sums -> head-bias grads.  inv_n = 1 / (frames the means span)
-__global__ void sample_bwd_kernel(const float* dz, const float* eps, const float* hz, float* dhz, float* dbh,
+__global__ void sample_bwd_kernel(const float* dz, const float* eps, const StepState* st, long long frame0, const float* hz, float* dhz, float* dbh,
                                   int z, long long frames, int frames_per_block, float inv_n, int out_split) {
   const int col = threadIdx.x;
   const long long f0 = (long long)blockIdx.x * frames_per_block;
@@ -1081,7 +1112,8 @@ __global__ void sample_bwd_kernel(const float* dz, const float* eps, const float
       const int d = col - z;
       float l = hz[f * 2 * z + col];
       float ev = expf(l);
-      o = dz[f * z + d] * eps[f * z + d] * 0.5f * sqrtf(ev) + 0.5f * (ev / NPVC_ONE_PLUS_EPS - 1.0f) * inv_n;
+      const float e = eps ? eps[f * z + d] : philox_normal(st->seed, (unsigned long long)st->draws, (unsigned long long)(frame0 + f), (uint32_t)d);
+      o = dz[f * z + d] * e * 0.5f * sqrtf(ev) + 0.5f * (ev / NPVC_ONE_PLUS_EPS - 1.0f) * inv_n;
     }
     if (out_split) split_st1(reinterpret_cast<uint16_t*>(dhz) + f * 4 * z + col, 2 * z, o);
     else dhz[f * 2 * z + col] = o;
@@ -1199,8 +1231,20 @@ __global__ void unpack_heavy_kernel(const float* adw, const int* ptr, const int*
 }
 
 // TF-form Adam (trainer/vae.py:16-24): theta -= lr_t * m / (sqrt(v) + eps)
+// st != nullptr: the step t lives on the device (StepState::step, advanced by the fwd+bwd pass) and
+// lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) is formed here -- nothing the host computes changes between steps, so a
+// captured CUDA graph of the whole training step replays unchanged.  lr_t then carries the base rate lr.
 __global__ void adam_kernel(float* theta, const float* grad, float* m, float* v, long long n,
-                            float lr_t, float b1, float b2, float eps, float gscale) {
+                            float lr_t, float b1, float b2, float eps, float gscale, const StepState* st) {
+  if (st) {
+    __shared__ float s_lr;
+    if (threadIdx.x == 0) {
+      const double t = (double)st->step;
+      s_lr = (float)((double)lr_t * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+    }
+    __syncthreads();
+    lr_t = s_lr;
+  }
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g = grad[i] * gscale;
@@ -1210,10 +1254,13 @@ __global__ void adam_kernel(float* theta, const float* grad, float* m, float* v,
   theta[i] -= lr_t * mm / (sqrtf(vv) + eps);
 }
 
-__global__ void finalize_losses_kernel(const double* acc, float* losses, double inv_n) {
+// losses = {G, D_KL, logP}; st != nullptr: the pass counter of the in-kernel sampler advances, and -- after a pass
+// that produced a gradient -- the step counter the device-side Adam reads
+__global__ void finalize_losses_kernel(const double* acc, float* losses, double inv_n, StepState* st, int had_grad) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double kl = acc[0] * inv_n, lp = acc[1] * inv_n;
-    losses[0] = (float)(-lp + kl); losses[1] = (float)kl; losses[2] = (float)lp;
+    if (losses) { losses[0] = (float)(-lp + kl); losses[1] = (float)kl; losses[2] = (float)lp; }
+    if (st) { st->draws += 1; if (had_grad) st->step += 1; }
   }
 }
 

@@ -4,8 +4,8 @@ PyTorch is plumbing here (allocation, streams, torch.distributed); every arithme
 path runs in the hand-written CUDA library through the C-ABI.  There is no CPU fallback: without a
 CUDA device (or without the built extension) the constructors raise.
 """
+import functools
 import math
-
 import os
 
 import torch
@@ -18,7 +18,19 @@ def _ptr(t):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream().cuda_stream     # (of the current device: see _on_device)
+
+
+def _on_device(fn):
+    """Run an Engine method with the engine's device current: the library binds its device tables, kernel
+    attributes and launches to the current device, and `_stream()` is that device's current stream."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapper
 
 
 def _f32c(t, name):
@@ -34,6 +46,10 @@ class Engine:
         if not torch.cuda.is_available():
             raise RuntimeError("vae_npvc_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("vae_npvc_b200 runs on CUDA devices only (got %s)" % self.device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.arch = arch
         self.handle = _lib.Handle(arch, max_chunk)
         self.lib = self.handle.lib
@@ -45,6 +61,7 @@ class Engine:
         self._ws_train = False
 
     # ------------------------------------------------------------------ parameters
+    @_on_device
     def init_theta(self, seed=0, perturb=0.0):
         """Flat fp32 parameter vector with the TF default initialisers of the path:
         glorot_uniform kernels, zero biases / LN offsets, unit LN scales.  perturb > 0 moves
@@ -68,6 +85,7 @@ class Engine:
         return {p["name"]: flat[p["offset"]:p["offset"] + p["size"]].view(p["shape"]) for p in self.table}
 
     # ------------------------------------------------------------------ workspace
+    @_on_device
     def workspace(self, n, train):
         need = self.handle.workspace_bytes(n, train)
         # the training layout is a superset of the inference layout with identical offsets for
@@ -81,6 +99,7 @@ class Engine:
 
     _packed_for = None
 
+    @_on_device
     def pack(self, theta, ws=None):
         ws = ws if ws is not None else self.workspace(1, False)
         _lib.check(self.lib.npvc_pack_weights(self.handle.h, _ptr(_f32c(theta, "theta")), ws.data_ptr(), ws.numel(), _stream()))
@@ -91,6 +110,7 @@ class Engine:
             self.pack(theta, ws)
 
     # ------------------------------------------------------------------ path entry points
+    @_on_device
     def encode(self, theta, x):
         """x [n,513] -> (mu, lv) [n,z]   (model/vae.py:72-82)."""
         x = _f32c(x, "x").view(-1, self.in_h)
@@ -102,11 +122,13 @@ class Engine:
         _lib.check(self.lib.npvc_encode(self.handle.h, _ptr(theta), _ptr(x), n, _ptr(mu), _ptr(lv), ws.data_ptr(), ws.numel(), _stream()))
         return mu, lv
 
+    @_on_device
     def sample(self, mu, lv, eps):
         z = torch.empty_like(mu)
         _lib.check(self.lib.npvc_sample(self.handle.h, _ptr(_f32c(mu, "mu")), _ptr(_f32c(lv, "lv")), _ptr(_f32c(eps, "eps")), mu.shape[0], _ptr(z), _stream()))
         return z
 
+    @_on_device
     def decode(self, theta, z, y):
         """z [n,z], y [n] int64 -> xh [n,513]   (model/vae.py:84-103)."""
         z = _f32c(z, "z")
@@ -119,16 +141,37 @@ class Engine:
         _lib.check(self.lib.npvc_decode(self.handle.h, _ptr(theta), _ptr(z), _ptr(y), n, _ptr(xh), ws.data_ptr(), ws.numel(), _stream()))
         return xh
 
-    def loss_fwd_bwd(self, theta, x, y, eps, grad=None, outputs=True, losses=None):
+    @_on_device
+    def new_step_state(self, seed=0):
+        """Device-resident {seed, draws, step, reserved} of a training loop (include/npvc_b200.h, npvc_step_state)."""
+        st = torch.zeros(4, dtype=torch.int64, device=self.device)
+        st[0] = int(seed) & 0x7FFFFFFFFFFFFFFF
+        return st
+
+    @_on_device
+    def normal_draw(self, state, n, frame_offset=0):
+        """The N(0,1) draw the next train pass over these frames will make (tests / debugging)."""
+        eps = torch.empty(n, self.z_dim, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.npvc_normal_draw(self.handle.h, state.data_ptr(), int(frame_offset), n, _ptr(eps), _stream()))
+        return eps
+
+    @_on_device
+    def loss_fwd_bwd(self, theta, x, y, eps=None, grad=None, outputs=True, losses=None, state=None, frame_offset=0):
         """Forward + losses (+ backward into `grad` when given)   (model/vae.py:106-130).
+        eps: the N(0,1) draw of the sampler as a tensor (parity tests), or None with `state` (new_step_state()):
+        drawn in-kernel, the state's pass / step counters advance on the device.
         Returns dict(losses=[G, D_KL, logP] device tensor, z, mu, lv, xh)."""
         x = _f32c(x, "x").view(-1, self.in_h)
         n = x.shape[0]
-        eps = _f32c(eps, "eps")
         if y.dtype != torch.int64 or not y.is_cuda or y.numel() != n:
             raise ValueError("y must be an int64 CUDA tensor of n labels")
-        if eps.shape != (n, self.z_dim):
-            raise ValueError("eps must be [n, z_dim]")
+        if eps is None:
+            if state is None or state.dtype != torch.int64 or state.numel() != 4 or not state.is_cuda:
+                raise ValueError("without eps a device step state (new_step_state()) is required")
+        else:
+            eps = _f32c(eps, "eps")
+            if eps.shape != (n, self.z_dim):
+                raise ValueError("eps must be [n, z_dim]")
         ws = self.workspace(n, True)
         if os.environ.get("NPVC_DEBUG_POISON"):          # bring-up: every byte the pass does not write itself reads as NaN
             ws.fill_(0xFF); self._packed_for = None
@@ -141,30 +184,45 @@ class Engine:
             losses = torch.empty(3, dtype=torch.float32, device=self.device)
         if grad is not None:
             _f32c(grad, "grad")
-        _lib.check(self.lib.npvc_loss_fwd_bwd(
-            self.handle.h, _ptr(_f32c(theta, "theta")), _ptr(x), _ptr(y), _ptr(eps), n,
-            _ptr(out.get("z")), _ptr(out.get("mu")), _ptr(out.get("lv")), _ptr(out.get("xh")),
-            _ptr(losses), _ptr(grad), 1 if repack else 0, ws.data_ptr(), ws.numel(), _stream()))
+        if eps is not None:
+            _lib.check(self.lib.npvc_loss_fwd_bwd(
+                self.handle.h, _ptr(_f32c(theta, "theta")), _ptr(x), _ptr(y), _ptr(eps), n,
+                _ptr(out.get("z")), _ptr(out.get("mu")), _ptr(out.get("lv")), _ptr(out.get("xh")),
+                _ptr(losses), _ptr(grad), 1 if repack else 0, ws.data_ptr(), ws.numel(), _stream()))
+        else:
+            _lib.check(self.lib.npvc_train_fwd_bwd(
+                self.handle.h, _ptr(_f32c(theta, "theta")), _ptr(x), _ptr(y), state.data_ptr(), int(frame_offset), n,
+                _ptr(out.get("z")), _ptr(out.get("mu")), _ptr(out.get("lv")), _ptr(out.get("xh")),
+                _ptr(losses), _ptr(grad), 1 if repack else 0, ws.data_ptr(), ws.numel(), _stream()))
         self._packed_for = (theta.data_ptr(), theta._version, ws.data_ptr())
         out["losses"] = losses
         return out
 
+    @_on_device
     def adam_step(self, theta, grad, m, v, step, lr, beta1, beta2, eps=1e-8, grad_scale=1.0):
-        """TF-form Adam on the flat buffers (trainer/vae.py:16-24)."""
-        _lib.check(self.lib.npvc_adam_step(self.handle.h, _ptr(theta), _ptr(grad), _ptr(m), _ptr(v), theta.numel(),
-                                           int(step), lr, beta1, beta2, eps, grad_scale, _stream()))
+        """TF-form Adam on the flat buffers (trainer/vae.py:16-24).  `step`: the 1-based t as a Python int, or a
+        device step state (new_step_state()) whose `step` counter the kernel reads."""
+        if torch.is_tensor(step):
+            _lib.check(self.lib.npvc_adam_step_dev(self.handle.h, _ptr(theta), _ptr(grad), _ptr(m), _ptr(v), theta.numel(),
+                                                   step.data_ptr(), lr, beta1, beta2, eps, grad_scale, _stream()))
+        else:
+            _lib.check(self.lib.npvc_adam_step(self.handle.h, _ptr(theta), _ptr(grad), _ptr(m), _ptr(v), theta.numel(),
+                                               int(step), lr, beta1, beta2, eps, grad_scale, _stream()))
         self._packed_for = None      # theta changed behind torch's version counter
 
+    @_on_device
     def tanhize_forward(self, x, xmin, xmax, out=None):
         out = torch.empty_like(x) if out is None else out
         _lib.check(self.lib.npvc_tanhize_forward(self.handle.h, _ptr(_f32c(x, "x")), _ptr(xmin), _ptr(xmax), x.shape[0], x.shape[1], _ptr(out), _stream()))
         return out
 
+    @_on_device
     def tanhize_backward(self, x, xmin, xmax, out=None):
         out = torch.empty_like(x) if out is None else out
         _lib.check(self.lib.npvc_tanhize_backward(self.handle.h, _ptr(_f32c(x, "x")), _ptr(xmin), _ptr(xmax), x.shape[0], x.shape[1], _ptr(out), _stream()))
         return out
 
+    @_on_device
     def unpack_records(self, records, sp_dim, xmin=None, xmax=None):
         """[n, 1029] float32 records -> (x [n,513] Tanhize'd, y [n] int64)   (analyzer.py:111-127)."""
         records = _f32c(records, "records")
@@ -174,6 +232,7 @@ class Engine:
         _lib.check(self.lib.npvc_unpack_records(self.handle.h, _ptr(records), n, rf, sp_dim, _ptr(xmin), _ptr(xmax), _ptr(x), _ptr(y), _stream()))
         return x, y
 
+    @_on_device
     def debug_buffer(self, name, n):
         per = self.lib.npvc_debug_buffer(self.handle.h, name.encode(), self._ws.data_ptr(), None, n, None)
         if per < 0:

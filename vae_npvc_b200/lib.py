@@ -48,6 +48,9 @@ SYMBOLS = {
     "npvc_decode": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "npvc_loss_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _P]),
     "npvc_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _P]),
+    "npvc_train_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _P]),
+    "npvc_normal_draw": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
+    "npvc_adam_step_dev": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _P]),
     "npvc_tanhize_forward": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P]),
     "npvc_tanhize_backward": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P]),
     "npvc_unpack_records": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
