@@ -83,27 +83,35 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.perf_counter()])
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0=None, t1=None):
+        """Samples taken while the workload ran (from the first warm-up step to the end of the load that follows the
+        timed steps); `samples_timed` of them fall inside the timed region [t0, t1] itself."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        timed = sum(1 for r in self.rows if t0 is not None and t0 <= r[-1] <= t1)
+        self.rows = [r[:-1] for r in self.rows]
+        self._timed = timed
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
         pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm), "samples_timed": self._timed}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -339,11 +347,23 @@ def main():
         trainer.use_graph = not args.no_graph and os.environ.get("NPVC_GRAPH", "1") != "0"
 
     # ---- device-resident arm: inputs already in HBM ------------------------------------------
-    for i in range(args.warmup):
-        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL])
+    # clocks / throttle reasons are sampled (nvidia-smi, 20 ms period) from the first warm-up step on, through the timed
+    # steps and through the same load repeated for >= 0.4 s afterwards (a 20-step timed region lasts < 0.1 s)
     sampler = ClockSampler(local); sampler.start()
+    t_w = time.perf_counter()
+    i = 0
+    while i < args.warmup or (time.perf_counter() - t_w < 0.25 and i < 2000):
+        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]); i += 1
+        if i >= args.warmup:
+            torch.cuda.synchronize()
+    t0 = sampler.mark()
     ms = timed(lambda i: step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]), args.steps)
-    clocks = sampler.stop()
+    t1 = sampler.mark()
+    t_l = time.perf_counter(); i = 0
+    while time.perf_counter() - t_l < 0.4 and i < 4000:
+        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]); i += 1
+        torch.cuda.synchronize()
+    clocks = sampler.stop(t0, t1)
     value = world * n * args.steps / (ms / 1000.0)
     graphed = bool(trainer is not None and trainer._state and any(q["graph"] is not None for q in trainer._state["graphs"].values()))
 

@@ -227,13 +227,18 @@ def test_benchmark_sizes_against_the_oracle(eng, arch, n, n_speakers):
     print("n=%d worst per-tensor gradient error %.2e" % (n, worst))
 
 
-def test_unfused_plan_matches_oracle(arch, monkeypatch):
-    """NPVC_FUSE=0: every plan op as its own kernel (the path shapes without a fused kernel take)."""
+@pytest.mark.parametrize("switch", ["NPVC_FUSE=0", "NPVC_FUSE_LN_TRAIN=1"])
+def test_fusion_switches_match_oracle(arch, monkeypatch, switch):
+    """NPVC_FUSE=0: every plan op as its own kernel (the path shapes without a fused kernel take).
+    NPVC_FUSE_LN_TRAIN=1: the Layernorm epilogue of the forward kernel (default for inference passes only) in a training
+    pass, where it also stores the raw conv output for the backward."""
     from vae_npvc_b200.engine import Engine
-    monkeypatch.setenv("NPVC_FUSE", "0")
+    k, v = switch.split("=")
+    monkeypatch.setenv(k, v)
     e2 = Engine(arch, "cuda:0")
-    monkeypatch.delenv("NPVC_FUSE")
-    _check_against_oracle(e2, arch, 37)
+    monkeypatch.delenv(k)
+    for n in (37, 300):
+        _check_against_oracle(e2, arch, n)
 
 
 def test_cfg3_inference_size(eng, arch):

@@ -41,6 +41,8 @@ struct npvc_handle {
   struct TMaps { const void* a; const void* b; long long frames; int bn, rows_tile, sw; CUtensorMap tAh, tAl, tBh, tBl; };
   std::map<int, TMaps> tmaps;        // per-op tensor-map cache
   std::map<int, TMaps> tmaps_pair;   // same, CTA-pair launches (B boxes of BN / 2 rows)
+  int fuse_ln_train = 0;             // NPVC_FUSE_LN_TRAIN=1: the Layernorm epilogue in training passes too (A/B comparisons; measured slower)
+  bool attr_fwd_ln = false;
   int umma_pair = 1;                 // NPVC_PAIR=0: no cta_group::2 CTA pairs; 2: every BN >= 128 layer (A/B comparisons)
   std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the shape rule)
   int wgrad_pair = 0;                // NPVC_WGRAD_PAIR=1|2: cta_group::2 form of the weight-gradient kernel for N >= 128 (2: 256-column
@@ -197,8 +199,28 @@ int make_view_maps(npvc_handle* h, const Ctx& c, const View& v, int extent, cons
 
 // Tap mode of the forward kernel (umma_gemm.cuh): eligible when the view is a conv window with 16 / 32 / 64
 // channels per tap, one N tile, and the weights of all taps plus >= 2 activation stages fit shared memory.
+constexpr int LN_EPI_SMEM = 32768;     // shared memory of the fused Layernorm epilogue (umma_gemm.cuh)
+
+// Layernorm + lrelu in the forward kernel's epilogue: `ln` is the OP_LN_FWD that follows the GEMM `o` in the plan
+// (Op::fuse == FUSE_LN_FWD).  Needs whole frames per M tile, whole rows per N tile and the dense row-major conv output
+// the Layernorm op reads; anything else runs the two ops as two kernels.
+// Used for inference passes: there the raw conv output is never stored and a whole pass per layer disappears (cfg3:
+// 11.26 -> 10.44 ms).  In training the raw output must be kept for the backward, the saving is one read per layer, and
+// the longer epilogue costs more than the separate Layernorm kernels did (measured: E1 0.121 -> 0.126 ms, E2 0.089 ->
+// 0.104, G1 0.146 -> 0.166, profiles/r2g_ops_per_step.txt) -- training keeps the two kernels.
+bool ln_epilogue_ok(const Ctx& c, const Op& o, const Op* ln, const RowTiling& rt, int n_tiles) {
+  const Plan& p = c.h->plan;
+  if (c.train && c.h->fuse_ln_train == 0) return false;
+  if (!ln || ln->kind != OP_LN_FWD || rt.Ra != 1 || n_tiles != 1) return false;
+  if (o.C.pred || o.C.split || o.C.off != 0 || o.C.rs != o.N || (o.C.fs % 4) || (o.N % 8) || o.N > 256) return false;
+  if (ln->in.space != SP_WS || o.C.ref.space != SP_WS || ln->in.buf != o.C.ref.buf) return false;
+  if (ln->L != o.A.R * o.N || (o.N % ln->Cn) || (ln->out_off % 8) || (ln->out_flen % 8)) return false;
+  if (ln->aout.space != SP_WS || !p.bufs[ln->aout.buf].split) return false;
+  return true;
+}
+
 struct TapGeom { bool ok; int sw, P, hr, BN, b_tile_al, stages; RowTiling rt; };
-TapGeom tap_geometry(const Op& o, long long frames) {
+TapGeom tap_geometry(const Op& o, long long frames, int reserve = 0) {
   TapGeom t; memset(&t, 0, sizeof t);
   const int C = o.tap_C, T = o.tap_T, s = o.tap_s;
   if (T <= 0 || !(C == 16 || C == 32 || C == 64) || o.N > 256 || o.A.R < 2 || o.A.rs != s * C || o.K > T * C || o.K <= (T - 1) * C) return t;   // (a last tap may be partly beyond K: its weights are TMA zero fill)
@@ -214,13 +236,23 @@ TapGeom tap_geometry(const Op& o, long long frames) {
   r.rows_tile = r.RbH * r.Ab * r.FB;
   r.frames = (int)frames; r.m_tiles = (int)(((frames + r.FB - 1) / r.FB) * r.TA);
   const int bres = T * 2 * t.b_tile_al, stage = t.P * 2 * 128 * t.sw;
-  t.stages = (225 * 1024 - 6144 - bres) / stage; if (t.stages > 8) t.stages = 8;
+  t.stages = (225 * 1024 - 6144 - reserve - bres) / stage; if (t.stages > 8) t.stages = 8;
   t.ok = t.stages >= 2;
   return t;
 }
 
-int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
+void fill_ln_epilogue(Ctx& c, const Op& ln, UmmaArgs& g) {
+  g.ln.on = 1; g.ln.store_c = c.train ? 1 : 0;               // inference never reads the raw conv output again
+  g.ln.aout = resolve(c, ln.aout); g.ln.mean = resolve(c, ln.r0); g.ln.rstd = resolve(c, ln.rstd);
+  g.ln.gamma = resolve(c, ln.gamma); g.ln.beta = resolve(c, ln.beta);
+  g.ln.Cn = ln.Cn; g.ln.L = ln.L; g.ln.out_flen = ln.out_flen; g.ln.out_off = ln.out_off;
+}
+
+int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg_in, const Op* ln, bool* fused) {
   npvc_handle* h = c.h; cudaStream_t st = c.st;
+  TapGeom tg = tg_in;
+  bool fuse_ln = ln_epilogue_ok(c, o, ln, tg.rt, 1);
+  if (fuse_ln) { const TapGeom t2 = tap_geometry(o, c.n, LN_EPI_SMEM); if (t2.ok) tg = t2; else fuse_ln = false; }
   const RowTiling& rt = tg.rt; const int BN = tg.BN, sw = tg.sw, C = o.tap_C;
   const void* a_base = resolve(c, o.A.ref);
   uint16_t* arena16 = reinterpret_cast<uint16_t*>(shared_ws(c) + h->plan.aw16_off);
@@ -260,12 +292,17 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg) {
   g.stages = tg.stages;
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
+  if (fuse_ln) { fill_ln_epilogue(c, *ln, g); if (fused) *fused = true; }
   if (!h->attr_fwd) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     h->attr_fwd = true;
   }
-  const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 4096;
+  const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 4096 + (fuse_ln ? LN_EPI_SMEM : 0);
   unsigned grid = (unsigned)(rt.m_tiles < h->sm_count ? rt.m_tiles : h->sm_count);
+  if (fuse_ln) {
+    if (!h->attr_fwd_ln) { CUDA_TRY(cudaFuncSetAttribute(umma_fwd_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); h->attr_fwd_ln = true; }
+    umma_fwd_ln_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  } else
   umma_fwd_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
@@ -332,12 +369,12 @@ int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, con
   return NPVC_OK;
 }
 
-int launch_umma(Ctx& c, const Op& o, int op_index) {
+int launch_umma(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fused = nullptr) {
   npvc_handle* h = c.h; cudaStream_t st = c.st;
   const long long frames = c.n;
   if (h->umma_tap) {
     const TapGeom tg = tap_geometry(o, frames);
-    if (tg.ok) return launch_umma_tap(c, o, op_index, tg);
+    if (tg.ok) return launch_umma_tap(c, o, op_index, tg, ln, fused);
   }
   int n_tiles = 1; const int BN = pick_bn(o.N, bn_cap(o), &n_tiles);
   const RowTiling rt = make_tiling(o.A.R, frames, 128);
@@ -377,17 +414,23 @@ int launch_umma(Ctx& c, const Op& o, int op_index) {
   const int stage_bytes = 2 * 128 * sw + 2 * BN * sw;
   g.acc_sets = 512 / (2 * BN) >= 4 ? 4 : (512 / (2 * BN) >= 2 ? 2 : 1);   // accumulator ring in TMEM: the epilogue of tile i overlaps the mainloops of the next tiles
   int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
-  int stages = (225 * 1024 - 6144) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
+  bool fuse_ln = ln_epilogue_ok(c, o, ln, rt, n_tiles) && (225 * 1024 - 6144 - LN_EPI_SMEM) / stage_bytes >= 2;
+  int stages = (225 * 1024 - 6144 - (fuse_ln ? LN_EPI_SMEM : 0)) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
   g.stages = stages;
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
+  if (fuse_ln) { fill_ln_epilogue(c, *ln, g); if (fused) *fused = true; }
   if (!h->attr_fwd) {
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     h->attr_fwd = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 4096;   // + bias_s[256]
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 4096 + (fuse_ln ? LN_EPI_SMEM : 0);   // + bias_s[4][256]
   long long total = rt.m_tiles * n_tiles;
   unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
+  if (fuse_ln) {
+    if (!h->attr_fwd_ln) { CUDA_TRY(cudaFuncSetAttribute(umma_fwd_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); h->attr_fwd_ln = true; }
+    umma_fwd_ln_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  } else
   umma_fwd_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
@@ -493,11 +536,12 @@ int launch_e0_fwd(Ctx& c, const Op& o, const Op& nx) {      // o: conv (OP_GEMM 
   if (!g.x) return fail(NPVC_ERR_ARG, "frames (x) required");
   g.xp = e0_row_floats(g.Ho, g.s, g.pl, g.Hi);
   const int G = ln_group(nx.L, nx.Cn, nx.out_off, nx.out_flen);
-  const long long fbs = (c.n + 256 / G - 1) / (256 / G);
-  long long blocks = (long long)h->sm_count * 6; if (blocks > fbs) blocks = fbs;
-  const size_t sm = ((size_t)(E0_KT + 3) * g.Co + (size_t)(256 / G) * g.xp) * sizeof(float);
+  const int bt = E0_BLOCK(G), fpb = bt / G;
+  const long long fbs = (c.n + fpb - 1) / fpb;
+  long long blocks = (long long)h->sm_count * 2 * (768 / bt); if (blocks > fbs) blocks = fbs;
+  const size_t sm = ((size_t)(E0_KT + 3) * g.Co + (size_t)fpb * g.xp) * sizeof(float);
   const bool v4 = nx.L / 8 > 3 * G;                       // units of 8 elements per thread: 3 or 4
-#define NPVC_E0_FWD(GG) do { if (v4) e0_fwd_kernel<GG, 4><<<(unsigned)blocks, 256, sm, c.st>>>(g); else e0_fwd_kernel<GG, 3><<<(unsigned)blocks, 256, sm, c.st>>>(g); } while (0)
+#define NPVC_E0_FWD(GG) do { if (v4) e0_fwd_kernel<GG, 4><<<(unsigned)blocks, bt, sm, c.st>>>(g); else e0_fwd_kernel<GG, 3><<<(unsigned)blocks, bt, sm, c.st>>>(g); } while (0)
   if (G == 32) NPVC_E0_FWD(32); else if (G == 64) NPVC_E0_FWD(64); else if (G == 128) NPVC_E0_FWD(128); else NPVC_E0_FWD(256);
 #undef NPVC_E0_FWD
   h->launches++;
@@ -514,11 +558,12 @@ int launch_e0_bwd(Ctx& c, const Op& o, const Op& nx) {      // o: OP_LN_BWD of t
   if (nx.ldb != nx.N) return fail(NPVC_ERR_ARG, "fused first-layer backward: packed weight gradient must be dense");
   g.xp = e0_row_floats(g.Ho, g.s, g.pl, g.Hi);
   const int G = e0_bwd_group(o.L, o.Cn);
-  const long long fbs = (c.n + 256 / G - 1) / (256 / G);
-  long long blocks = (long long)h->sm_count * 2; if (blocks > fbs) blocks = fbs;
-  const size_t sm = ((size_t)(E0_KT + 5) * g.Co + (size_t)(256 / G) * g.xp) * sizeof(float);
+  const int bt = E0_BLOCK(G), fpb = bt / G;
+  const long long fbs = (c.n + fpb - 1) / fpb;
+  long long blocks = (long long)h->sm_count * (512 / bt); if (blocks > fbs) blocks = fbs;
+  const size_t sm = ((size_t)(E0_KT + 5) * g.Co + (size_t)fpb * g.xp) * sizeof(float);
   const bool v4 = o.L / 4 > 3 * G;                        // units of 4 elements per thread: 3 or 4
-#define NPVC_E0_BWD(GG) do { if (v4) e0_bwd_kernel<GG, 4><<<(unsigned)blocks, 256, sm, c.st>>>(g); else e0_bwd_kernel<GG, 3><<<(unsigned)blocks, 256, sm, c.st>>>(g); } while (0)
+#define NPVC_E0_BWD(GG) do { if (v4) e0_bwd_kernel<GG, 4><<<(unsigned)blocks, bt, sm, c.st>>>(g); else e0_bwd_kernel<GG, 3><<<(unsigned)blocks, bt, sm, c.st>>>(g); } while (0)
   if (G == 32) NPVC_E0_BWD(32); else if (G == 64) NPVC_E0_BWD(64); else if (G == 128) NPVC_E0_BWD(128); else NPVC_E0_BWD(256);
 #undef NPVC_E0_BWD
   h->launches++;
@@ -531,7 +576,8 @@ bool umma_allowed(const npvc_handle* h, const Op& o) {
   return ("," + h->umma_allow + ",").find("," + o.name + ",") != std::string::npos;
 }
 
-int run_op(Ctx& c, const Op& o, int op_index) {
+// ln / fused: the OP_LN_FWD that follows a GEMM marked FUSE_LN_FWD; *fused = true when the launch covered both ops
+int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fused = nullptr) {
   npvc_handle* h = c.h; const Plan& p = h->plan; cudaStream_t st = c.st;
   switch (o.kind) {
     case OP_PACK: {
@@ -577,7 +623,7 @@ int run_op(Ctx& c, const Op& o, int op_index) {
       // few-tap, few-channel layers over millions of rows: through the overlapping-window boxes of the generic tensor
       // kernel they cost more than the thread-per-row FFMA kernel (measured) -- tensor cores only in tap mode
       const bool tensor_ok = umma_allowed(h, o) && (!row_shaped || (h->umma_tap && tap_geometry(o, c.n).ok));
-      if (tensor_ok) { int rc = launch_umma(c, o, op_index); if (rc) return rc; break; }
+      if (tensor_ok) { int rc = launch_umma(c, o, op_index, ln, fused); if (rc) return rc; break; }
       if (o.rows_fixed && o.rows_fixed <= 16 && !g.bias0 && o.C.ref.space == SP_GRAD && !g.A.pred && g.A.R == 1 && g.C.R == 1 && o.K >= 256) {
         // few-row GEMM accumulated into the (zero-initialised) gradient buffer
         const int kchunk = 32, ks = (o.K + kchunk - 1) / kchunk;
@@ -740,8 +786,12 @@ int run_phase(Ctx& c, int phase) {
       rc = launch_e0_fwd(c, o, ops[i + 1]); i++;
     } else if (o.fuse == FUSE_E0_BWD) {
       rc = launch_e0_bwd(c, o, ops[i + 1]); i++;
+    } else if (o.fuse == FUSE_LN_FWD) {              // Layernorm in the GEMM's epilogue when the tiling allows it
+      bool fused = false;
+      rc = run_op(c, o, (int)i, &ops[i + 1], &fused);
+      if (fused) i++;
     } else rc = run_op(c, o, (int)i);
-    if (rc == NPVC_OK && o.fuse) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = fail(NPVC_ERR_CUDA, "launch " + o.name + " (fused): " + cudaGetErrorString(e)); }
+    if (rc == NPVC_OK && (o.fuse == FUSE_E0_FWD || o.fuse == FUSE_E0_BWD)) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = fail(NPVC_ERR_CUDA, "launch " + o.name + " (fused): " + cudaGetErrorString(e)); }
     c.st = main_st;
     if (h->profiling) { cudaEventRecord(ev.b, c.st); h->events.push_back(ev); }
     if (rc) return rc;
@@ -824,6 +874,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
   if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
+  if (const char* fl = getenv("NPVC_FUSE_LN_TRAIN")) h->fuse_ln_train = atoi(fl);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);
   if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty() && !h->umma_pair) h->umma_pair = 1; }

@@ -35,6 +35,8 @@ struct E0BwdArgs {
 };
 
 constexpr int E0_KT = 8;        // taps per position (weights beyond k are zero)
+// threads per block: a frame's G threads (>= 128) are a block of their own, so the per-frame barriers span nothing else
+#define E0_BLOCK(G) ((G) >= 128 ? (G) : 128)
 __host__ __device__ inline int e0_row_floats(int Ho, int s, int pl, int Hi) {
   int need = s * (Ho - 1) + E0_KT; if (need < pl + Hi) need = pl + Hi;
   return (need + 3) / 4 * 4;
@@ -47,8 +49,8 @@ __device__ __forceinline__ void e0_stage_x(float* xs, const float* xp, bool fok,
 
 // G threads per frame, V units of 8 consecutive channels per thread (L <= 8 G V)
 template <int G, int V>
-__global__ void __launch_bounds__(256, 3) e0_fwd_kernel(E0FwdArgs g) {
-  constexpr int FPB = 256 / G;
+__global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(E0FwdArgs g) {
+  constexpr int FPB = E0_BLOCK(G) / G;
   extern __shared__ __align__(16) float e0sm[];      // [KT][Co] weights | bias | gamma | beta | [FPB][xp] staged frames
   __shared__ float red[8];
   const int Co = g.Co, XP = g.xp;
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(256, 3) e0_fwd_kernel(E0FwdArgs g) {
 
 // G threads per frame, V units of 4 consecutive channels per thread (L <= 4 G V)
 template <int G, int V>
-__global__ void __launch_bounds__(256, 2) e0_bwd_kernel(E0BwdArgs g) {
-  constexpr int FPB = 256 / G;
+__global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(E0BwdArgs g) {
+  constexpr int FPB = E0_BLOCK(G) / G;
   extern __shared__ __align__(16) float e0sm[];      // [3 Co] dgamma | dbeta | dbias sums, [KT Co] dW sums, gamma, beta, [FPB][xp] frames
   __shared__ float red[16];
   const int Co = g.Co, XP = g.xp;

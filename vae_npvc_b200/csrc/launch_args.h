@@ -23,6 +23,19 @@ struct RowTiling {
   int frames, m_tiles;        // m_tiles = ceil(frames / FB) * TA
 };
 
+// Layernorm + lrelu fused into the forward kernel's epilogue (umma_gemm.cuh): applies when an M tile holds whole
+// frames and one N tile holds whole rows.  The epilogue then owns every conv output of its frames: it forms the
+// per-frame moments, stores the raw conv output only when the backward will need it, and writes the activation
+// as zero-padded bf16 hi / lo planes -- the separate Layernorm pass (a read and a launch per layer) disappears.
+struct LnEpi {
+  int on;                // 0: plain GEMM epilogue
+  int store_c;           // training: keep the raw conv output (C view) for the Layernorm backward
+  float* aout;           // activation planes [frames][2][out_flen] bf16 (hi | lo)
+  float* mean; float* rstd;
+  const float* gamma; const float* beta;   // per channel; channel of column n = n % Cn
+  int Cn, L, out_flen, out_off;
+};
+
 struct UmmaArgs {
   int K, N;              // logical GEMM sizes (wgrad: dB is [K, N])
   int BN;                // N tile
@@ -40,6 +53,7 @@ struct UmmaArgs {
   int b_tile_al;         // tap mode: bytes of one resident weight tile (BN * sw rounded up to 1024)
   DView C;
   const float* bias0; const float* bias1; const float* bias2; int bias_mod;
+  LnEpi ln;
   // (W)
   int d_sw;              // swizzle span (bytes) of the dC boxes: 128 / 64 / 32 -> 64 / 32 / 16 columns per box
   int rows_al;           // rows_tile rounded up to 16 (MMA K step)

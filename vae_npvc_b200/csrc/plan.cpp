@@ -419,6 +419,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
     // Layernorm mapping applies
     const bool fuse_fwd = fuse && e == 0 && l.Ci == 1 && l.k <= 8 && ln_group(l.Ho * l.Co, l.Co, ae_off[e], ae_flen[e]) > 0;
     if (fuse_fwd) p.ops.back().fuse = FUSE_E0_FWD;
+    else if (fuse) p.ops.back().fuse = FUSE_LN_FWD;
     snprintf(nm, sizeof nm, "ln_e%d", e);
     Op& q = B.op(OP_LN_FWD, PH_ENC, nm);
     q.in = B.ws(b_ce[e]); q.r0 = B.ws(b_me[e]); q.aout = B.ws(b_ae[e]); q.rstd = B.ws(b_re[e]);
@@ -459,6 +460,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
       o.tap_T = l.wn; o.tap_C = l.Cip; o.tap_s = 1;
       o.C = B.view(B.ws(b_cg[g]), l.Hi, l.Ho * l.Co, l.s * l.Co, 0, l.Ho * l.Co);
       o.bias[0] = B.th(poff(P_gb[g])); o.bias_mod = l.Co;
+      if (fuse) p.ops.back().fuse = FUSE_LN_FWD;
       snprintf(nm, sizeof nm, "ln_g%d", g);
       Op& q = B.op(OP_LN_FWD, PH_DEC, nm);
       q.in = B.ws(b_cg[g]); q.r0 = B.ws(b_mg[g]); q.aout = B.ws(b_ag[g]); q.rstd = B.ws(b_rg[g]);

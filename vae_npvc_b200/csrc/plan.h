@@ -33,7 +33,9 @@ enum OpKind {
 //   FUSE_E0_FWD  conv of the first encoder layer (one input channel, <= 8 taps) + its Layernorm / lrelu
 //   FUSE_E0_BWD  Layernorm backward of the first encoder layer + its weight gradient: the gradient w.r.t. the
 //                conv output is consumed in registers, its buffer is never materialised (Buf::elide)
-enum Fuse { FUSE_NONE = 0, FUSE_E0_FWD = 1, FUSE_E0_BWD = 2 };
+//   FUSE_LN_FWD  a conv / transposed-conv GEMM + the Layernorm / lrelu that follows it: done in the GEMM kernel's
+//                epilogue when a tile holds whole frames (decided per launch; otherwise the two ops run separately)
+enum Fuse { FUSE_NONE = 0, FUSE_E0_FWD = 1, FUSE_E0_BWD = 2, FUSE_LN_FWD = 3 };
 
 struct Ref {
   int space = SP_NONE;
