@@ -21,8 +21,10 @@
  *     tf.trainable_variables() creation order, each in its TF layout (npvc_param_table()).
  *     Gradients / Adam moments use the same flat layout (one NCCL all-reduce bucket).
  *   - frames are frame-major: x[n,513] == NCHW [n,1,513,1] (analyzer.py:116-122).
- *   - labels are not range-checked on the device: a label outside [0, y_dim) selects no embedding row, i.e.
- *     contributes a zero speaker term (what tf.nn.embedding_lookup returns on a GPU), never an out-of-bounds access.
+ *   - labels must lie in [0, y_dim); they are not range-checked on the device.  A label outside the range never causes
+ *     an out-of-bounds access, but it selects no row of the per-speaker table, which carries the speaker term
+ *     emb[y].W_y AND the three merge biases (model/vae.py:51-61 folded per speaker): such a frame is decoded without
+ *     them, unlike tf.nn.embedding_lookup on a GPU (zero embedding row, biases still added).
  */
 #ifndef NPVC_B200_H
 #define NPVC_B200_H

@@ -47,7 +47,14 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
         dist.init_process_group('nccl')
 
-    dirs = validate_log_dirs(args)
+    # the (timestamped) logdir is chosen once, on rank 0, and shared: every rank then names the same directory for
+    # training.log / checkpoints / the architecture copy, and a resume finds one history (only rank 0 writes)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    dirs = validate_log_dirs(args) if (not distributed or dist.get_rank() == 0) else None
+    if distributed:
+        box = [dirs]
+        dist.broadcast_object_list(box, src=0, device=torch.device('cuda', torch.cuda.current_device()))
+        dirs = box[0]
     os.makedirs(dirs['logdir'], exist_ok=True)
     with open(args.architecture) as f:
         arch = json.load(f)

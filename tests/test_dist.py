@@ -62,3 +62,56 @@ def test_two_rank_dp_equals_single_process():
         assert np.abs(th1 - th_ref).max() <= 1e-9
         assert abs(losses[0] - ref["G"]) <= 1e-9 * abs(ref["G"])
     assert np.array_equal(out[0][0], out[1][0])                          # replicas stay bit-identical
+
+
+class _Machine(object):
+    """What VAETrainer touches of a machine (theta, variables(), the device step state), on CPU tensors."""
+
+    def __init__(self, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.theta = torch.randn(10, generator=g)
+        self.state = torch.zeros(4, dtype=torch.int64)
+
+    def variables(self):
+        return {"Encoder/dense/kernel": self.theta[:6].view(2, 3), "Encoder/dense/bias": self.theta[6:]}
+
+
+def _restore_worker(rank, world, port, root, out):
+    """Rank 0 owns the only logdir that holds checkpoints; rank 1 is given a directory that does not exist (no shared
+    filesystem, per-rank timestamped logdirs).  After restore() both replicas must hold rank 0's variables, Adam
+    slots and step."""
+    import importlib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tv = importlib.import_module("trainer.vae")
+    arch = {"training": {"lr": 1e-4, "beta1": 0.5, "beta2": 0.999, "max_iter": 1}}
+    logdir = os.path.join(root, "train") if rank == 0 else os.path.join(root, "rank1-does-not-exist")
+    m = _Machine(10 + rank)
+    t = tv.VAETrainer({"G": 0.0}, arch, None, {"logdir": None, "restore_from": logdir}); t.machine = m
+    step = t.restore()
+    st = t._state
+    out[rank] = (step, t.global_step, m.theta.clone().numpy(), st["m"].clone().numpy(), st["v"].clone().numpy(), m.state.tolist())
+    # a second logdir with nothing in it: every rank must agree that there is nothing to restore
+    t2 = tv.VAETrainer({"G": 0.0}, arch, None, {"logdir": None, "restore_from": os.path.join(root, "empty-%d" % rank)}); t2.machine = _Machine(3)
+    out["none%d" % rank] = t2.restore()
+    dist.destroy_process_group()
+
+
+def test_restore_reads_on_rank0_and_broadcasts(tmp_path):
+    import importlib
+    tv = importlib.import_module("trainer.vae")
+    arch = {"training": {"lr": 1e-4, "beta1": 0.5, "beta2": 0.999, "max_iter": 1}}
+    src = _Machine(1)
+    t0 = tv.VAETrainer({"G": 0.0}, arch, None, {"logdir": str(tmp_path / "train")}); t0.machine = src
+    st = t0._ensure_state(src); st["m"].fill_(0.25); st["v"].fill_(0.5)
+    t0.global_step = 77; path = t0.save()
+    assert path.endswith("model.ckpt-77") and not [f for f in os.listdir(tmp_path / "train") if ".tmp." in f]     # atomic rename left no temp file
+    t_fresh = tv.VAETrainer({"G": 0.0}, arch, None, {"logdir": str(tmp_path / "fresh")}); t_fresh.machine = _Machine(5)
+    assert t_fresh.save().endswith("model.ckpt-0")                  # a trainer that never stepped can still save (zero Adam slots)
+    mgr = mp.Manager(); out = mgr.dict()
+    mp.spawn(_restore_worker, args=(2, _free_port(), str(tmp_path), out), nprocs=2, join=True)
+    for r in range(2):
+        step, gs, theta, m, v, state = out[r]
+        assert step == 77 and gs == 77 and state[1:3] == [77, 77]
+        assert np.array_equal(theta, src.theta.numpy()) and np.all(m == 0.25) and np.all(v == 0.5)
+        assert out["none%d" % r] is None

@@ -286,6 +286,32 @@ def test_gradients_stay_finite_over_many_passes(eng, arch):
         assert bool(torch.isfinite(grad).all()) and bool(torch.isfinite(out["losses"]).all())
 
 
+@pytest.mark.parametrize("which", ["vcc2016"] + sorted(__import__("conftest").ALT_ARCHS))
+def test_poisoned_workspace_matches_oracle(arch, monkeypatch, which):
+    """NPVC_DEBUG_POISON=1 fills the whole workspace with 0xFF bytes (NaN bit patterns in fp32 and bf16) before every
+    pass: any operand tile, halo row or pad that the pass reads without having written it itself poisons the outputs
+    deterministically (the NaN * 0 rule of DESIGN.md, not left to whatever bits torch.empty returned)."""
+    import copy
+    from conftest import ALT_ARCHS
+    from vae_npvc_b200.engine import Engine
+    a = arch if which == "vcc2016" else copy.deepcopy(ALT_ARCHS[which])
+    e2 = Engine(a, "cuda:0")
+    monkeypatch.setenv("NPVC_DEBUG_POISON", "1")
+    for n in ((1, 37, 300) if which == "vcc2016" else (29,)):
+        _check_against_oracle(e2, a, n)
+    if which == "vcc2016":                                   # benchmark size: finite everywhere (routing of large batches)
+        n = 16384
+        g = torch.Generator(device="cpu").manual_seed(21)
+        x = (torch.rand(n, 513, generator=g) * 2 - 1).cuda(); y = torch.randint(0, 10, (n,), generator=g).cuda()
+        eps = torch.randn(n, 128, generator=g).cuda()
+        theta = e2.init_theta(0, 0.1); grad = torch.empty_like(theta)
+        out = e2.loss_fwd_bwd(theta, x, y, eps, grad=grad)
+        assert all(bool(torch.isfinite(out[k]).all()) for k in ("z", "mu", "lv", "xh", "losses")) and bool(torch.isfinite(grad).all())
+        mu, lv = e2.encode(theta, x[:5000].contiguous())     # inference layout + Layernorm epilogue
+        xh = e2.decode(theta, mu, y[:5000].contiguous())
+        assert bool(torch.isfinite(mu).all()) and bool(torch.isfinite(xh).all())
+
+
 def test_tanhize_and_record_reader(eng):
     g = torch.Generator(device="cpu").manual_seed(3)
     xmin = torch.randn(513, generator=g) - 3; xmax = xmin + 1 + torch.rand(513, generator=g)

@@ -12,5 +12,8 @@ x = (torch.rand(n, 513, generator=g) * 2 - 1).cuda(); y = torch.randint(0, 10, (
 eps = torch.randn(n, 128, generator=g).cuda()
 theta = eng.init_theta(0, 0.1); grad = torch.empty_like(theta)
 out = eng.loss_fwd_bwd(theta, x, y, eps, grad=grad, outputs=False)
+if len(sys.argv) > 2 and sys.argv[2] == "adam":            # the whole training step: + TF-form Adam on the flat buffers
+    m = torch.zeros_like(theta); v = torch.zeros_like(theta)
+    eng.adam_step(theta, grad, m, v, 1, 1e-4, 0.5, 0.999)
 torch.cuda.synchronize()
 print(out["losses"].tolist())

@@ -179,14 +179,14 @@ class VAETrainer(object):
     def _restore_distributed(self, logdir, ckpt, machine, rank):
         """Data-parallel resume: rank 0 alone reads the file (ranks need no shared filesystem and cannot disagree on
         which checkpoint is the newest); the variables, both Adam slots and global_step are then broadcast."""
+        self.machine = machine
+        st = self._ensure_state(machine)             # every rank: its first call broadcasts rank 0's variables (a collective)
         step = self._restore_local(logdir, ckpt, machine) if rank == 0 else None
         dev = machine.theta.device
         flag = torch.tensor([-1 if step is None else int(step)], dtype=torch.int64, device=dev)
         dist.broadcast(flag, src=0)
         if int(flag.item()) < 0:
             return None
-        self.machine = machine
-        st = self._ensure_state(machine)
         for t in (machine.theta, st['m'], st['v']):
             dist.broadcast(t, src=0)
         self.global_step = int(flag.item())

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <cuda.h>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges are emitted only with NPVC_NVTX=1 (ncu --nvtx --print-nvtx-rename kernel)
 
 #include <cstdlib>
 #include <map>
@@ -55,6 +56,7 @@ struct npvc_handle {
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int umma_groups = 4;               // NPVC_UMMA_GROUPS: epilogue groups of the forward kernel (1, 2 or 4; <= accumulator sets)
   int umma_tap = 1;                  // NPVC_UMMA_TAP=0: conv-shaped layers through the overlapping-window boxes (A/B comparisons)
+  int nvtx = 0;                      // NPVC_NVTX=1: an NVTX push / pop range named after the plan op around every launch
   bool profiling = false;
   struct Ev { int op; cudaEvent_t a, b; long long rows, frames; };
   std::vector<Ev> events;
@@ -781,6 +783,7 @@ int run_phase(Ctx& c, int phase) {
       cudaEventRecord(h->ev_fork, main_st); cudaStreamWaitEvent(h->side, h->ev_fork, 0);
       c.st = h->side; forked = true;
     }
+    if (h->nvtx) nvtxRangePushA(o.name.c_str());
     int rc;
     if (o.fuse == FUSE_E0_FWD) {                     // this op and the next one as one kernel (plan.h, Op::fuse)
       rc = launch_e0_fwd(c, o, ops[i + 1]); i++;
@@ -792,6 +795,7 @@ int run_phase(Ctx& c, int phase) {
       if (fused) i++;
     } else rc = run_op(c, o, (int)i);
     if (rc == NPVC_OK && (o.fuse == FUSE_E0_FWD || o.fuse == FUSE_E0_BWD)) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = fail(NPVC_ERR_CUDA, "launch " + o.name + " (fused): " + cudaGetErrorString(e)); }
+    if (h->nvtx) nvtxRangePop();
     c.st = main_st;
     if (h->profiling) { cudaEventRecord(ev.b, c.st); h->events.push_back(ev); }
     if (rc) return rc;
@@ -874,6 +878,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
   if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
+  if (const char* nv = getenv("NPVC_NVTX")) h->nvtx = atoi(nv);
   if (const char* fl = getenv("NPVC_FUSE_LN_TRAIN")) h->fuse_ln_train = atoi(fl);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);

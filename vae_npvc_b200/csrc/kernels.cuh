@@ -1011,8 +1011,16 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_bulk_kernel(LnBwdArgs g) {
       pd[0] = make_float4(d[0], d[1], d[2], d[3]); pd[1] = make_float4(d[4], d[5], d[6], d[7]);
       ph[0] = make_float4(h[0], h[1], h[2], h[3]); ph[1] = make_float4(h[4], h[5], h[6], h[7]);
     }
-    s1 = block_sum(s1, red) * invL;
-    s2 = block_sum(s2, red) * invL;
+    {                                                  // both frame sums behind ONE barrier (partials double-buffered by frame parity)
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      float* rp = red + (k & 1) * 16;
+      if ((threadIdx.x & 31) == 0) { rp[2 * (threadIdx.x >> 5)] = s1; rp[2 * (threadIdx.x >> 5) + 1] = s2; }
+      __syncthreads();
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { s1 += rp[2 * w]; s2 += rp[2 * w + 1]; }
+      s1 *= invL; s2 *= invL;
+    }
     // pass 2: dc = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) -> padded output frame
     for (int u = threadIdx.x; u < L8; u += blockDim.x) {
       float d[8], h[8], o[8];

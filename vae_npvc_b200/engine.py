@@ -105,6 +105,11 @@ class Engine:
         _lib.check(self.lib.npvc_pack_weights(self.handle.h, _ptr(_f32c(theta, "theta")), ws.data_ptr(), ws.numel(), _stream()))
         self._packed_for = (theta.data_ptr(), theta._version, ws.data_ptr())
 
+    def _poison(self, ws):
+        """NPVC_DEBUG_POISON=1 (tests / bring-up): every byte a pass does not write itself reads as a NaN pattern."""
+        if os.environ.get("NPVC_DEBUG_POISON"):
+            ws.fill_(0xFF); self._packed_for = None
+
     def _ensure_packed(self, theta, ws):
         if self._packed_for != (theta.data_ptr(), theta._version, ws.data_ptr()):
             self.pack(theta, ws)
@@ -116,6 +121,7 @@ class Engine:
         x = _f32c(x, "x").view(-1, self.in_h)
         n = x.shape[0]
         ws = self.workspace(n, False)
+        self._poison(ws)
         self._ensure_packed(theta, ws)
         mu = torch.empty(n, self.z_dim, dtype=torch.float32, device=self.device)
         lv = torch.empty_like(mu)
@@ -136,6 +142,7 @@ class Engine:
         if y.dtype != torch.int64 or not y.is_cuda or not y.is_contiguous() or y.numel() != n:
             raise ValueError("y must be a contiguous int64 CUDA tensor of n labels")
         ws = self.workspace(n, False)
+        self._poison(ws)
         self._ensure_packed(theta, ws)
         xh = torch.empty(n, self.in_h, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.npvc_decode(self.handle.h, _ptr(theta), _ptr(z), _ptr(y), n, _ptr(xh), ws.data_ptr(), ws.numel(), _stream()))
@@ -173,8 +180,7 @@ class Engine:
             if eps.shape != (n, self.z_dim):
                 raise ValueError("eps must be [n, z_dim]")
         ws = self.workspace(n, True)
-        if os.environ.get("NPVC_DEBUG_POISON"):          # bring-up: every byte the pass does not write itself reads as NaN
-            ws.fill_(0xFF); self._packed_for = None
+        self._poison(ws)
         repack = self._packed_for != (theta.data_ptr(), theta._version, ws.data_ptr())
         out = {}
         if outputs:
