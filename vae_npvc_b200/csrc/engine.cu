@@ -11,6 +11,7 @@
 #include <nvtx3/nvToolsExt.h>      // header-only; ranges are emitted only with NPVC_NVTX=1 (ncu --nvtx --print-nvtx-rename kernel)
 
 #include <cstdlib>
+#include <utility>
 #include <map>
 
 #include "kernels.cuh"
@@ -69,6 +70,20 @@ static int fail(int code, const std::string& m) { g_err = m; return code; }
 
 namespace {
 
+// Every launch of the library goes through here: programmatic stream serialisation (PDL) lets the blocks of a kernel be
+// scheduled while the previous kernel of the stream drains; the kernels begin with griddepcontrol.wait (kernels.cuh,
+// pdl_prologue), so only launch latency and block scheduling overlap, never the work.  NPVC_PDL=0 switches it off.
+int g_pdl = 1;
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);       // (errors surface through cudaGetLastError at the call sites)
+}
+
 struct Ctx {
   npvc_handle* h; float* ws; int64_t chunk_cap; bool train;
   const float* theta; float* grad; const float* x; const int64_t* y; const float* eps;
@@ -108,8 +123,8 @@ bool view_vec_ok(const DView& d) {
 template <int BN>
 void launch_gemm_bn(const GemmArgs& g, bool scalar, cudaStream_t st) {
   dim3 grid((unsigned)((g.rows + 127) / 128), (unsigned)((g.N + BN - 1) / BN));
-  if (scalar) gemm_view_kernel<BN, true><<<grid, 256, 0, st>>>(g);
-  else gemm_view_kernel<BN, false><<<grid, 256, 0, st>>>(g);
+  if (scalar) launch_k(gemm_view_kernel<BN, true>, dim3(grid), dim3(256), 0, st, g);
+  else launch_k(gemm_view_kernel<BN, false>, dim3(grid), dim3(256), 0, st, g);
 }
 void launch_gemm(const GemmArgs& g, bool scalar, cudaStream_t st) {
   if (g.N >= 96) launch_gemm_bn<128>(g, scalar, st);
@@ -132,8 +147,8 @@ void launch_wgrad_t(WgradArgs g, bool scalar, int sms, cudaStream_t st) {
   splits = (g.rows + rps - 1) / rps;
   g.rows_per_split = rps;
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  if (scalar) wgrad_view_kernel<BTK, BTN, true><<<grid, 256, 0, st>>>(g);
-  else wgrad_view_kernel<BTK, BTN, false><<<grid, 256, 0, st>>>(g);
+  if (scalar) launch_k(wgrad_view_kernel<BTK, BTN, true>, dim3(grid), dim3(256), 0, st, g);
+  else launch_k(wgrad_view_kernel<BTK, BTN, false>, dim3(grid), dim3(256), 0, st, g);
 }
 template <int BTK>
 void launch_wgrad_k(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
@@ -303,9 +318,9 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg_in, con
   unsigned grid = (unsigned)(rt.m_tiles < h->sm_count ? rt.m_tiles : h->sm_count);
   if (fuse_ln) {
     if (!h->attr_fwd_ln) { CUDA_TRY(cudaFuncSetAttribute(umma_fwd_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); h->attr_fwd_ln = true; }
-    umma_fwd_ln_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+    launch_k(umma_fwd_ln_kernel, dim3(grid), dim3(64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups)), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   } else
-  umma_fwd_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  launch_k(umma_fwd_kernel, dim3(grid), dim3(64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups)), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -364,8 +379,9 @@ int launch_umma_pair(Ctx& c, const Op& o, int op_index, int BN, int n_tiles, con
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3((unsigned)(64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups)));
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchAttribute at[2]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_fwd_pair_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
   h->launches++; h->umma_launches++;
   return NPVC_OK;
@@ -431,9 +447,9 @@ int launch_umma(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool*
   unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
   if (fuse_ln) {
     if (!h->attr_fwd_ln) { CUDA_TRY(cudaFuncSetAttribute(umma_fwd_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); h->attr_fwd_ln = true; }
-    umma_fwd_ln_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+    launch_k(umma_fwd_ln_kernel, dim3(grid), dim3(64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups)), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   } else
-  umma_fwd_kernel<<<grid, 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups), smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  launch_k(umma_fwd_kernel, dim3(grid), dim3(64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups)), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -515,13 +531,14 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchAttribute at[2]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_wgrad_pair_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
     h->launches++; h->umma_launches++;
     return NPVC_OK;
   }
-  umma_wgrad_kernel<<<grid, 192, smem, st>>>(it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  launch_k(umma_wgrad_kernel, dim3(grid), dim3(192), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -543,7 +560,7 @@ int launch_e0_fwd(Ctx& c, const Op& o, const Op& nx) {      // o: conv (OP_GEMM 
   long long blocks = (long long)h->sm_count * 2 * (768 / bt); if (blocks > fbs) blocks = fbs;
   const size_t sm = ((size_t)(E0_KT + 3) * g.Co + (size_t)fpb * g.xp) * sizeof(float);
   const bool v4 = nx.L / 8 > 3 * G;                       // units of 8 elements per thread: 3 or 4
-#define NPVC_E0_FWD(GG) do { if (v4) e0_fwd_kernel<GG, 4><<<(unsigned)blocks, bt, sm, c.st>>>(g); else e0_fwd_kernel<GG, 3><<<(unsigned)blocks, bt, sm, c.st>>>(g); } while (0)
+#define NPVC_E0_FWD(GG) do { if (v4) launch_k(e0_fwd_kernel<GG, 4>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); else launch_k(e0_fwd_kernel<GG, 3>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); } while (0)
   if (G == 32) NPVC_E0_FWD(32); else if (G == 64) NPVC_E0_FWD(64); else if (G == 128) NPVC_E0_FWD(128); else NPVC_E0_FWD(256);
 #undef NPVC_E0_FWD
   h->launches++;
@@ -565,7 +582,7 @@ int launch_e0_bwd(Ctx& c, const Op& o, const Op& nx) {      // o: OP_LN_BWD of t
   long long blocks = (long long)h->sm_count * (512 / bt); if (blocks > fbs) blocks = fbs;
   const size_t sm = ((size_t)(E0_KT + 5) * g.Co + (size_t)fpb * g.xp) * sizeof(float);
   const bool v4 = o.L / 4 > 3 * G;                        // units of 4 elements per thread: 3 or 4
-#define NPVC_E0_BWD(GG) do { if (v4) e0_bwd_kernel<GG, 4><<<(unsigned)blocks, bt, sm, c.st>>>(g); else e0_bwd_kernel<GG, 3><<<(unsigned)blocks, bt, sm, c.st>>>(g); } while (0)
+#define NPVC_E0_BWD(GG) do { if (v4) launch_k(e0_bwd_kernel<GG, 4>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); else launch_k(e0_bwd_kernel<GG, 3>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); } while (0)
   if (G == 32) NPVC_E0_BWD(32); else if (G == 64) NPVC_E0_BWD(64); else if (G == 128) NPVC_E0_BWD(128); else NPVC_E0_BWD(256);
 #undef NPVC_E0_BWD
   h->launches++;
@@ -584,13 +601,13 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
   switch (o.kind) {
     case OP_PACK: {
       long long n = p.aw16_off;
-      pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.theta, h->d_pack_src, c.ws, n);
+      launch_k(pack_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, c.theta, h->d_pack_src, c.ws, n);
       h->launches++; break;
     }
     case OP_PACK16: {
       long long n = p.aw16_count;
       if (n > 0) {
-        pack16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.theta, c.ws, h->d_pack16_src, reinterpret_cast<uint16_t*>(c.ws + p.aw16_off), n);
+        launch_k(pack16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, c.theta, c.ws, h->d_pack16_src, reinterpret_cast<uint16_t*>(c.ws + p.aw16_off), n);
         h->launches++;
       }
       break;
@@ -599,7 +616,7 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
       if (!c.y) return fail(NPVC_ERR_ARG, "labels (y) required");
       long long n4 = c.n * ((o.i0 + o.i1) / 4);
       if (n4 > 0) {
-        zcat_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1),
+        launch_k(zcat_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, resolve(c, o.r0), reinterpret_cast<const long long*>(c.y), resolve(c, o.r1),
                                                                 o.i0, o.i1, c.n, p.bufs[o.r1.buf].split);
         h->launches++;
       }
@@ -608,10 +625,10 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
     case OP_UNPACK: {
       long long n = p.n_params;
       const float* adw = shared_ws(c) + p.buf_offset(p.buf_adw, c.chunk_cap, c.train);
-      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(adw, h->d_unpack_ptr, h->d_unpack_idx, c.grad, n);
+      launch_k(unpack_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, adw, h->d_unpack_ptr, h->d_unpack_idx, c.grad, n);
       h->launches++;
       if (h->n_heavy > 0) {
-        unpack_heavy_kernel<<<(unsigned)((h->n_heavy * 32LL + 255) / 256), 256, 0, st>>>(adw, h->d_unpack_ptr, h->d_unpack_idx, h->d_heavy, h->n_heavy, c.grad);
+        launch_k(unpack_heavy_kernel, dim3((unsigned)((h->n_heavy * 32LL + 255) / 256)), dim3(256), 0, st, adw, h->d_unpack_ptr, h->d_unpack_idx, h->d_heavy, h->n_heavy, c.grad);
         h->launches++;
       }
       break;
@@ -630,7 +647,7 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
         // few-row GEMM accumulated into the (zero-initialised) gradient buffer
         const int kchunk = 32, ks = (o.K + kchunk - 1) / kchunk;
         dim3 grid((unsigned)((o.N + 127) / 128), (unsigned)ks);
-        fewrows_gemm_kernel<<<grid, 128, (size_t)o.rows_fixed * kchunk * sizeof(float), st>>>(
+        launch_k(fewrows_gemm_kernel, dim3(grid), dim3(128), (size_t)o.rows_fixed * kchunk * sizeof(float), st, 
             g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, kchunk);
         h->launches++; break;
       }
@@ -640,11 +657,11 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
         const bool sc = !view_vec_ok(g.A) || (o.K % 4 != 0);
         const unsigned b1 = (unsigned)((g.rows + 255) / 256), b2 = (unsigned)((g.rows + 511) / 512);
         (void)b2;   // 2 rows / thread measured slower for the 48x24 / 56x16 shapes (170 registers)
-        if (sc && o.K <= 8 && o.N <= 16) rowgemm_kernel<8, 16, true, 2><<<b2, 256, 0, st>>>(rg);
-        else if (!sc && o.K <= 48 && o.N <= 24) rowgemm_kernel<48, 24, false, 1><<<b1, 256, 0, st>>>(rg);
-        else if (!sc && o.K <= 56 && o.N <= 16) rowgemm_kernel<56, 16, false, 1><<<b1, 256, 0, st>>>(rg);
-        else if (!sc) rowgemm_kernel<64, 32, false, 1><<<b1, 256, 0, st>>>(rg);
-        else rowgemm_kernel<64, 32, true, 1><<<b1, 256, 0, st>>>(rg);
+        if (sc && o.K <= 8 && o.N <= 16) launch_k(rowgemm_kernel<8, 16, true, 2>, dim3(b2), dim3(256), 0, st, rg);
+        else if (!sc && o.K <= 48 && o.N <= 24) launch_k(rowgemm_kernel<48, 24, false, 1>, dim3(b1), dim3(256), 0, st, rg);
+        else if (!sc && o.K <= 56 && o.N <= 16) launch_k(rowgemm_kernel<56, 16, false, 1>, dim3(b1), dim3(256), 0, st, rg);
+        else if (!sc) launch_k(rowgemm_kernel<64, 32, false, 1>, dim3(b1), dim3(256), 0, st, rg);
+        else launch_k(rowgemm_kernel<64, 32, true, 1>, dim3(b1), dim3(256), 0, st, rg);
         h->launches++; break;
       }
       launch_gemm(g, !view_vec_ok(g.A), st); h->launches++; break;
@@ -658,13 +675,13 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
       if (o.K <= 8 && o.N <= 16 && g.rows >= 4096) {
         const long long blocks = (long long)h->sm_count * 4;
         long long rpb = (g.rows + blocks - 1) / blocks; rpb = (rpb + 255) / 256 * 256;
-        wgrad_tiny_kernel<8, 16><<<(unsigned)((g.rows + rpb - 1) / rpb), 256, 0, st>>>(g, rpb);
+        launch_k(wgrad_tiny_kernel<8, 16>, dim3((unsigned)((g.rows + rpb - 1) / rpb)), dim3(256), 0, st, g, rpb);
         h->launches++; break;
       }
       if (o.K > 8 && o.K <= 48 && o.N <= 24 && o.K % 4 == 0 && o.N % 4 == 0 && view_vec_ok(g.A) && g.rows >= 4096 && !g.A.split && !g.D.split) {
         const long long blocks = (long long)h->sm_count * 8;
         long long rpb = (g.rows + blocks - 1) / blocks; rpb = (rpb + 63) / 64 * 64;
-        wgrad_small_kernel<48, 24><<<(unsigned)((g.rows + rpb - 1) / rpb), 192, 0, st>>>(g, rpb);
+        launch_k(wgrad_small_kernel<48, 24>, dim3((unsigned)((g.rows + rpb - 1) / rpb)), dim3(192), 0, st, g, rpb);
         h->launches++; break;
       }
       launch_wgrad(g, !view_vec_ok(g.A), h->sm_count, st); h->launches++; break;
@@ -678,11 +695,11 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
       if (G) {
         const long long fbs = (c.n + 256 / G - 1) / (256 / G);
         long long blocks = (long long)h->sm_count * 8; if (blocks > fbs) blocks = fbs;
-        if (G == 32) ln_fwd_reg_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(g);
-        else if (G == 64) ln_fwd_reg_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(g);
-        else if (G == 128) ln_fwd_reg_kernel<128><<<(unsigned)blocks, 256, 0, st>>>(g);
-        else ln_fwd_reg_kernel<256><<<(unsigned)blocks, 256, 0, st>>>(g);
-      } else ln_fwd_kernel<<<(unsigned)c.n, 256, (size_t)o.L * sizeof(float), st>>>(g);
+        if (G == 32) launch_k(ln_fwd_reg_kernel<32>, dim3((unsigned)blocks), dim3(256), 0, st, g);
+        else if (G == 64) launch_k(ln_fwd_reg_kernel<64>, dim3((unsigned)blocks), dim3(256), 0, st, g);
+        else if (G == 128) launch_k(ln_fwd_reg_kernel<128>, dim3((unsigned)blocks), dim3(256), 0, st, g);
+        else launch_k(ln_fwd_reg_kernel<256>, dim3((unsigned)blocks), dim3(256), 0, st, g);
+      } else launch_k(ln_fwd_kernel, dim3((unsigned)c.n), dim3(256), (size_t)o.L * sizeof(float), st, g);
       h->launches++; break;
     }
     case OP_LN_BWD: {
@@ -698,10 +715,10 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
         const long long fbs = (c.n + 256 / G - 1) / (256 / G);
         long long blocks = (long long)h->sm_count * 4; if (blocks > fbs) blocks = fbs;
         const size_t sm = (size_t)5 * o.Cn * sizeof(float);
-        if (G == 32) ln_bwd_reg_kernel<32><<<(unsigned)blocks, 256, sm, st>>>(g);
-        else if (G == 64) ln_bwd_reg_kernel<64><<<(unsigned)blocks, 256, sm, st>>>(g);
-        else if (G == 128) ln_bwd_reg_kernel<128><<<(unsigned)blocks, 256, sm, st>>>(g);
-        else ln_bwd_reg_kernel<256><<<(unsigned)blocks, 256, sm, st>>>(g);
+        if (G == 32) launch_k(ln_bwd_reg_kernel<32>, dim3((unsigned)blocks), dim3(256), sm, st, g);
+        else if (G == 64) launch_k(ln_bwd_reg_kernel<64>, dim3((unsigned)blocks), dim3(256), sm, st, g);
+        else if (G == 128) launch_k(ln_bwd_reg_kernel<128>, dim3((unsigned)blocks), dim3(256), sm, st, g);
+        else launch_k(ln_bwd_reg_kernel<256>, dim3((unsigned)blocks), dim3(256), sm, st, g);
       } else if (ln_group(o.L, o.Cn, o.out_off, o.out_flen) && 2048 % o.Cn == 0 && h->ln_bulk &&
                  (size_t)(4 * o.L + 5 * o.Cn) * sizeof(float) <= 100 * 1024) {
         // large frames: double-buffered bulk-async frame stream (3 blocks / SM at L = 4104)
@@ -709,36 +726,36 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
         if (!h->attr_ln_bulk) { CUDA_TRY(cudaFuncSetAttribute(ln_bwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); h->attr_ln_bulk = true; }
         int per_sm = (int)((220 * 1024) / (sm + 1024)); if (per_sm > 3) per_sm = 3; if (per_sm < 1) per_sm = 1;
         long long blocks = (long long)h->sm_count * per_sm; if (blocks > c.n) blocks = c.n;
-        ln_bwd_bulk_kernel<<<(unsigned)blocks, 256, sm, st>>>(g);
+        launch_k(ln_bwd_bulk_kernel, dim3((unsigned)blocks), dim3(256), sm, st, g);
       } else {
         long long blocks = (long long)h->sm_count * 8; if (blocks > c.n) blocks = c.n;
-        ln_bwd_kernel<<<(unsigned)blocks, 256, (size_t)(2 * o.L + 3 * o.Cn) * sizeof(float), st>>>(g);
+        launch_k(ln_bwd_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(2 * o.L + 3 * o.Cn) * sizeof(float), st, g);
       }
       h->launches++; break;
     }
     case OP_SAMPLE: {
       const int z = o.i0, fpb = 8;
       double* acc = reinterpret_cast<double*>(shared_ws(c) + p.buf_offset(p.buf_acc, c.chunk_cap, c.train));
-      sample_kl_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 2 * z, 0, st>>>(
+      launch_k(sample_kl_kernel, dim3((unsigned)((c.n + fpb - 1) / fpb)), dim3(2 * z), 0, st, 
           resolve(c, o.r0), c.eps, c.state, c.frame0, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), (c.eps || c.state) ? acc : nullptr, z, c.n, fpb);
       h->launches++; break;
     }
     case OP_SAMPLE_BWD: {
       const int z = o.i0, fpb = 16;
-      sample_bwd_kernel<<<(unsigned)((c.n + fpb - 1) / fpb), 2 * z, 0, st>>>(
+      launch_k(sample_bwd_kernel, dim3((unsigned)((c.n + fpb - 1) / fpb)), dim3(2 * z), 0, st, 
           resolve(c, o.r0), c.eps, c.state, c.frame0, resolve(c, o.r1), resolve(c, o.r2), resolve(c, o.r3), z, c.n, fpb, 1.0f / (float)c.n_total, p.bufs[o.r2.buf].split);
       h->launches++; break;
     }
     case OP_RECON: {
       double* acc = reinterpret_cast<double*>(shared_ws(c) + p.buf_offset(p.buf_acc, c.chunk_cap, c.train)) + 1;
       const int wpb = 8;
-      recon_kernel<<<(unsigned)((c.n + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+      launch_k(recon_kernel, dim3((unsigned)((c.n + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, 
           c.x, resolve(c, o.r1), c.grad ? resolve(c, o.r2) : nullptr, c.grad ? resolve(c, o.r3) : nullptr, acc,
           o.i0, o.i1, 1, c.n, 1.0f / (float)c.n_total, p.bufs[o.r2.buf].split);
       h->launches++; break;
     }
     case OP_COLSUM: {
-      colsum_kernel<<<(unsigned)((o.i0 + 255) / 256), 256, 0, st>>>(resolve(c, o.r0), resolve(c, o.r1), o.i0, o.i1);
+      launch_k(colsum_kernel, dim3((unsigned)((o.i0 + 255) / 256)), dim3(256), 0, st, resolve(c, o.r0), resolve(c, o.r1), o.i0, o.i1);
       h->launches++; break;
     }
     case OP_ZERO: {
@@ -878,6 +895,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
   if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
+  if (const char* pd = getenv("NPVC_PDL")) g_pdl = atoi(pd) ? 1 : 0;
   if (const char* nv = getenv("NPVC_NVTX")) h->nvtx = atoi(nv);
   if (const char* fl = getenv("NPVC_FUSE_LN_TRAIN")) h->fuse_ln_train = atoi(fl);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
@@ -1015,7 +1033,7 @@ int npvc_sample(npvc_handle* h, const float* d_mu, const float* d_lv, const floa
   int rc = ensure_tables(h); if (rc) return rc;
   long long tot = n * h->plan.arch.z_dim;
   if (tot > 0) {
-    sample_only_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_mu, d_lv, d_eps, d_z, tot);
+    launch_k(sample_only_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, d_mu, d_lv, d_eps, d_z, tot);
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -1075,7 +1093,7 @@ static int loss_core(npvc_handle* h, const float* d_theta, const float* d_x, con
     rc = run_phase(c, PH_FINAL); if (rc) return rc;
   }
   if (d_losses || d_state) {
-    finalize_losses_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(ws + p.buf_offset(p.buf_acc, cap, true)), d_losses, 1.0 / (double)n,
+    launch_k(finalize_losses_kernel, dim3(1), dim3(32), 0, st, reinterpret_cast<const double*>(ws + p.buf_offset(p.buf_acc, cap, true)), d_losses, 1.0 / (double)n,
                                              d_state, d_grad ? 1 : 0);
     h->launches++;
   }
@@ -1104,7 +1122,7 @@ int npvc_normal_draw(npvc_handle* h, const npvc_step_state* d_state, int64_t fra
   int rc = ensure_tables(h); if (rc) return rc;
   const int z = h->plan.arch.z_dim; const long long tot = n * z;
   if (tot > 0) {
-    philox_normal_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const StepState*>(d_state), frame_offset, d_eps, z, n);
+    launch_k(philox_normal_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const StepState*>(d_state), frame_offset, d_eps, z, n);
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -1116,7 +1134,7 @@ int npvc_adam_step(npvc_handle* h, float* d_theta, const float* d_grad, float* d
   if (!h || !d_theta || !d_grad || !d_m || !d_v || step < 1) return fail(NPVC_ERR_ARG, "bad argument");
   int rc = ensure_tables(h); if (rc) return rc;
   double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) / (1.0 - std::pow((double)beta1, (double)step));
-  adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_theta, d_grad, d_m, d_v, n_params, (float)lr_t, beta1, beta2, eps, grad_scale, nullptr);
+  launch_k(adam_kernel, dim3((unsigned)((n_params + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, d_theta, d_grad, d_m, d_v, n_params, (float)lr_t, beta1, beta2, eps, grad_scale, nullptr);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return NPVC_OK;
@@ -1126,7 +1144,7 @@ int npvc_adam_step_dev(npvc_handle* h, float* d_theta, const float* d_grad, floa
                        const npvc_step_state* d_state, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
   if (!h || !d_theta || !d_grad || !d_m || !d_v || !d_state) return fail(NPVC_ERR_ARG, "bad argument");
   int rc = ensure_tables(h); if (rc) return rc;
-  adam_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_theta, d_grad, d_m, d_v, n_params, lr, beta1, beta2, eps, grad_scale,
+  launch_k(adam_kernel, dim3((unsigned)((n_params + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, d_theta, d_grad, d_m, d_v, n_params, lr, beta1, beta2, eps, grad_scale,
                                                                                     reinterpret_cast<const StepState*>(d_state));
   h->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1137,7 +1155,7 @@ int npvc_tanhize_forward(npvc_handle* h, const float* d_x, const float* d_xmin, 
   if (!h || !d_x || !d_xmin || !d_xmax || !d_out) return fail(NPVC_ERR_ARG, "null argument");
   int rc = ensure_tables(h); if (rc) return rc;
   long long tot = n * dim;
-  if (tot > 0) { tanhize_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_xmin, d_xmax, d_out, n, dim); h->launches++; }
+  if (tot > 0) { launch_k(tanhize_fwd_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, d_x, d_xmin, d_xmax, d_out, n, dim); h->launches++; }
   CUDA_TRY(cudaGetLastError());
   return NPVC_OK;
 }
@@ -1145,7 +1163,7 @@ int npvc_tanhize_backward(npvc_handle* h, const float* d_x, const float* d_xmin,
   if (!h || !d_x || !d_xmin || !d_xmax || !d_out) return fail(NPVC_ERR_ARG, "null argument");
   int rc = ensure_tables(h); if (rc) return rc;
   long long tot = n * dim;
-  if (tot > 0) { tanhize_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_xmin, d_xmax, d_out, n, dim); h->launches++; }
+  if (tot > 0) { launch_k(tanhize_bwd_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, d_x, d_xmin, d_xmax, d_out, n, dim); h->launches++; }
   CUDA_TRY(cudaGetLastError());
   return NPVC_OK;
 }
@@ -1156,7 +1174,7 @@ int npvc_unpack_records(npvc_handle* h, const float* d_records, int64_t n, int32
   int rc = ensure_tables(h); if (rc) return rc;
   long long tot = n * sp_dim;
   if (tot > 0) {
-    unpack_records_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_records, n, rec_floats, sp_dim, d_xmin, d_xmax, d_x, reinterpret_cast<long long*>(d_y));
+    launch_k(unpack_records_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, d_records, n, rec_floats, sp_dim, d_xmin, d_xmax, d_x, reinterpret_cast<long long*>(d_y));
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());

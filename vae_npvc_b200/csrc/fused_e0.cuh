@@ -50,6 +50,7 @@ __device__ __forceinline__ void e0_stage_x(float* xs, const float* xp, bool fok,
 // G threads per frame, V units of 8 consecutive channels per thread (L <= 8 G V)
 template <int G, int V>
 __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(E0FwdArgs g) {
+  pdl_prologue();
   constexpr int FPB = E0_BLOCK(G) / G;
   extern __shared__ __align__(16) float e0sm[];      // [KT][Co] weights | bias | gamma | beta | [FPB][xp] staged frames
   __shared__ float red[8];
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(
 // G threads per frame, V units of 4 consecutive channels per thread (L <= 4 G V)
 template <int G, int V>
 __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(E0BwdArgs g) {
+  pdl_prologue();
   constexpr int FPB = E0_BLOCK(G) / G;
   extern __shared__ __align__(16) float e0sm[];      // [3 Co] dgamma | dbeta | dbias sums, [KT Co] dW sums, gamma, beta, [FPB][xp] frames
   __shared__ float red[16];

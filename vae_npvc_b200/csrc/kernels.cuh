@@ -49,6 +49,16 @@ __device__ __forceinline__ float view_ld1(const DView& v, long long f, int e) {
   return split_ld1(reinterpret_cast<const uint16_t*>(v.p) + f * 2 * v.fs + e, v.fs);
 }
 
+// Programmatic dependent launch: the engine launches every kernel with programmatic stream serialisation, so a kernel's
+// blocks may be scheduled while the previous kernel of the stream is still draining.  Every kernel therefore BEGINS with
+// griddepcontrol.wait (returns once the previous kernel has completed and its writes are visible: nothing of a kernel's
+// work overlaps its producer, only the launch latency and block scheduling do) and then lets its own successor start
+// the same way.  Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float lrelu_f(float x) { return fmaxf(x, 0.02f * x); }
 
 #define NPVC_LN_EPS 1e-5f
@@ -66,6 +76,7 @@ struct GemmArgs {
 
 template <int BN, bool ASCALAR>
 __global__ void __launch_bounds__(256) gemm_view_kernel(GemmArgs g) {
+  pdl_prologue();
   constexpr int BM = 128, BK = 16, TN = BN / 16, LDA = BM + 4;
   constexpr int NB4 = (4 * BN + 255) / 256;            // float4 B loads per thread
   __shared__ __align__(16) float As[2][BK][LDA];
@@ -236,6 +247,7 @@ struct WgradArgs {
 
 template <int BTK, int BTN, bool ASCALAR>
 __global__ void __launch_bounds__(256) wgrad_view_kernel(WgradArgs g) {
+  pdl_prologue();
   constexpr int BR = 16, TK = BTK / 16, TNN = BTN / 16;
   constexpr int NA4 = (BR * BTK / 4 + 255) / 256, ND4 = (BR * BTN / 4 + 255) / 256;
   __shared__ __align__(16) float As[2][BR][BTK];
@@ -373,6 +385,7 @@ struct RowGemmArgs {
 
 template <int KMAX, int NMAX, bool ASCALAR, int ROWS>
 __global__ void __launch_bounds__(256) rowgemm_kernel(RowGemmArgs g) {
+  pdl_prologue();
   // ROWS output rows per thread (rows r, r + 256, ... of the block's slab): every weight fetched
   // from shared memory feeds ROWS FMAs, which moves the kernel from LDS-issue-bound to FMA-bound
   __shared__ __align__(16) float Ws[KMAX * NMAX];
@@ -457,6 +470,7 @@ __global__ void __launch_bounds__(256) rowgemm_kernel(RowGemmArgs g) {
 // (the per-speaker embedding gradient: 10 x 1596 x 128).
 __global__ void __launch_bounds__(128) fewrows_gemm_kernel(const float* A, int lda, int R, int K, const float* B, int ldb, int N,
                                                            float* C, int ldc, int kchunk) {
+  pdl_prologue();
   extern __shared__ float As[];                    // [R][kchunk]
   const int k0 = blockIdx.y * kchunk;
   const int kn = min(kchunk, K - k0);
@@ -485,6 +499,7 @@ __global__ void __launch_bounds__(128) fewrows_gemm_kernel(const float* A, int l
 // =============================================================================================
 template <int KMAX, int NMAX>
 __global__ void __launch_bounds__(256) wgrad_tiny_kernel(WgradArgs g, long long rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][KMAX * NMAX];
   float acc[KMAX][NMAX];
 #pragma unroll
@@ -547,6 +562,7 @@ __global__ void __launch_bounds__(256) wgrad_tiny_kernel(WgradArgs g, long long 
 // =============================================================================================
 template <int KT, int NT>
 __global__ void __launch_bounds__(192) wgrad_small_kernel(WgradArgs g, long long rows_per_block) {
+  pdl_prologue();
   constexpr int RB = 64, TG = (KT / 6) * (NT / 4), SL = 4;
   static_assert(TG * SL == 192, "thread layout");
   __shared__ __align__(16) float As[RB][KT];
@@ -639,6 +655,7 @@ struct LnFwdArgs {
 };
 
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs g) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];     // L floats
   __shared__ float red[40];
   const long long f = blockIdx.x;
@@ -692,6 +709,7 @@ struct LnBwdArgs {
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
+  pdl_prologue();
   extern __shared__ __align__(16) float lsm[];    // [L] dxhat | [L] xhat | [3*Cn] channel sums
   __shared__ float red[40];
   float* sdx = lsm; float* sxh = lsm + g.L; float* chs = lsm + 2 * g.L;
@@ -820,6 +838,7 @@ __device__ __forceinline__ void zero_pads(float* base, long long f, int flen, in
 
 template <int G>
 __global__ void __launch_bounds__(256) ln_fwd_reg_kernel(LnFwdArgs g) {
+  pdl_prologue();
   constexpr int V = 4, FPB = 256 / G;
   __shared__ float red[8];
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
@@ -872,6 +891,7 @@ __global__ void __launch_bounds__(256) ln_fwd_reg_kernel(LnFwdArgs g) {
 
 template <int G>
 __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
+  pdl_prologue();
   constexpr int V = 4, FPB = 256 / G;
   extern __shared__ __align__(16) float chs[];   // [3 * Cn] channel sums: dgamma | dbeta | dbias, then [2 * Cn] gamma | beta
   __shared__ float red[16];
@@ -951,6 +971,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
 // dynamic smem: [2 stages][2][L] floats | [3 Cn] channel sums | [2 Cn] gamma, beta
 // =============================================================================================
 __global__ void __launch_bounds__(256, 3) ln_bwd_bulk_kernel(LnBwdArgs g) {
+  pdl_prologue();
   extern __shared__ __align__(16) float bsm[];
   __shared__ float red[40];
   __shared__ __align__(8) unsigned long long mbar[2];
@@ -1072,6 +1093,7 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
 // =============================================================================================
 __global__ void sample_kl_kernel(const float* hz, const float* eps, const StepState* st, long long frame0, float* mu, float* lv, float* zout,
                                  double* acc_kl, int z, long long frames, int frames_per_block) {
+  pdl_prologue();
   __shared__ float red[40];
   const int col = threadIdx.x;
   const long long f0 = (long long)blockIdx.x * frames_per_block;
@@ -1094,12 +1116,14 @@ __global__ void sample_kl_kernel(const float* hz, const float* eps, const StepSt
 }
 // the in-kernel draw alone (tests: statistics / reproducibility of the generator): out[n, z]
 __global__ void philox_normal_kernel(const StepState* st, long long frame0, float* out, int z, long long n) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n * z) out[i] = philox_normal(st->seed, (unsigned long long)st->draws, (unsigned long long)(frame0 + i / z), (uint32_t)(i % z));
 }
 
 // GaussianSampleLayer alone (util/layers.py:152-156)
 __global__ void sample_only_kernel(const float* mu, const float* lv, const float* eps, float* z, long long n) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) z[i] = fmaf(eps[i], sqrtf(expf(lv[i])), mu[i]);
 }
@@ -1107,6 +1131,7 @@ __global__ void sample_only_kernel(const float* mu, const float* lv, const float
 // dz, eps, (mu|lv) -> (dmu|dlv); column sums -> head-bias grads.  inv_n = 1 / (frames the means span)
 __global__ void sample_bwd_kernel(const float* dz, const float* eps, const StepState* st, long long frame0, const float* hz, float* dhz, float* dbh,
                                   int z, long long frames, int frames_per_block, float inv_n, int out_split) {
+  pdl_prologue();
   const int col = threadIdx.x;
   const long long f0 = (long long)blockIdx.x * frames_per_block;
   float cs = 0.f;
@@ -1135,6 +1160,7 @@ __global__ void sample_bwd_kernel(const float* dz, const float* eps, const StepS
 // =============================================================================================
 __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float* dbias, double* acc_logp,
                              int H, int ld, int Co, long long frames, float inv_n, int out_split) {
+  pdl_prologue();
   __shared__ float red[40];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long f = (long long)blockIdx.x * nw + w;
@@ -1163,6 +1189,7 @@ __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float*
 }
 
 __global__ void colsum_kernel(const float* in, float* out, int N, int rows) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   float s = 0.f;
@@ -1174,6 +1201,7 @@ __global__ void colsum_kernel(const float* in, float* out, int N, int rows) {
 // pack / unpack / adam / finalize / tanhize / records
 // =============================================================================================
 __global__ void pack_kernel(const float* theta, const int* src, float* arena, long long n) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const int s = src[i]; arena[i] = (s >= 0) ? theta[s] : 0.f; }
 }
@@ -1181,6 +1209,7 @@ __global__ void pack_kernel(const float* theta, const int* src, float* arena, lo
 // bf16 operand packs of the tensor path (plan.h): src = index | flags; bit 29: the source is the fp32 pack
 // arena[index] instead of theta[index]; bit 30: store bf16(v - bf16(v)) instead of bf16(v)
 __global__ void pack16_kernel(const float* theta, const float* arena, const int* src, uint16_t* arena16, long long n) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const int s = src[i];
@@ -1198,6 +1227,7 @@ __global__ void pack16_kernel(const float* theta, const float* arena, const int*
 // zs[f] = [z[f] (zd floats) | one-hot(y[f]) (yp floats)], fp32 or split planes (zd, yp multiples of 4):
 // the merge GEMM's A operand (model/vae.py:64-70,89-90 -- embedding lookup folded into the GEMM)
 __global__ void zcat_kernel(const float* z, const long long* y, float* out, int zd, int yp, long long frames, int out_split) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // float4 index
   const int W4 = (zd + yp) >> 2;
   if (i >= frames * W4) return;
@@ -1218,6 +1248,7 @@ __global__ void zcat_kernel(const float* z, const long long* y, float* out, int 
 // unpack_heavy_kernel (one warp per parameter).
 constexpr int UNPACK_HEAVY = 32;
 __global__ void unpack_kernel(const float* adw, const int* ptr, const int* idx, float* grad, long long n) {
+  pdl_prologue();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   int b = ptr[t], e = ptr[t + 1];
@@ -1227,6 +1258,7 @@ __global__ void unpack_kernel(const float* adw, const int* ptr, const int* idx, 
   grad[t] += s;
 }
 __global__ void unpack_heavy_kernel(const float* adw, const int* ptr, const int* idx, const int* heavy, int n_heavy, float* grad) {
+  pdl_prologue();
   const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (w >= n_heavy) return;
   const int t = heavy[w];
@@ -1244,6 +1276,7 @@ __global__ void unpack_heavy_kernel(const float* adw, const int* ptr, const int*
 // captured CUDA graph of the whole training step replays unchanged.  lr_t then carries the base rate lr.
 __global__ void adam_kernel(float* theta, const float* grad, float* m, float* v, long long n,
                             float lr_t, float b1, float b2, float eps, float gscale, const StepState* st) {
+  pdl_prologue();
   if (st) {
     __shared__ float s_lr;
     if (threadIdx.x == 0) {
@@ -1265,6 +1298,7 @@ __global__ void adam_kernel(float* theta, const float* grad, float* m, float* v,
 // losses = {G, D_KL, logP}; st != nullptr: the pass counter of the in-kernel sampler advances, and -- after a pass
 // that produced a gradient -- the step counter the device-side Adam reads
 __global__ void finalize_losses_kernel(const double* acc, float* losses, double inv_n, StepState* st, int had_grad) {
+  pdl_prologue();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double kl = acc[0] * inv_n, lp = acc[1] * inv_n;
     if (losses) { losses[0] = (float)(-lp + kl); losses[1] = (float)kl; losses[2] = (float)lp; }
@@ -1273,6 +1307,7 @@ __global__ void finalize_losses_kernel(const double* acc, float* losses, double 
 }
 
 __global__ void tanhize_fwd_kernel(const float* x, const float* xmin, const float* xmax, float* out, long long n, int dim) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * dim) return;
   int d = (int)(i % dim);
@@ -1280,6 +1315,7 @@ __global__ void tanhize_fwd_kernel(const float* x, const float* xmin, const floa
   out[i] = fminf(fmaxf(t, 0.f), 1.f) * 2.f - 1.f;
 }
 __global__ void tanhize_bwd_kernel(const float* x, const float* xmin, const float* xmax, float* out, long long n, int dim) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * dim) return;
   int d = (int)(i % dim);
@@ -1288,6 +1324,7 @@ __global__ void tanhize_bwd_kernel(const float* x, const float* xmin, const floa
 // analyzer.py:111-127: record = [sp(513) | ap(513) | f0 | en | spk]; feature = Tanhize(sp), speaker = int64(last)
 __global__ void unpack_records_kernel(const float* rec, long long n, int rec_floats, int sp_dim,
                                       const float* xmin, const float* xmax, float* x, long long* y) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * sp_dim) return;
   long long f = i / sp_dim; int d = (int)(i - f * sp_dim);

@@ -224,6 +224,7 @@ template <bool PAIR, bool LNF = false>
 __global__ void __launch_bounds__(576, 1)
 umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
+  pdl_prologue();
   using namespace umma;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -709,6 +710,7 @@ template <bool PAIR>
 __global__ void __launch_bounds__(192, 1)
 umma_wgrad_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDl, UmmaArgs g) {
+  pdl_prologue();
   using namespace umma;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
