@@ -94,7 +94,7 @@ int64_t npvc_workspace_bytes(const npvc_handle* h, int64_t n_frames, int32_t tra
 
 /* Launch plan as JSON (buffers, ops, views) -- used by the CPU plan-interpreter tests. */
 const char* npvc_plan_json(const npvc_handle* h);
-/* Copy a named int32 plan table ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx") to host memory.
+/* Copy a named int32 plan table ("pack_src", "pack16_src", "pack_list", "unpack_ptr", "unpack_idx") to host memory.
  * Returns its length; copies at most `max` entries when out != NULL. */
 int64_t npvc_plan_table(const npvc_handle* h, const char* name, int32_t* out, int64_t max);
 /* Number of kernels this library has launched through this handle (bench: gpu_launches). */

@@ -115,15 +115,22 @@ class Interp:
     def op_10(self, op):   # PACK (fp32 operand packs)
         src = self.tables["pack_src"]
         n = self.plan["aw16_off"]
-        self.aw[:n] = np.where(src >= 0, self.theta[np.maximum(src, 0)], 0.0)
+        lst = self.tables.get("pack_list")
+        if lst is not None and lst.size:                 # tensor path: only the positions some op reads as fp32 are packed
+            self.aw[:n] = np.nan
+            self.aw[lst] = np.where(src[lst] >= 0, self.theta[np.maximum(src[lst], 0)], 0.0)
+        else:
+            self.aw[:n] = np.where(src >= 0, self.theta[np.maximum(src, 0)], 0.0)
 
     def op_12(self, op):   # PACK16 (bf16 hi / lo operand packs of the tensor path)
-        src = self.tables["pack16_src"]
+        src = self.tables["pack16_src"]                  # entry i -> hi pack element i and lo pack element i + half
+        half = self.plan["aw16_count"] // 2
+        assert src.size == half
         idx = np.maximum(src, 0) & ((1 << 29) - 1)
-        from_arena, want_lo = (src & (1 << 29)) != 0, (src & (1 << 30)) != 0
+        from_arena = (src & (1 << 29)) != 0
         val = np.where(from_arena, self.aw[np.minimum(idx, self.aw.size - 1)], self.theta[np.minimum(idx, self.theta.size - 1)])
         hi, lo = self.split(np.where(src >= 0, val, 0.0))
-        self.aw16[:] = np.where(src >= 0, np.where(want_lo, lo, hi), 0.0)
+        self.aw16[:half] = np.where(src >= 0, hi, 0.0); self.aw16[half:] = np.where(src >= 0, lo, 0.0)
 
     def op_13(self, op):   # ZCAT: zs = [z | one-hot(y)]
         zd, yp, n = op["i0"], op["i1"], self.n

@@ -50,7 +50,7 @@ def test_plan_matches_oracle(arch, n, umma, monkeypatch):
     tol_out, tol_g = (1e-12, 1e-9) if not umma else (3e-5, 5e-5)
     h = lib.Handle(arch)
     plan = h.plan()
-    tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx")}
+    tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "pack_list", "unpack_ptr", "unpack_idx")}
     P = R.init_params(arch, 0)
     x, y, eps = R.make_inputs(arch, n)
     it = PI.Interp(plan, tables, R.flatten_params(arch, P, np.float64), n, x, y, eps)
@@ -154,7 +154,7 @@ def test_alternative_architectures(alt_arch, umma, monkeypatch):
     from oracle import convvae_loops as L
     h = lib.Handle(alt_arch)
     plan = h.plan()
-    tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx")}
+    tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "pack_list", "unpack_ptr", "unpack_idx")}
     P = R.init_params(alt_arch, 0)
     x, y, eps = R.make_inputs(alt_arch, 3)
     ref = R.forward(alt_arch, P, x, y, eps, with_grads=True)
@@ -199,7 +199,7 @@ def test_random_architectures(seed, monkeypatch):
     for umma, tol in ((0, 1e-10), (1, 2e-4)):
         monkeypatch.setenv("NPVC_UMMA", str(umma))
         h = lib.Handle(arch)
-        tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "unpack_ptr", "unpack_idx")}
+        tables = {k: h.plan_table(k) for k in ("pack_src", "pack16_src", "pack_list", "unpack_ptr", "unpack_idx")}
         out = PI.Interp(h.plan(), tables, R.flatten_params(arch, P, np.float64), 3, x, y, eps).loss_fwd_bwd()
         for k in ("mu", "lv", "z", "xh"):
             assert rel(out[k], ref[k]) < tol, (umma, k, arch)

@@ -30,6 +30,7 @@ struct npvc_handle {
   int64_t max_chunk = 16384;
   int32_t* d_pack_src = nullptr;
   int32_t* d_pack16_src = nullptr;
+  int32_t* d_pack_list = nullptr;
   int32_t* d_unpack_ptr = nullptr;
   int32_t* d_unpack_idx = nullptr;
   int32_t* d_heavy = nullptr; int n_heavy = 0;     // parameters with >= UNPACK_HEAVY packed-gradient entries
@@ -600,12 +601,16 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
   npvc_handle* h = c.h; const Plan& p = h->plan; cudaStream_t st = c.st;
   switch (o.kind) {
     case OP_PACK: {
-      long long n = p.aw16_off;
-      launch_k(pack_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, c.theta, h->d_pack_src, c.ws, n);
+      // tensor path: only the fp32 packs some op reads (the bf16 packs are gathered from theta directly); with the
+      // debugging switch NPVC_UMMA_OPS any op may fall back to the CUDA-core kernels, which read all of them
+      const bool compact = h->use_umma && h->umma_allow.empty() && h->d_pack_list != nullptr;
+      long long n = compact ? (long long)p.pack_list.size() : p.aw16_off;
+      if (compact) launch_k(pack_list_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, c.theta, h->d_pack_src, h->d_pack_list, c.ws, n);
+      else launch_k(pack_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, c.theta, h->d_pack_src, c.ws, n);
       h->launches++; break;
     }
     case OP_PACK16: {
-      long long n = p.aw16_count;
+      long long n = p.aw16_count / 2;
       if (n > 0) {
         launch_k(pack16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, c.theta, c.ws, h->d_pack16_src, reinterpret_cast<uint16_t*>(c.ws + p.aw16_off), n);
         h->launches++;
@@ -822,6 +827,7 @@ int run_phase(Ctx& c, int phase) {
 }
 
 void free_tables(npvc_handle* h) {
+  cudaFree(h->d_pack_list); h->d_pack_list = nullptr;
   cudaFree(h->d_pack_src); cudaFree(h->d_pack16_src); cudaFree(h->d_unpack_ptr); cudaFree(h->d_unpack_idx); cudaFree(h->d_heavy);   // (cudaFree(nullptr) is a no-op)
   h->d_pack_src = h->d_pack16_src = h->d_unpack_ptr = h->d_unpack_idx = h->d_heavy = nullptr;
   h->tables_on_device = false;
@@ -851,6 +857,10 @@ int upload_tables(npvc_handle* h) {
   CUDA_TRY(cudaMalloc(&h->d_pack_src, (p.pack_src.size() + 1) * 4));
   CUDA_TRY(cudaMalloc(&h->d_pack16_src, (p.pack16_src.size() + 1) * 4));
   CUDA_TRY(cudaMemcpy(h->d_pack16_src, p.pack16_src.data(), p.pack16_src.size() * 4, cudaMemcpyHostToDevice));
+  if (!p.pack_list.empty()) {
+    CUDA_TRY(cudaMalloc(&h->d_pack_list, p.pack_list.size() * 4));
+    CUDA_TRY(cudaMemcpy(h->d_pack_list, p.pack_list.data(), p.pack_list.size() * 4, cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaMalloc(&h->d_unpack_ptr, p.unpack_ptr.size() * 4));
   CUDA_TRY(cudaMalloc(&h->d_unpack_idx, (p.unpack_idx.size() + 1) * 4));
   CUDA_TRY(cudaMemcpy(h->d_pack_src, p.pack_src.data(), p.pack_src.size() * 4, cudaMemcpyHostToDevice));
@@ -955,6 +965,7 @@ int64_t npvc_plan_table(const npvc_handle* h, const char* name, int32_t* out, in
   else if (!strcmp(name, "unpack_ptr")) v = &h->plan.unpack_ptr;
   else if (!strcmp(name, "unpack_idx")) v = &h->plan.unpack_idx;
   else if (!strcmp(name, "pack16_src")) v = &h->plan.pack16_src;
+  else if (!strcmp(name, "pack_list")) v = &h->plan.pack_list;
   if (!v) return -1;
   if (out) { int64_t n = (int64_t)v->size() < max ? (int64_t)v->size() : max; memcpy(out, v->data(), n * 4); }
   return (int64_t)v->size();

@@ -204,14 +204,19 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(
     }
   }
   __syncthreads();
+  {
+    const int P = lane_period(Co, 4); const bool owner = (int)(threadIdx.x & 31) < P;    // lanes P apart hold the same channel quad
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    atomicAdd(&chs[c0 + e], adg[e]); atomicAdd(&chs[Co + c0 + e], adb[e]); atomicAdd(&chs[2 * Co + c0 + e], adc[e]);
-  }
+    for (int e = 0; e < 4; e++) {
+      const float a = lane_period_sum(adg[e], P), b = lane_period_sum(adb[e], P), c = lane_period_sum(adc[e], P);
+      if (owner) { atomicAdd(&chs[c0 + e], a); atomicAdd(&chs[Co + c0 + e], b); atomicAdd(&chs[2 * Co + c0 + e], c); }
+    }
 #pragma unroll
-  for (int kk = 0; kk < E0_KT; kk++) {
-    atomicAdd(&sdw[kk * Co + c0 + 0], dw[kk][0].x); atomicAdd(&sdw[kk * Co + c0 + 1], dw[kk][0].y);
-    atomicAdd(&sdw[kk * Co + c0 + 2], dw[kk][1].x); atomicAdd(&sdw[kk * Co + c0 + 3], dw[kk][1].y);
+    for (int kk = 0; kk < E0_KT; kk++) {
+      const float w0 = lane_period_sum(dw[kk][0].x, P), w1 = lane_period_sum(dw[kk][0].y, P);
+      const float w2 = lane_period_sum(dw[kk][1].x, P), w3 = lane_period_sum(dw[kk][1].y, P);
+      if (owner) { atomicAdd(&sdw[kk * Co + c0 + 0], w0); atomicAdd(&sdw[kk * Co + c0 + 1], w1); atomicAdd(&sdw[kk * Co + c0 + 2], w2); atomicAdd(&sdw[kk * Co + c0 + 3], w3); }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Co; i += blockDim.x) {

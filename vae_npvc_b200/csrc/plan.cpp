@@ -596,7 +596,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
       if (o.kind != OP_GEMM || !view_ok(o.A) || o.K < 8 || o.N < 8 || o.B.space != SP_AW) continue;
       o.kpad = rup(o.K, 8);
       const int64_t sz = (int64_t)o.N * o.kpad;
-      o.bu_hi = a16_alloc(sz); o.bu_lo = a16_alloc(sz);
+      o.bu_hi = a16_alloc(sz);                 // the lo pack mirrors it half a region further on (set below)
       for (int n = 0; n < o.N; n++) for (int k = 0; k < o.K; k++) {
         const int64_t q = o.B.off + (int64_t)k * o.ldb + n;
         int32_t src = p.pack_src[q];
@@ -606,11 +606,28 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
           src = (int32_t)q | PACK16_FROM_ARENA;
         }
         p.pack16_src[o.bu_hi + (int64_t)n * o.kpad + k] = src;
-        p.pack16_src[o.bu_lo + (int64_t)n * o.kpad + k] = src | PACK16_LO;
       }
       o.umma = 1;
     }
+    // bf16 region = [hi packs of every op | lo packs in the same layout]: one table entry (and one gather) per
+    // element writes both planes
+    const int64_t half = p.aw16_count;
+    for (Op& o : p.ops) if (o.umma && o.kind == OP_GEMM) o.bu_lo = o.bu_hi + half;
+    p.aw16_count = 2 * half;
     p.arena_w = rup64(p.aw16_off + (p.aw16_count + 1) / 2, 64);
+    // fp32 packs nobody reads: the B operand of an op that always runs on the tensor path (its bf16 packs are gathered
+    // from theta directly).  Few-tap ops that may fall back to the row kernel keep theirs.
+    std::vector<uint8_t> need(p.aw16_off, 1);
+    for (const Op& o : p.ops)
+      if (o.umma && o.kind == OP_GEMM && !(o.K <= 64 && o.N <= 32))
+        for (int64_t k = 0; k < o.K; k++) for (int n = 0; n < o.ldb; n++) {
+          const int64_t q = o.B.off + k * o.ldb + n;
+          if (q < (int64_t)need.size() && !(q >= ptab_lo && q < ptab_hi)) need[q] = 0;
+        }
+    for (const Op& o : p.ops)          // ... unless another op reads the same pack without the tensor path
+      if (o.kind == OP_GEMM && !o.umma && o.B.space == SP_AW)
+        for (int64_t k = 0; k < o.K; k++) for (int n = 0; n < o.ldb; n++) { const int64_t q = o.B.off + k * o.ldb + n; if (q < (int64_t)need.size()) need[q] = 1; }
+    for (int64_t q = 0; q < p.aw16_off; q++) if (need[q]) p.pack_list.push_back((int32_t)q);     // (structural zeros included)
   }
 
   // ---------------------------------------------------------------- JSON

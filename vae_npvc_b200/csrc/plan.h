@@ -109,7 +109,8 @@ struct Plan {
   int64_t aw16_off = 0;      // float offset of the bf16 pack region inside arena_w
   int64_t aw16_count = 0;    // bf16 elements in it
   std::vector<int32_t> pack_src;     // [aw16_off]  theta index or -1 (fp32 packs)
-  std::vector<int32_t> pack16_src;   // [aw16_count] theta index | mode << 29, or -1
+  std::vector<int32_t> pack16_src;   // [aw16_count / 2] theta index | mode << 29, or -1: entry i fills hi pack i and lo pack i + aw16_count / 2
+  std::vector<int32_t> pack_list;    // tensor path: the positions of [0, aw16_off) that some op reads as fp32 (the rest is not packed)
   std::vector<int32_t> unpack_ptr;   // [n_params+1] CSR over theta
   std::vector<int32_t> unpack_idx;   // positions in arena_dw
   int buf_z = -1, buf_mu = -1, buf_lv = -1, buf_xh = -1, buf_acc = -1, buf_hz = -1, buf_adw = -1;
@@ -120,9 +121,9 @@ struct Plan {
   int64_t buf_offset(int b, int64_t chunk, bool train) const;   // float offset inside ws
 };
 
-// pack16_src entries: -1 = zero; else source index | flags: the bf16 hi (or, with PACK16_LO, the bf16 of the
-// residual) of theta[index] (or, with PACK16_FROM_ARENA, of the fp32 pack arena_w[index])
-constexpr int32_t PACK16_FROM_ARENA = 1 << 29, PACK16_LO = 1 << 30;
+// pack16_src entries: -1 = zero; else source index | flags: the bf16 hi and the bf16 of the residual of theta[index]
+// (or, with PACK16_FROM_ARENA, of the fp32 pack arena_w[index])
+constexpr int32_t PACK16_FROM_ARENA = 1 << 29;
 constexpr int32_t PACK_INDEX_MASK = (1 << 29) - 1;
 
 // Returns empty string on success, else an error message.  use_umma: route GEMM-shaped ops to the
