@@ -581,7 +581,7 @@ int launch_e0_bwd(Ctx& c, const Op& o, const Op& nx) {      // o: OP_LN_BWD of t
   const int bt = E0_BLOCK(G), fpb = bt / G;
   const long long fbs = (c.n + fpb - 1) / fpb;
   long long blocks = (long long)h->sm_count * (512 / bt); if (blocks > fbs) blocks = fbs;
-  const size_t sm = ((size_t)(E0_KT + 5) * g.Co + (size_t)fpb * g.xp) * sizeof(float);
+  const size_t sm = ((size_t)(E0_KT + 5) * g.Co + (size_t)2 * fpb * g.xp) * sizeof(float);      // (staged frames double-buffered)
   const bool v4 = o.L / 4 > 3 * G;                        // units of 4 elements per thread: 3 or 4
 #define NPVC_E0_BWD(GG) do { if (v4) launch_k(e0_bwd_kernel<GG, 4>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); else launch_k(e0_bwd_kernel<GG, 3>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); } while (0)
   if (G == 32) NPVC_E0_BWD(32); else if (G == 64) NPVC_E0_BWD(64); else if (G == 128) NPVC_E0_BWD(128); else NPVC_E0_BWD(256);

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(
   pdl_prologue();
   constexpr int FPB = E0_BLOCK(G) / G;
   extern __shared__ __align__(16) float e0sm[];      // [KT][Co] weights | bias | gamma | beta | [FPB][xp] staged frames
-  __shared__ float red[8];
+  __shared__ float red[2 * 8];
+  int par = 0;
   const int Co = g.Co, XP = g.xp;
   float* sw = e0sm; float* sb = sw + E0_KT * Co; float* sg = sb + Co; float* sbt = sg + Co;
   for (int i = threadIdx.x; i < E0_KT * Co; i += blockDim.x) sw[i] = (i < g.k * Co) ? g.W[i] : 0.f;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(
         for (int q = 0; q < 4; q++) s[0] += v[i][q].x + v[i][q].y;
       }
     }
-    group_sum<G, 1>(s, red);
+    group_sum_db<G, 1>(s, red, par);
     const float mean = s[0] * invL;
     float q2[1] = {0.f};
 #pragma unroll
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(
         for (int q = 0; q < 4; q++) { const float d0 = v[i][q].x - mean, d1 = v[i][q].y - mean; q2[0] = fmaf(d0, d0, q2[0]); q2[0] = fmaf(d1, d1, q2[0]); }
       }
     }
-    group_sum<G, 1>(q2, red);
+    group_sum_db<G, 1>(q2, red, par);
     const float rs = rsqrtf(q2[0] * invL + NPVC_LN_EPS);
     if (!fok) continue;                    // (every thread still reaches the barriers at the top of the next iteration)
     if (t == 0) { g.rstd[f] = rs; g.mean[f] = mean; }
@@ -130,15 +131,15 @@ template <int G, int V>
 __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(E0BwdArgs g) {
   pdl_prologue();
   constexpr int FPB = E0_BLOCK(G) / G;
-  extern __shared__ __align__(16) float e0sm[];      // [3 Co] dgamma | dbeta | dbias sums, [KT Co] dW sums, gamma, beta, [FPB][xp] frames
-  __shared__ float red[16];
+  extern __shared__ __align__(16) float e0sm[];      // [3 Co] dgamma | dbeta | dbias sums, [KT Co] dW sums, gamma, beta, [2][FPB][xp] frames
+  __shared__ float red[2][E0_BLOCK(G) / 32][2];
   const int Co = g.Co, XP = g.xp;
   float* chs = e0sm; float* sdw = chs + 3 * Co; float* sgm = sdw + E0_KT * Co; float* sbt = sgm + Co;
   for (int i = threadIdx.x; i < (3 + E0_KT) * Co; i += blockDim.x) e0sm[i] = 0.f;
   for (int i = threadIdx.x; i < Co; i += blockDim.x) { sgm[i] = g.gamma[i]; sbt[i] = g.beta[i]; }
   __syncthreads();
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
-  float* xs = sbt + Co + grp * XP;
+  float* xs0 = sbt + Co + grp * XP;                    // staged frames and warp partials are double-buffered by frame parity:
   const int qpp = Co >> 2;                             // channel quads per position (a power of two: divides G)
   const int qshift = 31 - __clz(qpp);
   const int c0 = (t & (qpp - 1)) << 2;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(
   for (int e = 0; e < 4; e++) { gm[e] = sgm[c0 + e]; bt[e] = sbt[c0 + e]; adg[e] = adb[e] = adc[e] = 0.f; }
 #pragma unroll
   for (int kk = 0; kk < E0_KT; kk++) dw[kk][0] = dw[kk][1] = make_float2(0.f, 0.f);
+  int par = 0;
   for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
     const long long f = fb * FPB + grp; const bool fok = f < g.frames;
     float dx[V][4], xh[V][4];
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(
         dx[i][0] = a.x; dx[i][1] = a.y; dx[i][2] = a.z; dx[i][3] = a.w; xh[i][0] = b.x; xh[i][1] = b.y; xh[i][2] = b.z; xh[i][3] = b.w;
       }
     }
-    __syncthreads();                                   // the previous frame's taps are done with the staged rows
+    float* xs = xs0 + par * FPB * XP;                  // ONE barrier per frame orders both (see below)
     e0_stage_x(xs, g.x + f * g.Hi, fok, t, G, XP, g.pl, g.Hi);
     float s[2] = {0.f, 0.f};
 #pragma unroll
@@ -182,8 +184,19 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(
         }
       }
     }
-    __syncthreads();                                   // staged rows visible
-    group_sum<G, 2>(s, red);
+    {
+      // frame sums over the group's warps; the barrier also publishes the staged rows.  A buffer written in iteration k is
+      // next written in k + 2, and every thread passes the barrier of k + 1 (after its reads of k) before any gets there.
+      s[0] = warp_sum(s[0]); s[1] = warp_sum(s[1]);
+      const int warp = threadIdx.x >> 5;
+      if ((threadIdx.x & 31) == 0) { red[par][warp][0] = s[0]; red[par][warp][1] = s[1]; }
+      __syncthreads();
+      const int w0 = (warp / (G / 32)) * (G / 32);
+      s[0] = 0.f; s[1] = 0.f;
+#pragma unroll
+      for (int w = 0; w < G / 32; w++) { s[0] += red[par][w0 + w][0]; s[1] += red[par][w0 + w][1]; }
+    }
+    par ^= 1;
     if (!fok) continue;
     const float s1 = s[0] * invL, s2 = s[1] * invL;
 #pragma unroll

@@ -825,6 +825,32 @@ __device__ __forceinline__ void group_sum(float (&v)[NV], float* red /* [8][NV] 
     }
   }
 }
+// The same with ONE barrier: the warp partials are double-buffered (red[2][8][NV], `par` toggles per call).  A buffer
+// written in call k is next written in call k + 2, and every thread passes the barrier of call k + 1 -- after its reads of
+// call k -- before any thread gets there.
+template <int G, int NV>
+__device__ __forceinline__ void group_sum_db(float (&v)[NV], float* red /* [2][8][NV] */, int& par) {
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = warp_sum(v[i]);
+  if (G > 32) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* rp = red + par * 8 * NV;
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) rp[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+    const int w0 = (warp / (G / 32)) * (G / 32);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < G / 32; w++) t += rp[(w0 + w) * NV + i];
+      v[i] = t;
+    }
+    par ^= 1;
+  }
+}
 __device__ __forceinline__ void ld8(const float* p, float (&x)[8]) {
   const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
   x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
@@ -853,7 +879,8 @@ template <int G>
 __global__ void __launch_bounds__(256) ln_fwd_reg_kernel(LnFwdArgs g) {
   pdl_prologue();
   constexpr int V = 4, FPB = 256 / G;
-  __shared__ float red[8];
+  __shared__ float red[2 * 8];
+  int par = 0;
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
   const int L8 = g.L >> 3, off8 = g.out_off >> 3, F8 = g.out_flen >> 3;
   float gm[8], bt[8];
@@ -874,7 +901,7 @@ __global__ void __launch_bounds__(256) ln_fwd_reg_kernel(LnFwdArgs g) {
         for (int e = 0; e < 8; e++) s[0] += x[k][e];
       }
     }
-    group_sum<G, 1>(s, red);
+    group_sum_db<G, 1>(s, red, par);
     const float mean = s[0] * invL;
     float q[1] = {0.f};
 #pragma unroll
@@ -884,7 +911,7 @@ __global__ void __launch_bounds__(256) ln_fwd_reg_kernel(LnFwdArgs g) {
         for (int e = 0; e < 8; e++) { const float d = x[k][e] - mean; q[0] = fmaf(d, d, q[0]); }
       }
     }
-    group_sum<G, 1>(q, red);
+    group_sum_db<G, 1>(q, red, par);
     const float rs = rsqrtf(q[0] * invL + NPVC_LN_EPS);
     if (!fok) continue;                    // (no block-wide barrier after this point in the iteration)
     if (t == 0) { g.rstd[f] = rs; g.mean[f] = mean; }
@@ -907,7 +934,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
   pdl_prologue();
   constexpr int V = 4, FPB = 256 / G;
   extern __shared__ __align__(16) float chs[];   // [3 * Cn] channel sums: dgamma | dbeta | dbias, then [2 * Cn] gamma | beta
-  __shared__ float red[16];
+  __shared__ float red[2 * 16];
+  int par = 0;
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
   const int L8 = g.L >> 3, off8 = g.out_off >> 3, F8 = g.out_flen >> 3;
   float* sgm = chs + 3 * g.Cn; float* sbt = sgm + g.Cn;
@@ -950,7 +978,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
         }
       }
     }
-    group_sum<G, 2>(s, red);
+    group_sum_db<G, 2>(s, red, par);
     if (!fok) continue;
     const float s1 = s[0] * invL, s2 = s[1] * invL;
 #pragma unroll
