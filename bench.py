@@ -194,10 +194,24 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------------------------
+def rank_roster(world, local):
+    """Every rank's (rank, host, GPU uuid) gathered through the communicator itself: N distinct GPUs took part in a
+    collective of this run (evidence that does not depend on NCCL's debug log)."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    me = {"rank": dist.get_rank(), "host": socket.gethostname(), "gpu": str(torch.cuda.get_device_properties(local).uuid),
+          "pci_bus": torch.cuda.get_device_properties(local).pci_bus_id}
+    box = [None] * world
+    dist.all_gather_object(box, me)
+    return box
+
+
 def nccl_evidence(world):
     """NCCL_DEBUG=INFO goes to files under the repo (stdout stays ONE JSON line); afterwards rank 0 echoes the
     communicator lines (nranks / nNodes / algorithm) to stderr so the rank count of the run is observable."""
     out = []
+    print("[nccl] debug files: %s" % sorted(os.path.basename(p) for p in glob.glob(os.path.join(ROOT, "gpurun_out", "nccl_debug.*"))), file=sys.stderr)
     for p in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "nccl_debug.*.log"))):
         try:
             for ln in open(p, errors="replace"):
@@ -285,7 +299,15 @@ def main():
         os.environ.setdefault("NCCL_DEBUG", "INFO")           # rank evidence; into files: stdout carries the ONE JSON line
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
         os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log"))
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator comes up: stdout must carry ONE JSON line,
+        # so file descriptor 1 points at stderr until a first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t = torch.ones(1, device=torch.device("cuda", local)); dist.all_reduce(t); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
     dev = torch.device("cuda", local)
     cfg = CONFIGS[args.config]
     kind, n = cfg["kind"], cfg["frames"]
@@ -442,7 +464,12 @@ def main():
         cpu = {"value": fps, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
                "sample": "%d frames/step x 3 steps (+1 warm-up): the whole workload step, fp32 PyTorch-CPU restatement of the "
                          "reference graph (oracle/convvae_ref.py)" % n}
+    roster = rank_roster(world, local) if world > 1 else None
     nccl = nccl_evidence(world) if (rank == 0 and world > 1) else None
+    if nccl is not None:
+        nccl["ranks"] = roster
+        nccl["distinct_gpus"] = len({(r["host"], r["gpu"]) for r in roster})
+        print("[nccl] %d ranks on %d distinct GPUs: %s" % (world, nccl["distinct_gpus"], roster), file=sys.stderr)
 
     if rank == 0:
         line = {
@@ -465,7 +492,16 @@ def main():
             line["nccl"] = nccl
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL kernels go before the communicator; a communicator teardown that does not
+        # return (seen once with captured collectives) must not hang the run: the line is out, leave after 20 s
+        if trainer is not None and trainer._state:
+            trainer._state["graphs"].clear()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        th.start(); th.join(20.0)
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -81,7 +81,13 @@ def check_recording(rec, n):
                 else:
                     assert L["grid"][0] <= min(148, u["m_tiles"] * u["n_tiles"]), (L["grid"], u)
             # 1024-byte alignment slack + ring + barriers + TMEM slot + bias staging of up to 4 epilogue groups
-            assert L["smem"] >= 1023 + ring + 8 * (2 * st + 10) + 16 + 4096, (name, L["smem"], ring, u)
+            assert L["smem"] >= 1023 + ring + 8 * (2 * st + 10) + 16 + 4096 + (32768 if u["ln_on"] else 0), (name, L["smem"], ring, u)
+            assert bool(u["ln_on"]) == ("umma_fwd_kernel_tILb0ELb1E" in name), (name, u["ln_on"])     # the LNF instantiation <-> ln.on
+            if u["ln_on"]:
+                # Layernorm epilogue: whole frames per tile, one N tile, plane rows of the frame inside its (padded) output frame
+                assert not pair and u["Ra"] == 1 and u["n_tiles"] == 1 and u["N"] % 8 == 0 and u["ln_L"] == u["c_R"] * u["N"], u
+                assert u["ln_out_off"] % 8 == 0 and u["ln_out_flen"] % 8 == 0 and u["ln_out_off"] + u["ln_L"] <= u["ln_out_flen"], u
+                assert not rec.train or u["ln_store_c"] == 1, u
             assert tm[0]["box"] == tm[1]["box"] and tm[2]["box"] == tm[3]["box"]
         else:                                                     # weight-gradient kernel
             BN, dsw, st, ral = u["BN"], u["d_sw"], u["stages"], u["rows_al"]
@@ -93,7 +99,8 @@ def check_recording(rec, n):
                 d_boxes = BN // dw // 2
             else:
                 d_boxes = -(-BN // dw)
-            stage = 2 * (2 * ral * 128) + 2 * d_boxes * _rup(ral * dsw, 1024)
+            assert u["a_boxes"] == (1 if (not pair and u["K"] <= 64) else 2), u
+            stage = 2 * (u["a_boxes"] * ral * 128) + 2 * d_boxes * _rup(ral * dsw, 1024)
             assert L["smem"] >= 1023 + st * stage + 8 * (2 * st + 1) + 8 + 4, (name, L["smem"], st, stage, u)
             gx, gy, gz = L["grid"]
             assert gx * 128 >= u["K"] and (gx - (2 if pair else 1)) * 128 < u["K"], (L["grid"], u)

@@ -479,7 +479,8 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   }
   const int m_tiles_k = (o.K + 127) / 128;
   // rows per stage: keep >= 3 stages in shared memory
-  const int per_row = pair ? 512 + 2 * BN : 512 + 4 * BN;          // (pair: each CTA stages half of the dC columns)
+  const int a_boxes = (!pair && o.K <= 64) ? 1 : 2;                // 64-column A boxes per stage and plane
+  const int per_row = pair ? 512 + 2 * BN : 256 * a_boxes + 4 * BN;   // (pair: each CTA stages half of the dC columns)
   const int budget = h->wgrad_smem_kb * 1024;       // < 227 KB leaves shared memory for a co-resident Layernorm block (side-stream overlap)
   int row_target = ((budget - 5 * 1024) / 3 / per_row) / 16 * 16; if (row_target > 128) row_target = 128; if (row_target < 16) row_target = 16;
   const RowTiling rt = make_tiling(o.A.R, frames, row_target);
@@ -496,9 +497,10 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.rt = rt; g.n_tiles = n_tiles; g.d_sw = d_sw;
   g.rows_al = (rt.rows_tile + 15) / 16 * 16;
+  g.a_boxes = a_boxes;
   const int d_boxes = pair ? BN / 128 : (BN + d_sw / 2 - 1) / (d_sw / 2);      // per CTA
   const int d_region = (g.rows_al * d_sw + 1023) / 1024 * 1024;
-  const int stage_bytes = 2 * (2 * g.rows_al * 128) + 2 * d_boxes * d_region;
+  const int stage_bytes = 2 * (a_boxes * g.rows_al * 128) + 2 * d_boxes * d_region;
   int tc = 32; while (tc < 2 * BN) tc *= 2; g.tmem_cols = tc;
   int stages = (budget - 3072) / stage_bytes; if (stages > 8) stages = 8; if (stages < 1) stages = 1;
   g.stages = stages;
@@ -654,6 +656,12 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
         dim3 grid((unsigned)((o.N + 127) / 128), (unsigned)ks);
         launch_k(fewrows_gemm_kernel, dim3(grid), dim3(128), (size_t)o.rows_fixed * kchunk * sizeof(float), st, 
             g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, kchunk);
+        h->launches++; break;
+      }
+      if (o.rows_fixed && o.rows_fixed <= 16 && o.K <= 512 && !g.A.pred && g.A.R == 1 && g.C.R == 1 && !g.A.split && !g.C.split && !g.C.pred) {
+        // few rows, short K, plain store (+ biases): the per-speaker table at pack time
+        launch_k(fewrows_fwd_kernel, dim3((unsigned)((o.N + 255) / 256)), dim3(256), (size_t)o.rows_fixed * o.K * sizeof(float), st,
+                 g.A.p + g.A.off, (int)g.A.fs, (int)o.rows_fixed, o.K, g.B, o.ldb, o.N, g.C.p + g.C.off, (int)g.C.fs, g.bias0, g.bias1, g.bias2, o.bias_mod);
         h->launches++; break;
       }
       if (row_shaped) {     // (independent of n: per-frame results must not depend on the batch size)

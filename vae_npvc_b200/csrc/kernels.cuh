@@ -493,6 +493,31 @@ __global__ void __launch_bounds__(128) fewrows_gemm_kernel(const float* A, int l
   for (int r = 0; r < 16; r++) if (r < R) atomicAdd(&C[(long long)r * ldc + n], acc[r]);
 }
 
+// C[R,N] = A[R,K] . B[K,N] + biases for a handful of rows (R <= 16) and a short K: one thread per output column keeps the
+// R sums in registers, A sits in shared memory, B is read once, coalesced (the per-speaker table of the merge layer:
+// 10 x 128 x 1672 at pack time -- the tiled GEMM spent 33 us of latency on it).
+__global__ void __launch_bounds__(256) fewrows_fwd_kernel(const float* A, int lda, int R, int K, const float* B, int ldb, int N,
+                                                          float* C, int ldc, const float* bias0, const float* bias1, const float* bias2, int bias_mod) {
+  pdl_prologue();
+  extern __shared__ float As[];                    // [R][K]
+  for (int i = threadIdx.x; i < R * K; i += blockDim.x) As[i] = A[(long long)(i / K) * lda + (i % K)];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) acc[r] = 0.f;
+  for (int k = 0; k < K; k++) {
+    const float b = B[(long long)k * ldb + n];
+#pragma unroll
+    for (int r = 0; r < 16; r++) if (r < R) acc[r] = fmaf(As[r * K + k], b, acc[r]);
+  }
+  float bs = 0.f;
+  if (bias0) { const int bi = n % bias_mod; bs = bias0[bi]; if (bias1) bs += bias1[bi]; if (bias2) bs += bias2[bi]; }
+#pragma unroll
+  for (int r = 0; r < 16; r++) if (r < R) C[(long long)r * ldc + n] = acc[r] + bs;
+}
+
 // =============================================================================================
 // (W) for tiny K x N (first layer: 7 taps x 16 channels) and millions of rows: every thread keeps
 // the whole K x N gradient in registers over its rows, one block reduction + K*N atomics per block.

@@ -58,6 +58,8 @@ struct UmmaArgs {
   int d_sw;              // swizzle span (bytes) of the dC boxes: 128 / 64 / 32 -> 64 / 32 / 16 columns per box
   int rows_al;           // rows_tile rounded up to 16 (MMA K step)
   int tiles_per_split;
+  int a_boxes;           // 64-column boxes of the A view per stage and plane: 2, or 1 when K <= 64 (the MMA's upper 64 rows then
+                         // read the lo plane's box -- finite values that only reach accumulator rows k >= K, which are never added)
   float* out; int ld;
 };
 

@@ -718,7 +718,7 @@ umma_wgrad_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const int d_boxes = PAIR ? (g.BN / dw) >> 1 : (g.BN + dw - 1) / dw;      // dC boxes THIS CTA stages (PAIR: its half of the N tile)
   const uint32_t a_region = (uint32_t)g.rows_al * 128u;         // one 64-column A box (rows_al % 16 == 0 -> 1024-aligned)
   const uint32_t d_region = ((uint32_t)g.rows_al * (uint32_t)g.d_sw + 1023u) & ~1023u;
-  const uint32_t a_plane = 2u * a_region, d_plane = (uint32_t)d_boxes * d_region;
+  const uint32_t a_plane = (uint32_t)g.a_boxes * a_region, d_plane = (uint32_t)d_boxes * d_region;
   const uint32_t stage_bytes = 2u * a_plane + 2u * d_plane;
   const uint32_t bar_base = sbase + (uint32_t)g.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -764,7 +764,7 @@ umma_wgrad_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
-    const uint32_t tx = (PAIR ? 2u : 1u) * 2u * (2u * (uint32_t)g.rt.rows_tile * 128u + (uint32_t)d_boxes * (uint32_t)g.rt.rows_tile * (uint32_t)g.d_sw);
+    const uint32_t tx = (PAIR ? 2u : 1u) * 2u * ((uint32_t)g.a_boxes * (uint32_t)g.rt.rows_tile * 128u + (uint32_t)d_boxes * (uint32_t)g.rt.rows_tile * (uint32_t)g.d_sw);
     RingPos sp(g.stages);
     if constexpr (PAIR) {
       // the K tile past the last one (odd tile count) re-reads the last tile; its rows are never added (k >= K)
@@ -799,8 +799,7 @@ umma_wgrad_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       const uint32_t st = sbase + (uint32_t)s * stage_bytes;
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), tx);
-#pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < g.a_boxes; b++) {
           tma_load_4d(st + (uint32_t)b * a_region, &tmAh, full_bar(s), m0 + 64 * b, 0, a0, f0);
           tma_load_4d(st + a_plane + (uint32_t)b * a_region, &tmAl, full_bar(s), m0 + 64 * b, 0, a0, f0);
         }
