@@ -58,6 +58,7 @@ struct npvc_handle {
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int umma_groups = 4;               // NPVC_UMMA_GROUPS: epilogue groups of the forward kernel (1, 2 or 4; <= accumulator sets)
   int umma_tap = 1;                  // NPVC_UMMA_TAP=0: conv-shaped layers through the overlapping-window boxes (A/B comparisons)
+  int umma_merge = 1;                // NPVC_UMMA_MERGE=0: three MMAs per K step instead of two (A/B comparisons; see UmmaArgs::merge)
   int nvtx = 0;                      // NPVC_NVTX=1: an NVTX push / pop range named after the plan op around every launch
   bool profiling = false;
   struct Ev { int op; cudaEvent_t a, b; long long rows, frames; };
@@ -308,6 +309,7 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg_in, con
   g.acc_sets = 512 / (2 * BN) >= 4 ? 4 : (512 / (2 * BN) >= 2 ? 2 : 1);
   int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
   g.stages = tg.stages;
+  g.merge = (h->umma_merge && 2 * BN <= 256 && tg.b_tile_al == BN * sw) ? 1 : 0;     // (hi and lo weight tiles back to back)
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
   if (fuse_ln) { fill_ln_epilogue(c, *ln, g); if (fused) *fused = true; }
@@ -436,6 +438,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool*
   bool fuse_ln = ln_epilogue_ok(c, o, ln, rt, n_tiles) && (225 * 1024 - 6144 - LN_EPI_SMEM) / stage_bytes >= 2;
   int stages = (225 * 1024 - 6144 - (fuse_ln ? LN_EPI_SMEM : 0)) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
   g.stages = stages;
+  g.merge = (h->umma_merge && 2 * BN <= 256) ? 1 : 0;
   g.C = dview(c, o.C);
   g.bias0 = resolve(c, o.bias[0]); g.bias1 = resolve(c, o.bias[1]); g.bias2 = resolve(c, o.bias[2]); g.bias_mod = o.bias_mod;
   if (fuse_ln) { fill_ln_epilogue(c, *ln, g); if (fused) *fused = true; }
@@ -498,6 +501,7 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   g.K = o.K; g.N = o.N; g.BN = BN; g.rt = rt; g.n_tiles = n_tiles; g.d_sw = d_sw;
   g.rows_al = (rt.rows_tile + 15) / 16 * 16;
   g.a_boxes = a_boxes;
+  g.merge = (h->umma_merge && !pair && 2 * BN <= 256 && BN % (d_sw / 2) == 0) ? 1 : 0;     // (whole dC boxes: the lo plane's boxes follow the hi plane's)
   const int d_boxes = pair ? BN / 128 : (BN + d_sw / 2 - 1) / (d_sw / 2);      // per CTA
   const int d_region = (g.rows_al * d_sw + 1023) / 1024 * 1024;
   const int stage_bytes = 2 * (a_boxes * g.rows_al * 128) + 2 * d_boxes * d_region;
@@ -915,6 +919,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
   if (const char* pd = getenv("NPVC_PDL")) g_pdl = atoi(pd) ? 1 : 0;
   if (const char* nv = getenv("NPVC_NVTX")) h->nvtx = atoi(nv);
+  if (const char* mg = getenv("NPVC_UMMA_MERGE")) h->umma_merge = atoi(mg);
   if (const char* fl = getenv("NPVC_FUSE_LN_TRAIN")) h->fuse_ln_train = atoi(fl);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);

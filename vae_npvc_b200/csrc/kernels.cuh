@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(256) fewrows_fwd_kernel(const float* A, int ld
   float acc[16];
 #pragma unroll
   for (int r = 0; r < 16; r++) acc[r] = 0.f;
-  for (int k = 0; k < K; k++) {
+#pragma unroll 8
+  for (int k = 0; k < K; k++) {                      // (8 loads in flight: the single wave of blocks is latency-bound)
     const float b = B[(long long)k * ldb + n];
 #pragma unroll
     for (int r = 0; r < 16; r++) if (r < R) acc[r] = fmaf(As[r * K + k], b, acc[r]);
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(192) wgrad_small_kernel(WgradArgs g, long long
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < re && q * 4 < g.K) {
         const long long f = r / g.A.R; const int j = (int)(r - f * g.A.R);
-        v = *reinterpret_cast<const float4*>(g.A.p + f * g.A.fs + (long long)j * g.A.rs + g.A.off + q * 4);
+        v = view_ld4(g.A, f, j * g.A.rs + g.A.off + q * 4);            // (fp32 or bf16 hi / lo planes)
       }
       *reinterpret_cast<float4*>(&As[rr][q * 4]) = v;
     }
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(192) wgrad_small_kernel(WgradArgs g, long long
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < re && q * 4 < g.N) {
         const long long f = r / g.D.R; const int j = (int)(r - f * g.D.R);
-        v = *reinterpret_cast<const float4*>(g.D.p + f * g.D.fs + (long long)j * g.D.rs + g.D.off + q * 4);
+        v = view_ld4(g.D, f, j * g.D.rs + g.D.off + q * 4);
       }
       *reinterpret_cast<float4*>(&Ds[rr][q * 4]) = v;
     }

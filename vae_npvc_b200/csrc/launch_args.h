@@ -51,6 +51,11 @@ struct UmmaArgs {
   // rows (row-shifted K-major descriptor) with the resident weight tile of tap t.  sw = 2 * tapC bytes.
   int tapT, tapC, tapP;
   int b_tile_al;         // tap mode: bytes of one resident weight tile (BN * sw rounded up to 1024)
+  // merge != 0 (single-CTA forms, 2 * BN <= 256): the hi and lo tiles of the B (wgrad: dC) operand lie back to back in
+  // shared memory, so ONE MMA with N = 2 * BN computes  Ah.[Bh | Bl]  into the two adjacent accumulators (main | correction)
+  // and a second adds  Al.Bh  to the correction: two MMAs per K step instead of three.  The few-tap layers are paced by the
+  // MMA warp's instruction stream (a small-N MMA costs ~90 cycles whatever its N), so this is a third less of it.
+  int merge;
   DView C;
   const float* bias0; const float* bias1; const float* bias2; int bias_mod;
   LnEpi ln;

@@ -186,9 +186,9 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 // base descriptor plus a constant (the MMA warp's serial instruction stream paces the few-tap layers).
 //   a0d / b0d: descriptors of phase tile 0 (hi plane) of the stage / of tap 0's resident weight tile (hi)
 //   a_tile16 / b_tile16 / sw16: tile pitches and the row pitch in 16-byte units
-template <int T, int P>
+template <int T, int P, bool MERGE>
 __device__ __forceinline__ void issue_taps(uint32_t acc, uint32_t acc2, uint64_t a0d, uint64_t b0d, uint32_t a_tile16,
-                                           uint32_t b_tile16, uint32_t sw16, int ksteps_c, uint32_t idesc) {
+                                           uint32_t b_tile16, uint32_t sw16, int ksteps_c, uint32_t idesc, uint32_t idesc2) {
 #pragma unroll
   for (int tp = 0; tp < T; tp++) {
     const int pz = tp % P, m = tp / P;                  // tap tp = P * m + pz: phase tile pz, shifted by m rows
@@ -197,9 +197,14 @@ __device__ __forceinline__ void issue_taps(uint32_t acc, uint32_t acc2, uint64_t
     for (int k4 = 0; k4 < ksteps_c; k4++) {             // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr >> 4) field
       const uint64_t o = (uint64_t)(k4 * 2);
       const uint32_t first = (tp > 0 || k4 > 0) ? 1u : 0u;
-      mma_bf16(acc, ah + o, bh + o, idesc, first);      // main products
-      mma_bf16(acc2, al + o, bh + o, idesc, first);     // corrections: separate accumulator
-      mma_bf16(acc2, ah + o, bl + o, idesc, 1u);
+      if constexpr (MERGE) {
+        mma_bf16(acc, ah + o, bh + o, idesc2, first);   // Ah.[Bh | Bl] -> main | correction accumulators (N = 2 BN)
+        mma_bf16(acc2, al + o, bh + o, idesc, 1u);      // + Al.Bh
+      } else {
+        mma_bf16(acc, ah + o, bh + o, idesc, first);      // main products
+        mma_bf16(acc2, ah + o, bl + o, idesc, first);     // corrections: separate accumulator (same order as the merged form)
+        mma_bf16(acc2, al + o, bh + o, idesc, 1u);
+      }
     }
   }
 }
@@ -310,7 +315,8 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     }
   } else if (warp == 1 && tap) {
     // ------------------------------------------------------------------ MMA issuer, tap mode
-    const uint32_t idesc = make_idesc(g.BN, false);
+    const uint32_t idesc = make_idesc(g.BN, false), idesc2 = make_idesc(2 * g.BN, false);
+    const bool merge = g.merge != 0;
     const uint64_t dbase = sdesc_base(0, sw);
     const int ksteps_c = g.tapC >> 4;
     const uint64_t b0d = sdesc_at(dbase, sbase);
@@ -328,10 +334,10 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       if (elect_one()) {
         const uint32_t a16 = a_tile_bytes >> 4, b16 = (uint32_t)g.b_tile_al >> 4, sw16 = sw >> 4;
         // the tap / phase combinations of the supported layer shapes, unrolled; anything else: generic loop
-        if (g.tapT == 3 && g.tapP == 1) issue_taps<3, 1>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc);
-        else if (g.tapT == 7 && g.tapP == 3) issue_taps<7, 3>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc);
-        else if (g.tapT == 4 && g.tapP == 3) issue_taps<4, 3>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc);
-        else if (g.tapT == 9 && g.tapP == 3) issue_taps<9, 3>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc);
+        if (g.tapT == 3 && g.tapP == 1) { if (merge) issue_taps<3, 1, true>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc, idesc2); else issue_taps<3, 1, false>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc, idesc2); }
+        else if (g.tapT == 7 && g.tapP == 3) { if (merge) issue_taps<7, 3, true>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc, idesc2); else issue_taps<7, 3, false>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc, idesc2); }
+        else if (g.tapT == 4 && g.tapP == 3) { if (merge) issue_taps<4, 3, true>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc, idesc2); else issue_taps<4, 3, false>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc, idesc2); }
+        else if (g.tapT == 9 && g.tapP == 3) { if (merge) issue_taps<9, 3, true>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc, idesc2); else issue_taps<9, 3, false>(acc, acc2, a0d, b0d, a16, b16, sw16, ksteps_c, idesc, idesc2); }
         else {
           int pz = 0, m = 0;                              // tap tp = tapP * m + pz
           for (int tp = 0; tp < g.tapT; tp++) {
@@ -340,9 +346,14 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             for (int k4 = 0; k4 < ksteps_c; k4++) {
               const uint64_t o = (uint64_t)(k4 * 2);
               const uint32_t first = (tp > 0 || k4 > 0) ? 1u : 0u;
-              mma_bf16(acc, ah + o, bh + o, idesc, first);
-              mma_bf16(acc2, al + o, bh + o, idesc, first);
-              mma_bf16(acc2, ah + o, bl + o, idesc, 1u);
+              if (merge) {
+                mma_bf16(acc, ah + o, bh + o, idesc2, first);
+                mma_bf16(acc2, al + o, bh + o, idesc, 1u);
+              } else {
+                mma_bf16(acc, ah + o, bh + o, idesc, first);
+                mma_bf16(acc2, ah + o, bl + o, idesc, first);
+                mma_bf16(acc2, al + o, bh + o, idesc, 1u);
+              }
             }
             if (++pz == g.tapP) { pz = 0; m++; }
           }
@@ -396,6 +407,8 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
     const uint32_t idesc = make_idesc(g.BN, false, PAIR ? 2 * BM : BM);
+    const uint32_t idesc_m = make_idesc(2 * g.BN, false, BM);          // (merge: single-CTA forms only)
+    const bool merge_w = g.merge != 0;
     const uint64_t dbase = sdesc_base(0, sw);
     RingPos sp(g.stages), ap(g.acc_sets);
     for (int t = (PAIR && rank != 0u) ? total_tiles : NPVC_TILE0; t < total_tiles; t += NPVC_TILE_STEP, ap.advance()) {   // (PAIR: the leader issues for both CTAs)
@@ -416,19 +429,28 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
               const uint64_t o = (uint64_t)(k4 * 2);
               const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
               mma_bf16_pair(acc, ah + o, bh + o, idesc, first);
-              mma_bf16_pair(acc2, al + o, bh + o, idesc, first);
-              mma_bf16_pair(acc2, ah + o, bl + o, idesc, 1u);
+              mma_bf16_pair(acc2, ah + o, bl + o, idesc, first);      // (the accumulation order of the merged single-CTA form)
+              mma_bf16_pair(acc2, al + o, bh + o, idesc, 1u);
             }
             umma_commit_pair(empty_bar(s));             // frees the stage in both CTAs
             if (kb == g.kblocks - 1) umma_commit_pair(accf_bar(buf));
           }
         } else if (elect_one()) {
-          for (int k4 = 0; k4 < ksteps; k4++) {             // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr >> 4) field
-            const uint64_t o = (uint64_t)(k4 * 2);
-            const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
-            mma_bf16(acc, ah + o, bh + o, idesc, first);         // main products
-            mma_bf16(acc2, al + o, bh + o, idesc, first);        // corrections: separate accumulator
-            mma_bf16(acc2, ah + o, bl + o, idesc, 1u);           //  (tensor-core fp32 accumulation truncates)
+          if (merge_w) {
+            for (int k4 = 0; k4 < ksteps; k4++) {           // UMMA_K = 16 bf16 = 32 bytes -> +2 in the (addr >> 4) field
+              const uint64_t o = (uint64_t)(k4 * 2);
+              const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
+              mma_bf16(acc, ah + o, bh + o, idesc_m, first);     // Ah.[Bh | Bl] -> main | correction accumulators (N = 2 BN)
+              mma_bf16(acc2, al + o, bh + o, idesc, 1u);         // + Al.Bh
+            }
+          } else {
+            for (int k4 = 0; k4 < ksteps; k4++) {
+              const uint64_t o = (uint64_t)(k4 * 2);
+              const uint32_t first = (kb > 0 || k4 > 0) ? 1u : 0u;
+              mma_bf16(acc, ah + o, bh + o, idesc, first);         // main products
+              mma_bf16(acc2, ah + o, bl + o, idesc, first);        // corrections: separate accumulator
+              mma_bf16(acc2, al + o, bh + o, idesc, 1u);           //  (tensor-core fp32 accumulation truncates)
+            }
           }
           umma_commit(empty_bar(s));                  // frees the smem stage when these MMAs retire
           if (kb == g.kblocks - 1) umma_commit(accf_bar(buf));
@@ -813,6 +835,7 @@ umma_wgrad_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
     const uint32_t idesc = make_idesc(g.BN, true, PAIR ? 2 * BM : BM);
+    const uint32_t idesc_m = make_idesc(2 * g.BN, true, BM);           // (merge: single-CTA form only)
     const int ksteps = g.rows_al >> 4;
     const uint64_t abase = sdesc_base(a_region, 128), dbase = sdesc_base(d_region, (uint32_t)g.d_sw);
     const uint32_t acc2 = tmem_base + (uint32_t)g.BN;
@@ -831,19 +854,28 @@ umma_wgrad_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             const uint64_t ah = ah0 + astep * ks, al = al0 + astep * ks, dh = dh0 + dstep * ks, dl = dl0 + dstep * ks;
             const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
             mma_bf16_pair(tmem_base, ah, dh, idesc, first);
-            mma_bf16_pair(acc2, al, dh, idesc, first);
-            mma_bf16_pair(acc2, ah, dl, idesc, 1u);
+            mma_bf16_pair(acc2, ah, dl, idesc, first);
+            mma_bf16_pair(acc2, al, dh, idesc, 1u);
           }
           umma_commit_pair(empty_bar(s));
           if (i == ntl - 1) umma_commit_pair(accum_bar);
         }
       } else if (elect_one()) {
-        for (int ks = 0; ks < ksteps; ks++) {
-          const uint64_t ah = ah0 + astep * ks, al = al0 + astep * ks, dh = dh0 + dstep * ks, dl = dl0 + dstep * ks;
-          const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
-          mma_bf16(tmem_base, ah, dh, idesc, first);          // main products
-          mma_bf16(acc2, al, dh, idesc, first);               // corrections
-          mma_bf16(acc2, ah, dl, idesc, 1u);
+        if (g.merge) {
+          for (int ks = 0; ks < ksteps; ks++) {
+            const uint64_t ah = ah0 + astep * ks, al = al0 + astep * ks, dh = dh0 + dstep * ks;
+            const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+            mma_bf16(tmem_base, ah, dh, idesc_m, first);      // Ah^T.[Dh | Dl] -> main | correction accumulators (N = 2 BN)
+            mma_bf16(acc2, al, dh, idesc, 1u);                // + Al^T.Dh
+          }
+        } else {
+          for (int ks = 0; ks < ksteps; ks++) {
+            const uint64_t ah = ah0 + astep * ks, al = al0 + astep * ks, dh = dh0 + dstep * ks, dl = dl0 + dstep * ks;
+            const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+            mma_bf16(tmem_base, ah, dh, idesc, first);          // main products
+            mma_bf16(acc2, ah, dl, idesc, first);               // corrections
+            mma_bf16(acc2, al, dh, idesc, 1u);
+          }
         }
         umma_commit(empty_bar(s));
         if (i == ntl - 1) umma_commit(accum_bar);
