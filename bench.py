@@ -372,19 +372,22 @@ def main():
     # clocks / throttle reasons are sampled (nvidia-smi, 20 ms period) from the first warm-up step on, through the timed
     # steps and through the same load repeated for >= 0.4 s afterwards (a 20-step timed region lasts < 0.1 s)
     sampler = ClockSampler(local); sampler.start()
-    t_w = time.perf_counter()
-    i = 0
-    while i < args.warmup or (time.perf_counter() - t_w < 0.25 and i < 2000):
-        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]); i += 1
-        if i >= args.warmup:
-            torch.cuda.synchronize()
+    for i in range(args.warmup):
+        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL])
+    # how many steps make ~0.3 s of load: measured once, agreed across ranks (every rank must run the SAME number of steps --
+    # a step contains a collective)
+    est = torch.tensor([timed(lambda i: step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]), 3) / 3.0], device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    n_load = int(max(5, min(2000, 300.0 / max(float(est), 1e-3))))
+    for i in range(n_load):
+        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL])
     t0 = sampler.mark()
     ms = timed(lambda i: step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]), args.steps)
     t1 = sampler.mark()
-    t_l = time.perf_counter(); i = 0
-    while time.perf_counter() - t_l < 0.4 and i < 4000:
-        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]); i += 1
-        torch.cuda.synchronize()
+    for i in range(n_load):
+        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL])
+    torch.cuda.synchronize()
     clocks = sampler.stop(t0, t1)
     value = world * n * args.steps / (ms / 1000.0)
     graphed = bool(trainer is not None and trainer._state and any(q["graph"] is not None for q in trainer._state["graphs"].values()))

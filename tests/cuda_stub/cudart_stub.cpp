@@ -155,6 +155,11 @@ cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKin
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) {
   log_op(3, (uint64_t)(uintptr_t)st, 0, (uint64_t)(uintptr_t)d, n); memset(d, v, n); return cudaSuccess;
 }
+cudaError_t cudaMemset2DAsync(void* d, size_t pitch, int v, size_t w, size_t hgt, cudaStream_t st) {
+  log_op(3, (uint64_t)(uintptr_t)st, 0, (uint64_t)(uintptr_t)d, hgt ? (hgt - 1) * pitch + w : 0);      // extent touched: the workspace-bounds checks see it
+  for (size_t r = 0; r < hgt; r++) memset((char*)d + r * pitch, v, w);
+  return cudaSuccess;
+}
 cudaError_t cudaFuncSetAttribute(const void*, enum cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)(uintptr_t)(g_next_handle++); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

@@ -596,6 +596,21 @@ int launch_e0_bwd(Ctx& c, const Op& o, const Op& nx) {      // o: OP_LN_BWD of t
   return NPVC_OK;
 }
 
+// speaker branch backward (kernels.cuh, speaker_bwd_kernel): w = wgrad_merge_y, d = dgrad_emb, cs = colsum_dptab
+int launch_speaker_bwd(Ctx& c, const Op& w, const Op& d, const Op& cs) {
+  npvc_handle* h = c.h;
+  const int S = (int)w.rows_fixed, Z = w.K, Nm = w.N;
+  if (d.K != Nm || d.N != Z || cs.i0 != Nm || w.ldb != Nm || d.ldb != Z) return fail(NPVC_ERR_ARG, "speaker backward: unexpected plan shapes");
+  const float* dP = resolve(c, w.C.ref) + w.C.off;                 // per-speaker sums of the merge gradient [S, Nm]
+  const float* emb = resolve(c, w.A.ref) + w.A.off;
+  const int nA = (Nm + 255) / 256, nB = (Nm + SPK_CH - 1) / SPK_CH;
+  const size_t sm = (size_t)S * (Z > SPK_CH ? Z : SPK_CH) * sizeof(float);
+  launch_k(speaker_bwd_kernel, dim3((unsigned)(nA + nB)), dim3(256), sm, c.st, dP, emb, (int)w.A.fs, resolve(c, d.B), resolve(c, w.B),
+           resolve(c, d.C.ref) + d.C.off, (int)d.C.fs, resolve(c, cs.r1), S, Z, Nm, nA);
+  h->launches++;
+  return NPVC_OK;
+}
+
 bool umma_allowed(const npvc_handle* h, const Op& o) {
   if (!o.umma || !h->encode) return false;
   if (h->umma_allow.empty()) return true;
@@ -777,6 +792,18 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
     }
     case OP_ZERO: {
       long long cnt = o.per_frame_count ? o.count * c.n : o.count;
+      if (o.per_frame_count && o.i1 > 0 && o.r0.space == SP_WS && p.bufs[o.r0.buf].split && c.n > 0) {
+        // only the pads: a frame is [hi plane: count bf16][lo plane: count bf16], the interior [i0, i0 + i1) of each plane is written
+        // by the producing GEMM -- four strided memsets of the pad columns instead of the whole buffer
+        uint8_t* base = reinterpret_cast<uint8_t*>(resolve(c, o.r0));
+        const size_t pitch = (size_t)o.count * 4, plane = (size_t)o.count * 2;
+        const size_t front = (size_t)o.i0 * 2, back0 = (size_t)(o.i0 + o.i1) * 2, back = plane - back0;
+        for (int pl = 0; pl < 2; pl++) {
+          if (front) CUDA_TRY(cudaMemset2DAsync(base + pl * plane, pitch, 0, front, (size_t)c.n, st));
+          if (back) CUDA_TRY(cudaMemset2DAsync(base + pl * plane + back0, pitch, 0, back, (size_t)c.n, st));
+        }
+        break;
+      }
       CUDA_TRY(cudaMemsetAsync(resolve(c, o.r0), 0, (size_t)cnt * sizeof(float), st));
       break;
     }
@@ -823,12 +850,14 @@ int run_phase(Ctx& c, int phase) {
       rc = launch_e0_fwd(c, o, ops[i + 1]); i++;
     } else if (o.fuse == FUSE_E0_BWD) {
       rc = launch_e0_bwd(c, o, ops[i + 1]); i++;
+    } else if (o.fuse == FUSE_SPK_BWD) {
+      rc = launch_speaker_bwd(c, o, ops[i + 1], ops[i + 2]); i += 2;
     } else if (o.fuse == FUSE_LN_FWD) {              // Layernorm in the GEMM's epilogue when the tiling allows it
       bool fused = false;
       rc = run_op(c, o, (int)i, &ops[i + 1], &fused);
       if (fused) i++;
     } else rc = run_op(c, o, (int)i);
-    if (rc == NPVC_OK && (o.fuse == FUSE_E0_FWD || o.fuse == FUSE_E0_BWD)) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = fail(NPVC_ERR_CUDA, "launch " + o.name + " (fused): " + cudaGetErrorString(e)); }
+    if (rc == NPVC_OK && (o.fuse == FUSE_E0_FWD || o.fuse == FUSE_E0_BWD || o.fuse == FUSE_SPK_BWD)) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = fail(NPVC_ERR_CUDA, "launch " + o.name + " (fused): " + cudaGetErrorString(e)); }
     if (h->nvtx) nvtxRangePop();
     c.st = main_st;
     if (h->profiling) { cudaEventRecord(ev.b, c.st); h->events.push_back(ev); }

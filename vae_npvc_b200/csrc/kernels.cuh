@@ -519,6 +519,48 @@ __global__ void __launch_bounds__(256) fewrows_fwd_kernel(const float* A, int ld
   for (int r = 0; r < 16; r++) if (r < R) C[(long long)r * ldc + n] = acc[r] + bs;
 }
 
+// Speaker-branch backward, once per call (model/vae.py:51-70: embedding lookup -> fully_connected_1 -> + biases, hoisted
+// per speaker): from the per-speaker sums dP[S, Nm] of the merge gradient (rows z.. of the merge weight gradient)
+//   blocks [0, nA):   dW_y[k, n] += sum_s emb[s, k] dP[s, n]   and   dbias[n] += sum_s dP[s, n]       (thread = column n)
+//   blocks [nA, ..):  demb[s, d] += sum_n dP[s, n] W_y^T[n, d]  over a chunk of 32 columns             (thread = (s, d) pairs)
+// One launch instead of three latency-bound ones (a 10-row weight gradient, a 10-row GEMM with K = 1672, a column sum).
+constexpr int SPK_CH = 32;
+__global__ void __launch_bounds__(256) speaker_bwd_kernel(const float* dP, const float* emb, int lde, const float* WyT, float* dWy, float* demb, int ldd,
+                                                          float* dbias, int S, int Z, int Nm, int nA) {
+  pdl_prologue();
+  extern __shared__ float ssm[];                   // role A: emb [S][Z]; role B: dP chunk [S][SPK_CH]
+  if ((int)blockIdx.x < nA) {
+    for (int i = threadIdx.x; i < S * Z; i += blockDim.x) ssm[i] = emb[(long long)(i / Z) * lde + (i % Z)];
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= Nm) return;
+    float dp[16]; float cs = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; r++) { dp[r] = (r < S) ? dP[(long long)r * Nm + n] : 0.f; cs += dp[r]; }
+    dbias[n] += cs;
+    for (int k = 0; k < Z; k++) {
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; r++) if (r < S) a = fmaf(ssm[r * Z + k], dp[r], a);
+      dWy[(long long)k * Nm + n] += a;
+    }
+  } else {
+    const int n0 = ((int)blockIdx.x - nA) * SPK_CH;
+    for (int i = threadIdx.x; i < S * SPK_CH; i += blockDim.x) {
+      const int r = i / SPK_CH, n = n0 + i % SPK_CH;
+      ssm[i] = (n < Nm) ? dP[(long long)r * Nm + n] : 0.f;
+    }
+    __syncthreads();
+    const int nn = min(SPK_CH, Nm - n0);
+    for (int pq = threadIdx.x; pq < S * Z; pq += blockDim.x) {          // consecutive threads = consecutive d: W_y^T rows read coalesced
+      const int r = pq / Z, d = pq % Z;
+      float a = 0.f;
+      for (int j = 0; j < nn; j++) a = fmaf(ssm[r * SPK_CH + j], WyT[(long long)(n0 + j) * Z + d], a);
+      atomicAdd(&demb[(long long)r * ldd + d], a);
+    }
+  }
+}
+
 // =============================================================================================
 // (W) for tiny K x N (first layer: 7 taps x 16 channels) and millions of rows: every thread keeps
 // the whole K x N gradient in registers over its rows, one block reduction + K*N atomics per block.

@@ -437,7 +437,9 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
     o.r0 = B.ws(p.buf_hz); o.r1 = B.ws(p.buf_mu); o.r2 = B.ws(p.buf_lv); o.r3 = B.ws(p.buf_z); o.i0 = z;
   }
   // generator  (model/vae.py:84-103)
-  { Op& o = B.op(OP_ZERO, PH_DEC, "zero_hm"); o.r0 = B.ws(b_hm); o.count = hm_flen; o.per_frame_count = 1; }
+  // zero padding of the merge output (the merge GEMM writes the interior [hm_off, hm_off + Nm) of every frame): i0 / i1 = the
+  // interior, so only the pads around it need clearing
+  { Op& o = B.op(OP_ZERO, PH_DEC, "zero_hm"); o.r0 = B.ws(b_hm); o.count = hm_flen; o.per_frame_count = 1; o.i0 = hm_off; o.i1 = Nm; }
   {  // zs = [z | one-hot(y)]  (model/vae.py:64-70,89-90: embedding lookup + the two FCs of _merge)
     Op& o = B.op(OP_ZCAT, PH_DEC, "zcat"); o.r0 = B.ws(p.buf_z); o.r1 = B.ws(b_zs); o.i0 = z; o.i1 = ypad;
   }
@@ -568,6 +570,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
     Op& o = B.op(OP_GEMM, PH_FINAL, "dgrad_emb"); o.rows_fixed = a.y_dim; o.A = V_dptab; o.K = Nm;
     o.B = B.aw(A_bzd[1]); o.ldb = z; o.N = z; o.C = B.view(B.gr(poff(P_emb)), 1, z, 0, 0, z);
     Op& c = B.op(OP_COLSUM, PH_FINAL, "colsum_dptab"); c.r0 = B.adw(A_bz[0] + (int64_t)z * Nm); c.r1 = B.adw(A_bm[0]); c.i0 = Nm; c.i1 = a.y_dim;
+    if (fuse && a.y_dim <= 16) p.ops[p.ops.size() - 3].fuse = FUSE_SPK_BWD;      // wgrad_merge_y + dgrad_emb + colsum_dptab
     Op& u = B.op(OP_UNPACK, PH_FINAL, "unpack"); u.count = p.n_params;
   }
 

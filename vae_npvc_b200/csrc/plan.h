@@ -35,7 +35,9 @@ enum OpKind {
 //                conv output is consumed in registers, its buffer is never materialised (Buf::elide)
 //   FUSE_LN_FWD  a conv / transposed-conv GEMM + the Layernorm / lrelu that follows it: done in the GEMM kernel's
 //                epilogue when a tile holds whole frames (decided per launch; otherwise the two ops run separately)
-enum Fuse { FUSE_NONE = 0, FUSE_E0_FWD = 1, FUSE_E0_BWD = 2, FUSE_LN_FWD = 3 };
+//   FUSE_SPK_BWD the three once-per-call ops of the speaker branch's backward (weight gradient of the per-speaker FC,
+//                embedding gradient, bias column sums): this op and the next TWO as one kernel
+enum Fuse { FUSE_NONE = 0, FUSE_E0_FWD = 1, FUSE_E0_BWD = 2, FUSE_LN_FWD = 3, FUSE_SPK_BWD = 4 };
 
 struct Ref {
   int space = SP_NONE;
