@@ -208,11 +208,12 @@ def rank_roster(world, local):
 
 
 def nccl_evidence(world):
-    """NCCL_DEBUG=INFO goes to files under the repo (stdout stays ONE JSON line); afterwards rank 0 echoes the
-    communicator lines (nranks / nNodes / algorithm) to stderr so the rank count of the run is observable."""
+    """When the caller sent NCCL's debug output to files (NCCL_DEBUG_FILE), rank 0 echoes the communicator lines
+    (nranks / algorithm) to stderr; by default NCCL_DEBUG=INFO already lands on stderr (see main)."""
     out = []
-    print("[nccl] debug files: %s" % sorted(os.path.basename(p) for p in glob.glob(os.path.join(ROOT, "gpurun_out", "nccl_debug.*"))), file=sys.stderr)
-    for p in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "nccl_debug.*.log"))):
+    pat = os.environ.get("NCCL_DEBUG_FILE", "")
+    files = sorted(glob.glob(re.sub(r"%[hp]", "*", pat))) if pat else []
+    for p in files:
         try:
             for ln in open(p, errors="replace"):
                 if re.search(r"nranks \d+|nRanks \d+|NVLS|Connected all (rings|trees)", ln):
@@ -222,7 +223,7 @@ def nccl_evidence(world):
     for ln in out[:40]:
         print("[nccl] " + ln, file=sys.stderr)
     n = sorted({int(m.group(1)) for ln in out for m in [re.search(r"n[rR]anks (\d+)", ln)] if m})
-    return {"nranks_seen": n, "lines": len(out), "log": "gpurun_out/nccl_debug.<host>.<pid>.log"}
+    return {"nranks_seen": n, "lines": len(out), "log": pat or "stderr (NCCL_DEBUG=INFO, subsystem INIT)"}
 
 
 def op_rooflines(prof, pk, steps):
@@ -290,24 +291,22 @@ def main():
     import torch.distributed as dist
     from vae_npvc_b200 import vcc2016_vae_arch
     from importlib import import_module
+    real_stdout = sys.stdout
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the native arm")
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local)
     if world > 1:
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")           # rank evidence; into files: stdout carries the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log"))
-        # NCCL prints its version banner on stdout when the first communicator comes up: stdout must carry ONE JSON line,
-        # so file descriptor 1 points at stderr until a first collective has run
+        # Rank evidence: NCCL_DEBUG=INFO (communicator lines: "... rank r nranks N ..."), left where NCCL writes it by default.
+        # That default is STDOUT, which must carry ONE JSON line -- so for the whole run file descriptor 1 points at stderr
+        # (NCCL's lines land there) and the JSON line is written to the saved, real stdout at the end.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         sys.stdout.flush()
-        saved_fd = os.dup(1); os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            t = torch.ones(1, device=torch.device("cuda", local)); dist.all_reduce(t); torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
+        real_stdout = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        t = torch.ones(1, device=torch.device("cuda", local)); dist.all_reduce(t); torch.cuda.synchronize()
     dev = torch.device("cuda", local)
     cfg = CONFIGS[args.config]
     kind, n = cfg["kind"], cfg["frames"]
@@ -493,7 +492,7 @@ def main():
         }
         if nccl:
             line["nccl"] = nccl
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
     if world > 1:
         # CUDA graphs that captured NCCL kernels go before the communicator; a communicator teardown that does not
         # return (seen once with captured collectives) must not hang the run: the line is out, leave after 20 s

@@ -371,12 +371,12 @@ def test_cta_pair_form_is_bit_identical_to_single_cta(arch, monkeypatch):
     assert torch.isfinite(g2).all() and rel(g2, g1.cpu().numpy()) < 1e-5
 
 
-EXPERIMENTS = {                    # library switches written without a GPU (DESIGN.md "Next"): run with NPVC_TEST_EXPERIMENTS=1
-    "wgrad_pair": {"NPVC_WGRAD_PAIR": "1"}, "wgrad_pair_256": {"NPVC_WGRAD_PAIR": "2"},
+EXPERIMENTS = {                    # A/B switches of the library: every form they select must reproduce the default engine
+    "wgrad_pair": {"NPVC_WGRAD_PAIR": "1"}, "wgrad_pair_256": {"NPVC_WGRAD_PAIR": "2"}, "wgrad_single": {"NPVC_WGRAD_PAIR": "0"},
+    "no_merge": {"NPVC_UMMA_MERGE": "0"}, "no_pdl": {"NPVC_PDL": "0"},
 }
 
 
-@pytest.mark.skipif(not os.environ.get("NPVC_TEST_EXPERIMENTS"), reason="switches that have not been measured yet: opt-in")
 @pytest.mark.parametrize("name", sorted(EXPERIMENTS))
 @pytest.mark.parametrize("n", [300, 16384])
 def test_experimental_switch_matches_default(arch, monkeypatch, name, n):

@@ -193,8 +193,10 @@ def test_default_rule_pairs_only_the_measured_shapes():
     dgrad (BN >= 128, >= 8 k-blocks, >= 64 M tiles); small batches keep the single-CTA form."""
     arch = vcc2016_vae_arch()
     big = HS.record_loss_fwd_bwd(arch, 16384)
-    pairs = sorted((L["umma"]["K"], L["umma"]["N"]) for L in big.launches if L["cluster_x"] == 2)
+    pairs = sorted((L["umma"]["K"], L["umma"]["N"]) for L in big.launches if L["cluster_x"] == 2 and "umma_fwd" in L["name"])
     assert pairs == sorted([(4104, 513), (513, 4104), (896, 256), (768, 256), (768, 384), (1672, 128)]), pairs
+    wpairs = [(L["umma"]["K"], L["umma"]["N"]) for L in big.launches if L["cluster_x"] == 2 and "umma_wgrad" in L["name"]]
+    assert wpairs == [(4104, 513)], wpairs                     # the pair weight-gradient kernel: the last generator layer only
     small = HS.record_loss_fwd_bwd(arch, 64)
     assert not any(L["cluster_x"] == 2 for L in small.launches)
 

@@ -48,8 +48,8 @@ struct npvc_handle {
   bool attr_fwd_ln = false;
   int umma_pair = 1;                 // NPVC_PAIR=0: no cta_group::2 CTA pairs; 2: every BN >= 128 layer (A/B comparisons)
   std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the shape rule)
-  int wgrad_pair = 0;                // NPVC_WGRAD_PAIR=1|2: cta_group::2 form of the weight-gradient kernel for N >= 128 (2: 256-column
-                                     // N tiles); opt-in: compiled and reviewed, NOT yet run on a GPU (round-2 experiment)
+  int wgrad_pair = -1;               // cta_group::2 form of the weight-gradient kernel: -1 (default) where it measured faster (launch_umma_wgrad),
+                                     // NPVC_WGRAD_PAIR=0 never, 1 every N >= 128 layer, 2 the same with 256-column N tiles (A/B comparisons)
   bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
   int64_t umma_launches = 0;
   int ln_bulk = 1;                   // NPVC_LN_BULK=0: shared-memory Layernorm backward for large frames (A/B comparisons)
@@ -465,7 +465,11 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
   const long long frames = c.n;
   // N tile: 16 / 32 columns in one 32B / 64B-swizzled box, else 64-column boxes (128B swizzle)
   int BN, n_tiles = 1, d_sw;
-  const bool pair = h->wgrad_pair > 0 && o.N >= 128 && o.K > 128;      // (>= 2 K tiles, whole 64-column boxes per CTA)
+  // CTA-pair form (cta_group::2, 256 x BN MMAs, each CTA half of the dC columns): measured on the B200 (profiles/
+  // r2q_wgrad_pair.txt) it wins only where both dimensions are large -- the 4104 x 513 gradient of the last generator layer
+  // (0.284 -> 0.257 ms) -- and loses on 896 x 256 / 144 x 1672 (E4, merge).  NPVC_WGRAD_PAIR=0 off, 1 / 2 everywhere it fits.
+  const bool pair_shape = o.N >= 128 && o.K > 128;                     // (>= 2 K tiles, whole 64-column boxes per CTA)
+  const bool pair = pair_shape && (h->wgrad_pair > 0 || (h->wgrad_pair < 0 && h->umma_pair != 0 && o.K >= 2048 && o.N >= 512 && frames * o.A.R >= 4096));
   if (pair) {
     d_sw = 128;
     const int t128 = (o.N + 127) / 128, t256 = (o.N + 255) / 256;
@@ -541,7 +545,14 @@ int launch_umma_wgrad(Ctx& c, const Op& o, int op_index) {
     cudaLaunchAttribute at[2]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_wgrad_pair_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g));
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, umma_wgrad_pair_kernel, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+    if (le != cudaSuccess) {
+      if (h->wgrad_pair > 0) return fail(NPVC_ERR_CUDA, std::string("cluster launch of the pair weight-gradient kernel: ") + cudaGetErrorString(le));
+      // default rule and the cluster launch was refused (a device / partition that cannot co-schedule two such CTAs): the
+      // single-CTA form from now on (as the forward kernel does)
+      cudaGetLastError(); h->wgrad_pair = 0;
+      return launch_umma_wgrad(c, o, op_index);
+    }
     h->launches++; h->umma_launches++;
     return NPVC_OK;
   }
@@ -792,15 +803,14 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
     }
     case OP_ZERO: {
       long long cnt = o.per_frame_count ? o.count * c.n : o.count;
-      if (o.per_frame_count && o.i1 > 0 && o.r0.space == SP_WS && p.bufs[o.r0.buf].split && c.n > 0) {
-        // only the pads: a frame is [hi plane: count bf16][lo plane: count bf16], the interior [i0, i0 + i1) of each plane is written
-        // by the producing GEMM -- four strided memsets of the pad columns instead of the whole buffer
-        uint8_t* base = reinterpret_cast<uint8_t*>(resolve(c, o.r0));
-        const size_t pitch = (size_t)o.count * 4, plane = (size_t)o.count * 2;
-        const size_t front = (size_t)o.i0 * 2, back0 = (size_t)(o.i0 + o.i1) * 2, back = plane - back0;
-        for (int pl = 0; pl < 2; pl++) {
-          if (front) CUDA_TRY(cudaMemset2DAsync(base + pl * plane, pitch, 0, front, (size_t)c.n, st));
-          if (back) CUDA_TRY(cudaMemset2DAsync(base + pl * plane + back0, pitch, 0, back, (size_t)c.n, st));
+      if (o.per_frame_count && o.i1 > 0 && o.r0.space == SP_WS && p.bufs[o.r0.buf].split && c.n > 0 &&
+          o.i0 % 8 == 0 && o.i1 % 8 == 0 && o.count % 8 == 0) {
+        // only the pads: a frame is [hi plane: count bf16][lo plane: count bf16]; the interior [i0, i0 + i1) of each plane is
+        // written by the producing GEMM
+        const long long per = 2LL * ((o.i0 >> 3) + ((o.count - o.i0 - o.i1) >> 3)), tot = per * c.n;
+        if (tot > 0) {
+          launch_k(zero_pads_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, reinterpret_cast<uint16_t*>(resolve(c, o.r0)), (int)o.count, o.i0, o.i1, (long long)c.n);
+          h->launches++;
         }
         break;
       }
@@ -946,7 +956,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
   if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
-  if (const char* pd = getenv("NPVC_PDL")) g_pdl = atoi(pd) ? 1 : 0;
+  { const char* pd = getenv("NPVC_PDL"); g_pdl = (pd && !atoi(pd)) ? 0 : 1; }      // (process-wide: the launch helper has no handle)
   if (const char* nv = getenv("NPVC_NVTX")) h->nvtx = atoi(nv);
   if (const char* mg = getenv("NPVC_UMMA_MERGE")) h->umma_merge = atoi(mg);
   if (const char* fl = getenv("NPVC_FUSE_LN_TRAIN")) h->fuse_ln_train = atoi(fl);

@@ -538,11 +538,11 @@ __global__ void __launch_bounds__(256) speaker_bwd_kernel(const float* dP, const
 #pragma unroll
     for (int r = 0; r < 16; r++) { dp[r] = (r < S) ? dP[(long long)r * Nm + n] : 0.f; cs += dp[r]; }
     dbias[n] += cs;
-    for (int k = 0; k < Z; k++) {
-      float a = 0.f;
+    for (int k = 0; k < Z; k++) {                    // plain stores: this launch is the only writer of dW_y (zeroed per call, one launch per call);
+      float a = 0.f;                                 // a read-modify-write here is 128 dependent L2 round trips per thread
 #pragma unroll
       for (int r = 0; r < 16; r++) if (r < S) a = fmaf(ssm[r * Z + k], dp[r], a);
-      dWy[(long long)k * Nm + n] += a;
+      dWy[(long long)k * Nm + n] = a;
     }
   } else {
     const int n0 = ((int)blockIdx.x - nA) * SPK_CH;
@@ -1236,6 +1236,19 @@ __global__ void philox_normal_kernel(const StepState* st, long long frame0, floa
   pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n * z) out[i] = philox_normal(st->seed, (unsigned long long)st->draws, (unsigned long long)(frame0 + i / z), (uint32_t)(i % z));
+}
+
+// Zero pads of a split (bf16 hi / lo planes) per-frame buffer whose interior [i0, i0 + i1) is written by the producing
+// GEMM: only the pad elements [0, i0) and [i0 + i1, flen) of both planes are cleared (all multiples of 8 elements).
+__global__ void zero_pads_kernel(uint16_t* buf, int flen, int i0, int i1, long long frames) {
+  pdl_prologue();
+  const int front8 = i0 >> 3, back8 = (flen - i0 - i1) >> 3, per = 2 * (front8 + back8);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= frames * per) return;
+  const long long f = i / per; int q = (int)(i - f * per);
+  const int plane = q / (front8 + back8); q -= plane * (front8 + back8);
+  const int e = (q < front8) ? 8 * q : i0 + i1 + 8 * (q - front8);
+  *reinterpret_cast<uint4*>(buf + f * 2 * flen + (long long)plane * flen + e) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // GaussianSampleLayer alone (util/layers.py:152-156)
