@@ -369,25 +369,15 @@ def main():
 
     # ---- device-resident arm: inputs already in HBM ------------------------------------------
     # clocks / throttle reasons are sampled (nvidia-smi, 20 ms period) from the first warm-up step on, through the timed
-    # steps and through the same load repeated for >= 0.4 s afterwards (a 20-step timed region lasts < 0.1 s)
+    # steps, the end-to-end arm, and the same load repeated for ~0.3 s AFTER both (a 20-step timed region lasts < 0.1 s: a
+    # handful of samples; the follow-on load shows what the clocks settle to -- it does not precede the timed steps, which run
+    # after exactly W warm-up steps as the contract says)
     sampler = ClockSampler(local); sampler.start()
     for i in range(args.warmup):
-        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL])
-    # how many steps make ~0.3 s of load: measured once, agreed across ranks (every rank must run the SAME number of steps --
-    # a step contains a collective)
-    est = torch.tensor([timed(lambda i: step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]), 3) / 3.0], device=dev)
-    if world > 1:
-        dist.all_reduce(est, op=dist.ReduceOp.MAX)
-    n_load = int(max(5, min(2000, 300.0 / max(float(est), 1e-3))))
-    for i in range(n_load):
         step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL])
     t0 = sampler.mark()
     ms = timed(lambda i: step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL]), args.steps)
     t1 = sampler.mark()
-    for i in range(n_load):
-        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL])
-    torch.cuda.synchronize()
-    clocks = sampler.stop(t0, t1)
     value = world * n * args.steps / (ms / 1000.0)
     graphed = bool(trainer is not None and trainer._state and any(q["graph"] is not None for q in trainer._state["graphs"].values()))
 
@@ -425,6 +415,12 @@ def main():
     for k in range(2):
         consumed[k].record(torch.cuda.current_stream())
     ms_e2e = timed(e2e_step, args.steps)
+    # every rank must run the SAME number of follow-on steps (a step contains a collective): derived from the agreed `ms`
+    n_load = int(max(5, min(2000, 300.0 / max(ms / args.steps, 1e-3))))
+    for i in range(n_load):
+        step_fn(dev_x[i % NPOOL], dev_y[i % NPOOL])
+    torch.cuda.synchronize()
+    clocks = sampler.stop(t0, t1)
     e2e = world * n * args.steps / (ms_e2e / 1000.0)
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
     d2h = out_host.numel() * 4

@@ -106,3 +106,25 @@ def test_graph_replay_equals_eager_steps(arch, monkeypatch, n):
     assert d < 8 * 1e-4 * 1.5, d
     assert float((res["0"][1] - res["1"][1]).abs().max() / res["0"][1].abs().max()) < 1e-4
     assert bool(torch.isfinite(res["1"][1]).all())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_engine_on_a_non_current_device(arch):
+    """Engine(device='cuda:1') while cuda:0 is current: every library call must run with the engine's device current (its
+    device tables, kernel attributes and launches are bound to the current device) and on that device's stream."""
+    from oracle import convvae_ref as R
+    from vae_npvc_b200.engine import Engine
+    torch.cuda.set_device(0)
+    e1 = Engine(arch, "cuda:1")
+    P = R.init_params(arch, 0)
+    x, y, eps = R.make_inputs(arch, 8)
+    d = torch.device("cuda:1")
+    theta = torch.tensor(R.flatten_params(arch, P), device=d)
+    grad = torch.empty_like(theta)
+    out = e1.loss_fwd_bwd(theta, torch.tensor(x, dtype=torch.float32, device=d), torch.tensor(y, device=d),
+                          torch.tensor(eps, dtype=torch.float32, device=d), grad=grad)
+    torch.cuda.synchronize(d)
+    assert torch.cuda.current_device() == 0 and out["xh"].device == d
+    ref = R.forward(arch, P, x, y, eps)
+    assert float(np.abs(out["xh"].cpu().numpy() - ref["xh"]).max() / np.abs(ref["xh"]).max()) < 1e-4
+    assert bool(torch.isfinite(grad).all())
