@@ -669,16 +669,32 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           }
         } else {                                                              // edges: N tail, predicated range, odd alignment
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int n4 = nb + 4 * q;
-            if (al16 && n4 >= n_lo && n4 + 4 <= n_hi) {
-              if (g.C.split) split_st4(chp + n4, g.C.fs, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
-              else *reinterpret_cast<float4*>(cp + n4) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-            } else {
+          for (int h8 = 0; h8 < 2; h8++) {
+            // a whole aligned 8-column half (N = 24, 40, 88 ... end in one): one 32-byte fp32 store / one 16-byte store per plane,
+            // or nothing at all when the half lies beyond N -- without the per-column checks below
+            const int n8 = nb + 8 * h8;
+            if (n8 >= n_hi || n8 + 8 <= n_lo) continue;
+            if (n8 >= n_lo && n8 + 8 <= n_hi && (g.C.split ? al16 : al32)) {
+              if (g.C.split) {
+                uint4 hh, ll;
+                hh.x = split_pack2(o[8 * h8 + 0], o[8 * h8 + 1], ll.x); hh.y = split_pack2(o[8 * h8 + 2], o[8 * h8 + 3], ll.y);
+                hh.z = split_pack2(o[8 * h8 + 4], o[8 * h8 + 5], ll.z); hh.w = split_pack2(o[8 * h8 + 6], o[8 * h8 + 7], ll.w);
+                *reinterpret_cast<uint4*>(chp + n8) = hh; *reinterpret_cast<uint4*>(chp + g.C.fs + n8) = ll;
+              } else st_global_v8f(cp + n8, o + 8 * h8);
+              continue;
+            }
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const int n = n4 + e;
-                if (n >= n_lo && n < n_hi) { if (g.C.split) split_st1(chp + n, g.C.fs, o[4 * q + e]); else cp[n] = o[4 * q + e]; }
+            for (int q = 2 * h8; q < 2 * h8 + 2; q++) {
+              const int n4 = nb + 4 * q;
+              if (al16 && n4 >= n_lo && n4 + 4 <= n_hi) {
+                if (g.C.split) split_st4(chp + n4, g.C.fs, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+                else *reinterpret_cast<float4*>(cp + n4) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  const int n = n4 + e;
+                  if (n >= n_lo && n < n_hi) { if (g.C.split) split_st1(chp + n, g.C.fs, o[4 * q + e]); else cp[n] = o[4 * q + e]; }
+                }
               }
             }
           }
