@@ -300,8 +300,10 @@ def main():
         # Rank evidence: NCCL_DEBUG=INFO (communicator lines: "... rank r nranks N ..."), left where NCCL writes it by default.
         # That default is STDOUT, which must carry ONE JSON line -- so for the whole run file descriptor 1 points at stderr
         # (NCCL's lines land there) and the JSON line is written to the saved, real stdout at the end.
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        print("[nccl] environment before init: %s" % {k: v for k, v in os.environ.items() if k.startswith("NCCL_")}, file=sys.stderr)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):      # (a caller's INFO / TRACE setting is left alone)
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         sys.stdout.flush()
         real_stdout = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
