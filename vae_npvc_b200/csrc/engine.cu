@@ -52,11 +52,11 @@ struct npvc_handle {
                                      // NPVC_WGRAD_PAIR=0 never, 1 every N >= 128 layer, 2 the same with 256-column N tiles (A/B comparisons)
   bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
   int64_t umma_launches = 0;
-  int ln_bulk = 1;                   // NPVC_LN_BULK=0: shared-memory Layernorm backward for large frames (A/B comparisons)
-  int wgrad_smem_kb = 225;           // NPVC_WGRAD_SMEM_KB
+  int ln_bulk = 1;                   // double-buffered bulk-copy Layernorm backward for frames > 2048 floats
+  int wgrad_smem_kb = 225;           // shared-memory budget of the weight-gradient kernel
   int overlap_wgrad = 1;             // NPVC_OVERLAP=0: weight gradients on the caller's stream (A/B comparisons, per-op profiling)
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int umma_groups = 4;               // NPVC_UMMA_GROUPS: epilogue groups of the forward kernel (1, 2 or 4; <= accumulator sets)
+  int umma_groups = 4;               // epilogue groups of the forward kernel (<= accumulator sets)
   int umma_tap = 1;                  // NPVC_UMMA_TAP=0: conv-shaped layers through the overlapping-window boxes (A/B comparisons)
   int umma_merge = 1;                // NPVC_UMMA_MERGE=0: three MMAs per K step instead of two (A/B comparisons; see UmmaArgs::merge)
   int nvtx = 0;                      // NPVC_NVTX=1: an NVTX push / pop range named after the plan op around every launch
@@ -954,7 +954,6 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   const char* eu = getenv("NPVC_UMMA");            // "0" = CUDA-core GEMMs only (debug / A-B comparisons)
   h->use_umma = !(eu && eu[0] == '0');
   if (const char* tp = getenv("NPVC_UMMA_TAP")) h->umma_tap = atoi(tp);
-  if (const char* gr = getenv("NPVC_UMMA_GROUPS")) { int v = atoi(gr); h->umma_groups = v >= 4 ? 4 : (v >= 2 ? 2 : 1); }
   if (const char* ov = getenv("NPVC_OVERLAP")) h->overlap_wgrad = atoi(ov);
   { const char* pd = getenv("NPVC_PDL"); g_pdl = (pd && !atoi(pd)) ? 0 : 1; }      // (process-wide: the launch helper has no handle)
   if (const char* nv = getenv("NPVC_NVTX")) h->nvtx = atoi(nv);
@@ -963,8 +962,6 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);
   if (const char* po = getenv("NPVC_PAIR_OPS")) { h->pair_ops = po; if (!h->pair_ops.empty() && !h->umma_pair) h->umma_pair = 1; }
-  if (const char* lb = getenv("NPVC_LN_BULK")) h->ln_bulk = atoi(lb);
-  if (const char* wk = getenv("NPVC_WGRAD_SMEM_KB")) { h->wgrad_smem_kb = atoi(wk); if (h->wgrad_smem_kb < 64) h->wgrad_smem_kb = 64; if (h->wgrad_smem_kb > 225) h->wgrad_smem_kb = 225; }
   const char* ea = getenv("NPVC_UMMA_OPS");
   if (ea) h->umma_allow = ea;
   const char* fz = getenv("NPVC_FUSE");            // "0" = every plan op as its own kernel (A/B comparisons, fallback-path tests)
@@ -1053,6 +1050,9 @@ const char* npvc_profile_json(npvc_handle* h) {
     else if (o.kind == OP_WGRAD) { per_frame = frame_floats(o.A.ref) + (o.A.ref.space == SP_USER ? p.arch.in_h : 0) + frame_floats(o.C.ref); fixed = (double)o.K * o.N; }
     else if (o.kind == OP_LN_FWD) per_frame = o.L + o.out_flen;
     else if (o.kind == OP_LN_BWD) per_frame = 2.0 * o.L + o.out_flen;
+    // fused first layer: x in, raw conv output + activation planes out (training) / dy, c and x in, nothing per frame out
+    if (o.fuse == FUSE_E0_FWD) { const Op& ln = ops[i + 1]; per_frame = p.arch.in_h + (h->last_train ? ln.L : 0) + ln.out_flen; fixed = 0.0; }
+    if (o.fuse == FUSE_E0_BWD) per_frame = 2.0 * o.L + p.arch.in_h;
     const double bytes = 4.0 * (per_frame * (double)frames[i] + fixed * (double)calls[i]);
     const bool tensor = o.umma && umma_allowed(h, o);
     snprintf(buf, sizeof buf, "%s{\"name\":\"%s\",\"kind\":%d,\"calls\":%lld,\"ms\":%.6f,\"rows\":%lld,\"K\":%d,\"N\":%d,\"tensor\":%d,\"bytes\":%.0f}",
