@@ -192,9 +192,15 @@ def buffer_ranges(plan, chunk, train):
     """[(name, first float, floats per frame, is-split)] of the per-frame workspace buffers for a pass over `chunk` frames
     (Plan::buf_offset of plan.cpp restated: 64-float aligned buffers behind the operand-pack arena)."""
     rup = lambda v: (v + 63) // 64 * 64
-    off, out = rup(plan["arena_w"]), []
-    for b in plan["bufs"]:
-        sz = 0 if ((b["train_only"] and not train) or b.get("elide")) else rup(b["fixed"] + b["per_frame"] * chunk)
+    off, out, start = rup(plan["arena_w"]), [], {}
+    for i, b in enumerate(plan["bufs"]):
+        own = rup(b["fixed"] + b["per_frame"] * chunk)
+        if b.get("alias", -1) >= 0:                      # a tenant of another buffer: same start, its own extent, no storage
+            if not (b["train_only"] and not train):
+                out.append((b["name"], start[b["alias"]], start[b["alias"]] + own, b["per_frame"], b["split"]))
+            continue
+        sz = 0 if ((b["train_only"] and not train) or b.get("elide")) else own
+        start[i] = off
         out.append((b["name"], off, off + sz, b["per_frame"], b["split"]))
         off += sz
     return out

@@ -282,7 +282,9 @@ def _check_epilogue_stores_stay_in_their_frame(rec, chunk):
         if not u or "umma_fwd" not in L["name"]:
             continue
         pos = (u["c_ptr"] - rec.ws_lo) // 4
-        hit = [b for b in bufs if b[1] <= pos < b[2]]
+        hit = [b for b in bufs if b[1] <= pos < b[2] and b[0] != "da_shared"]
+        if len(hit) > 1:                                 # tenants of the shared gradient buffer: the one with this view's frame stride
+            hit = [b for b in hit if b[3] == u["c_fs"]][:1]
         assert len(hit) == 1 and pos == hit[0][1], (L["name"], "output view does not start at a workspace buffer", pos)
         name, lo, hi, per_frame, split = hit[0]
         assert u["c_fs"] == per_frame and bool(u["c_split"]) == bool(split), (name, u)

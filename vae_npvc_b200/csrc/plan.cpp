@@ -97,8 +97,8 @@ int64_t Plan::buf_offset(int b, int64_t chunk, bool train) const {
   int64_t off = rup64(arena_w, 64);
   for (int i = 0; i < (int)bufs.size(); i++) {
     const Buf& q = bufs[i];
-    int64_t sz = ((q.train_only && !train) || q.elide) ? 0 : rup64(q.fixed + q.per_frame * chunk, 64);
-    if (i == b) return off;
+    int64_t sz = ((q.train_only && !train) || q.elide || q.alias >= 0) ? 0 : rup64(q.fixed + q.per_frame * chunk, 64);
+    if (i == b) return q.alias >= 0 ? buf_offset(q.alias, chunk, train) : off;
     off += sz;
   }
   return off;
@@ -345,6 +345,13 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
   // acc comes first so that theta-derived state (arena_w) sits at the same offsets in
   // the inference and training layouts
   p.buf_adw = B.add_buf("arena_dw", 0, p.arena_dw, true);
+  // gradients w.r.t. the activations (fp32): da_l is written by ONE dgrad GEMM and read by the Layernorm backward that
+  // follows it on the caller's stream, and the next da is written only after that -- all of them share one buffer
+  // (sized for the largest: 48 KB per frame less workspace for the reference architecture)
+  int64_t da_max = 0;
+  for (int e = 0; e < nE; e++) da_max = std::max<int64_t>(da_max, (int64_t)E[e].Ho * E[e].Co);
+  for (int g = 0; g + 1 < nG; g++) da_max = std::max<int64_t>(da_max, (int64_t)G[g].Ho * G[g].Co);
+  const int b_da = B.add_buf("da_shared", da_max, 0, true);
   std::vector<int> b_ce(nE), b_me(nE), b_ae(nE), b_re(nE), b_dce(nE), b_dae(nE);
   std::vector<int> ae_flen(nE), ae_off(nE), dce_flen(nE), dce_off(nE);
   for (int e = 0; e < nE; e++) {
@@ -357,7 +364,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
     snprintf(nm, sizeof nm, "rstd_e%d", e); b_re[e] = B.add_buf(nm, 1, 0, false);
     dce_flen[e] = (e_pf[e] + l.Ho + e_pb[e]) * l.Co; dce_off[e] = e_pf[e] * l.Co;
     snprintf(nm, sizeof nm, "dc_e%d", e);   b_dce[e] = B.add_buf(nm, dce_flen[e], 0, true, SPLIT);
-    snprintf(nm, sizeof nm, "da_e%d", e);   b_dae[e] = B.add_buf(nm, L, 0, true);
+    snprintf(nm, sizeof nm, "da_e%d", e);   b_dae[e] = B.add_buf(nm, L, 0, true); p.bufs[b_dae[e]].alias = b_da;
   }
   p.buf_hz = B.add_buf("hz", 2 * z, 0, false);
   p.buf_mu = B.add_buf("mu", z, 0, false);
@@ -385,7 +392,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
     // zero weights, so they must be zeros of this frame's own plane, never a neighbour's bits (NaN * 0)
     if (gen_parity_split(l.Co, l.s, l.Hi, use_umma)) dcg_flen[g] += cdiv(l.k * l.Co, 16) * 16 - l.k * l.Co;
     snprintf(nm, sizeof nm, "dc_g%d", g);   b_dcg[g] = B.add_buf(nm, dcg_flen[g], 0, true, SPLIT);
-    snprintf(nm, sizeof nm, "da_g%d", g);   b_dag[g] = B.add_buf(nm, L, 0, true);
+    snprintf(nm, sizeof nm, "da_g%d", g);   b_dag[g] = B.add_buf(nm, L, 0, true); p.bufs[b_dag[g]].alias = b_da;
   }
   p.buf_xh = B.add_buf("xh", a.in_h, 0, false);
   int b_dxh = B.add_buf("dxh", xhld, 0, true, SPLIT);
@@ -648,7 +655,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
   for (size_t i = 0; i < p.bufs.size(); i++) {
     const Buf& q = p.bufs[i];
     js << (i ? "," : "") << "{\"name\":\"" << q.name << "\",\"per_frame\":" << q.per_frame << ",\"fixed\":" << q.fixed
-       << ",\"train_only\":" << q.train_only << ",\"split\":" << q.split << ",\"elide\":" << q.elide << "}";
+       << ",\"train_only\":" << q.train_only << ",\"split\":" << q.split << ",\"elide\":" << q.elide << ",\"alias\":" << q.alias << "}";
   }
   js << "],\"ops\":[";
   for (size_t i = 0; i < p.ops.size(); i++) {

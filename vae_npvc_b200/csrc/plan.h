@@ -66,6 +66,9 @@ struct Buf {
   // tensor path multiplies such operands as hi.hi + hi.lo + lo.hi in fp32 (bf16x3).
   int split = 0;
   int elide = 0;           // no storage: every producer / consumer of the buffer runs inside a fused kernel (Op::fuse)
+  int alias = -1;          // >= 0: the buffer has no storage of its own and lives at the start of buffer `alias` (its lifetime does
+                           // not overlap the other tenants': the da_l gradients, each written by one dgrad GEMM and consumed by the
+                           // Layernorm backward that follows it on the same stream)
 };
 
 struct Op {
