@@ -397,8 +397,17 @@ int launch_umma(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool*
     const TapGeom tg = tap_geometry(o, frames);
     if (tg.ok) return launch_umma_tap(c, o, op_index, tg, ln, fused);
   }
-  int n_tiles = 1; const int BN = pick_bn(o.N, bn_cap(o), &n_tiles);
+  int n_tiles = 1; int BN = pick_bn(o.N, bn_cap(o), &n_tiles);
   const RowTiling rt = make_tiling(o.A.R, frames, 128);
+  // small batches (the reference trains on 16 frames per step): a handful of M tiles times a few wide N tiles leaves most
+  // SMs idle while 3 CTAs stream the whole weight matrix -- narrower N tiles spread it (per-element arithmetic is the
+  // same for any tile width: the K order does not change, results stay bit-identical)
+  // (not where the Layernorm epilogue applies: it needs the whole row in one N tile, and a frame's result must not depend
+  // on the size of the batch it arrives in -- fused and separate Layernorm differ in the last bits)
+  const bool ln_tile = ln_epilogue_ok(c, o, ln, rt, n_tiles);
+  while (!ln_tile && (long long)rt.m_tiles * n_tiles < h->sm_count / 2 && BN > 16) {
+    BN = (BN / 2 + 15) / 16 * 16; n_tiles = (o.N + BN - 1) / BN;
+  }
   if (pair_wanted(h, o, BN, rt.m_tiles)) {
     const int rc = launch_umma_pair(c, o, op_index, BN, n_tiles, rt);
     if (rc == NPVC_OK || h->umma_pair >= 2 || !h->pair_ops.empty()) return rc;     // (an explicit request reports its failure)
