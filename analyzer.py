@@ -171,6 +171,7 @@ class FrameLoader(object):
         self.cv = threading.Condition()
         self.stream = torch.cuda.Stream(device=self.dev)
         self._peek = None
+        self._pending = []                  # events of H2D copies whose pinned slots are not yet back with the producer
         self._stop = False
         self.thread = threading.Thread(target=self._produce, daemon=True)
         self.thread.start()
@@ -187,11 +188,25 @@ class FrameLoader(object):
                 self.ready.append(k % len(self.host)); self.cv.notify()
             k += 1
 
+    def _release_copied(self, block=False):
+        """Pinned slots go back to the producer once their H2D copy has completed -- polled, so the consumer does not
+        stall on the copy it has just issued; it blocks on the OLDEST copy only when the producer is out of slots."""
+        while self._pending and (block or self._pending[0].query()):
+            self._pending.pop(0).synchronize()
+            self.free.release()
+            block = False
+
     def _next_device_batch(self):
-        with self.cv:
-            while not self.ready:
-                self.cv.wait()
-            slot = self.ready.pop(0)
+        self._release_copied()
+        while True:
+            with self.cv:
+                if self.ready:
+                    slot = self.ready.pop(0)
+                    break
+                if not self._pending:
+                    self.cv.wait(0.05)
+                    continue
+            self._release_copied(block=True)            # every slot is in flight: wait for the oldest copy, not for the producer
         with torch.cuda.stream(self.stream):
             rec = self.host[slot].to(self.dev, non_blocking=True)
             x, y = self.engine.unpack_records(rec, SP_DIM, self.norm[0], self.norm[1])
@@ -201,8 +216,7 @@ class FrameLoader(object):
         # allocated on the loader's stream, consumed on the caller's: the caching allocator must not hand the
         # blocks back to the loader's stream while the training step still reads them
         x.record_stream(cur); y.record_stream(cur)
-        done.synchronize()                  # the pinned slot may be refilled once the H2D copy is done
-        self.free.release()
+        self._pending.append(done)          # the pinned slot may be refilled once the H2D copy is done (_release_copied)
         if self.fmt == 'NCHW':
             x = x.view(-1, 1, SP_DIM, 1)
         elif self.fmt == 'NHWC':

@@ -307,3 +307,30 @@ def test_epilogue_stores_stay_in_their_frame(switch):
         _check_epilogue_stores_stay_in_their_frame(HS.record_loss_fwd_bwd(ALT_ARCHS[name], 29, SWITCHES[switch]), 29)
     for seed in range(12):
         _check_epilogue_stores_stay_in_their_frame(HS.record_loss_fwd_bwd(_random_arch(np.random.RandomState(seed)), 50, SWITCHES[switch]), 50)
+
+
+def test_fused_kernels_and_small_batch_tiles_of_the_default_plan():
+    """What the default engine launches for the reference architecture: the fused first-layer kernels (and no launch of the
+    ops they replace), one speaker-backward kernel per call, the Layernorm epilogue for inference passes only, and -- at
+    16 frames -- narrow N tiles that spread the dense generator layer over tens of CTAs."""
+    arch = vcc2016_vae_arch()
+    tr = HS.record_loss_fwd_bwd(arch, 16384)
+    names = [L["name"] for L in tr.launches]
+    assert sum("e0_fwd_kernel" in n for n in names) == 1 and sum("e0_bwd_kernel" in n for n in names) == 1
+    assert not any("rowgemm_kernel" in n or "wgrad_tiny_kernel" in n for n in names)          # the unfused first-layer kernels
+    assert sum("speaker_bwd_kernel" in n for n in names) == 1 and not any("colsum_kernel" in n for n in names)
+    assert sum("zero_pads_kernel" in n for n in names) == 1
+    assert not any(L["umma"] and L["umma"]["ln_on"] for L in tr.launches)                   # training keeps the Layernorm kernels
+    assert sum("ln_fwd_reg_kernel" in n for n in names) == 7                                  # 8 Layernorms - the fused first layer
+    bufs = {b["name"]: b for b in tr.plan["bufs"]}
+    assert bufs["dc_e0"]["elide"] == 1 and all(bufs[k]["alias"] == [i for i, b in enumerate(tr.plan["bufs"]) if b["name"] == "da_shared"][0]
+                                               for k in bufs if k.startswith("da_") and k != "da_shared")
+    inf = HS.record_encode_decode(arch, 16384)
+    fused = [L for L in inf.launches if L["umma"] and L["umma"]["ln_on"]]
+    assert sorted((L["umma"]["K"], L["umma"]["N"]) for L in fused) == sorted([(112, 32), (224, 64), (448, 128), (264, 96), (96, 48)])
+    assert sum("ln_fwd" in L["name"] for L in inf.launches) == 2                              # E4 (two N tiles) and G2 (frames span tiles)
+    unf = HS.record_loss_fwd_bwd(arch, 300, {"NPVC_FUSE": "0"})
+    assert any("rowgemm_kernel" in L["name"] for L in unf.launches) and not any("e0_" in L["name"] for L in unf.launches)
+    small = HS.record_loss_fwd_bwd(arch, 16)
+    g3 = [L for L in small.launches if L["umma"] and "umma_fwd" in L["name"] and (L["umma"]["K"], L["umma"]["N"]) == (4104, 513)]
+    assert len(g3) == 1 and g3[0]["grid"][0] >= 30 and g3[0]["umma"]["BN"] == 16, g3
