@@ -135,6 +135,43 @@ def check_streams(rec, caller=0):
             assert seen.get(s, -1) >= q, "work on internal stream %#x is not joined into the caller's stream" % s
 
 
+def observed_before(rec, seq, caller=0):
+    """{stream: last seq of that stream the caller's stream has observed} just before the caller's operation `seq`."""
+    clock, snap = {}, {}
+    for o in sorted(rec.ops, key=lambda o: o["seq"]):
+        s = o["stream"]; c = clock.setdefault(s, {})
+        if s == caller and o["seq"] == seq:
+            return dict(c)
+        if o["kind"] == 1:
+            e = dict(c); e[s] = o["seq"]; snap[o["event"]] = e
+        elif o["kind"] == 2:
+            for k, v in snap[o["event"]].items():
+                c[k] = max(c.get(k, -1), v)
+        c[s] = o["seq"]
+    raise AssertionError("no operation %d on the caller's stream" % seq)
+
+
+def test_packs_run_beside_the_first_layer():
+    """Training call: the fused first layer reads only the fp32 pack, so the speaker table and the bf16 planes are
+    issued on the side stream; the first tensor-path GEMM (their first reader) waits for them, the first layer does not.
+    With NPVC_OVERLAP=0 everything stays on the caller's stream."""
+    r = HS.record_loss_fwd_bwd(vcc2016_vae_arch(), 16384)
+    by = lambda frag: [L for L in r.launches if frag in L["name"]]
+    p16, e0, um = by("pack16_kernel")[0], by("e0_fwd_kernel")[0], [L for L in r.launches if L["umma"]][0]
+    ptab = by("fewrows_fwd_kernel")[0]
+    assert p16["stream"] != 0 and ptab["stream"] == p16["stream"] and e0["stream"] == 0 and um["stream"] == 0
+    pk = [L for L in r.launches if "pack_list_kernel" in L["name"] or "npvc::pack_kernel" in L["name"]][0]
+    assert pk["stream"] == 0 and pk["seq"] < e0["seq"]
+    assert observed_before(r, e0["seq"]).get(p16["stream"], -1) < ptab["seq"]            # not waited for
+    assert observed_before(r, um["seq"]).get(p16["stream"], -1) >= max(p16["seq"], ptab["seq"])
+    r0 = HS.record_loss_fwd_bwd(vcc2016_vae_arch(), 16384, {"NPVC_OVERLAP": "0"})
+    assert {L["stream"] for L in r0.launches} == {0}
+    rf = HS.record_loss_fwd_bwd(vcc2016_vae_arch(), 64, {"NPVC_FUSE": "0"})                # no fused first layer: joined at once
+    first = [L for L in rf.launches if L["stream"] == 0 and "pack" not in L["name"]][0]
+    side = [L for L in rf.launches if L["stream"] != 0 and L["seq"] < first["seq"]]
+    assert side and observed_before(rf, first["seq"]).get(side[0]["stream"], -1) >= max(L["seq"] for L in side)
+
+
 SWITCHES = {
     "default": {},
     "single_cta": {"NPVC_PAIR": "0"},

@@ -55,7 +55,8 @@ struct npvc_handle {
   int ln_bulk = 1;                   // double-buffered bulk-copy Layernorm backward for frames > 2048 floats
   int wgrad_smem_kb = 225;           // shared-memory budget of the weight-gradient kernel
   int overlap_wgrad = 1;             // NPVC_OVERLAP=0: weight gradients on the caller's stream (A/B comparisons, per-op profiling)
-  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
+  bool pack_defer = false, pack_pending = false;   // training call: the pack ops after the first run beside the first layer (run_phase)
   int umma_groups = 4;               // epilogue groups of the forward kernel (<= accumulator sets)
   int umma_tap = 1;                  // NPVC_UMMA_TAP=0: conv-shaped layers through the overlapping-window boxes (A/B comparisons)
   int umma_merge = 1;                // NPVC_UMMA_MERGE=0: three MMAs per K step instead of two (A/B comparisons; see UmmaArgs::merge)
@@ -842,11 +843,16 @@ int run_phase(Ctx& c, int phase) {
   // HBM-bound Layernorm backward kernels and the tails of the dgrad GEMMs.  Still ordered w.r.t. the
   // caller's stream (fork / join events only); nothing synchronises the device.
   const bool fork = (phase == PH_BWD) && h->overlap_wgrad && !h->profiling;
+  // Packing inside a training call: the fused first layer reads only the fp32 pack (the phase's first op), so
+  // the speaker table and the bf16 planes are forked onto the side stream and joined in front of the first op
+  // that is not the fused first layer (below) - they run beside it instead of in front of it.
+  const bool fork_pack = (phase == PH_PACK) && h->pack_defer && h->overlap_wgrad && !h->profiling;
   const cudaStream_t main_st = c.st;
-  bool forked = false;
-  if (fork && !h->side) {
+  bool forked = false, first = true;
+  if ((fork || fork_pack) && !h->side) {
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) return fail(NPVC_ERR_CUDA, "cudaStreamCreate failed");
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming);
   }
   for (size_t i = 0; i < ops.size(); i++) {
     const Op& o = ops[i];
@@ -858,11 +864,15 @@ int run_phase(Ctx& c, int phase) {
       ev.rows = (o.kind == OP_GEMM || o.kind == OP_WGRAD) ? (o.rows_fixed ? o.rows_fixed : c.n * o.A.R) : c.n;
       cudaEventRecord(ev.a, c.st);
     }
-    const bool on_side = fork && o.kind == OP_WGRAD;
-    if (on_side) {                                   // everything issued so far on the caller's stream happens-before this op
-      cudaEventRecord(h->ev_fork, main_st); cudaStreamWaitEvent(h->side, h->ev_fork, 0);
-      c.st = h->side; forked = true;
+    if (h->pack_pending && phase != PH_PACK && o.fuse != FUSE_E0_FWD) {   // first reader of the forked packs
+      cudaStreamWaitEvent(main_st, h->ev_pack, 0); h->pack_pending = false;
     }
+    const bool on_side = (fork && o.kind == OP_WGRAD) || (fork_pack && !first);
+    if (on_side && !(fork_pack && forked)) {         // everything issued so far on the caller's stream happens-before this op
+      cudaEventRecord(h->ev_fork, main_st); cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    }
+    if (on_side) { c.st = h->side; forked = true; }
+    first = false;
     if (h->nvtx) nvtxRangePushA(o.name.c_str());
     int rc;
     if (o.fuse == FUSE_E0_FWD) {                     // this op and the next one as one kernel (plan.h, Op::fuse)
@@ -882,7 +892,8 @@ int run_phase(Ctx& c, int phase) {
     if (h->profiling) { cudaEventRecord(ev.b, c.st); h->events.push_back(ev); }
     if (rc) return rc;
   }
-  if (forked) { cudaEventRecord(h->ev_join, h->side); cudaStreamWaitEvent(main_st, h->ev_join, 0); }
+  if (forked && fork_pack) { cudaEventRecord(h->ev_pack, h->side); h->pack_pending = true; }
+  else if (forked) { cudaEventRecord(h->ev_join, h->side); cudaStreamWaitEvent(main_st, h->ev_join, 0); }
   return NPVC_OK;
 }
 
@@ -986,7 +997,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
 
 void npvc_destroy(npvc_handle* h) {
   if (!h) return;
-  if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+  if (h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_pack); }
   if (h->tables_on_device) free_tables(h);
   delete h;
 }
@@ -1147,7 +1158,8 @@ static int loss_core(npvc_handle* h, const float* d_theta, const float* d_x, con
   }
   if (repack) {
     Ctx c{h, ws, cap, true, d_theta, nullptr, nullptr, nullptr, nullptr, 0, n, st};
-    rc = run_phase(c, PH_PACK); if (rc) return rc;
+    h->pack_defer = true; rc = run_phase(c, PH_PACK); h->pack_defer = false;
+    if (rc) return rc;
   }
   for (int64_t c0 = 0; c0 < n; c0 += cap) {
     int64_t m = n - c0 < cap ? n - c0 : cap;
