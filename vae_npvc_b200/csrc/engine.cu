@@ -50,7 +50,7 @@ struct npvc_handle {
   std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the shape rule)
   int wgrad_pair = -1;               // cta_group::2 form of the weight-gradient kernel: -1 (default) where it measured faster (launch_umma_wgrad),
                                      // NPVC_WGRAD_PAIR=0 never, 1 every N >= 128 layer, 2 the same with 256-column N tiles (A/B comparisons)
-  bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false;   // cudaFuncSetAttribute done (per handle = per device)
+  bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false, attr_e0_bwd = false;   // cudaFuncSetAttribute done (per handle = per device)
   int64_t umma_launches = 0;
   int ln_bulk = 1;                   // double-buffered bulk-copy Layernorm backward for frames > 2048 floats
   int wgrad_smem_kb = 225;           // shared-memory budget of the weight-gradient kernel
@@ -586,7 +586,7 @@ int launch_e0_fwd(Ctx& c, const Op& o, const Op& nx) {      // o: conv (OP_GEMM 
   const int bt = E0_BLOCK(G), fpb = bt / G;
   const long long fbs = (c.n + fpb - 1) / fpb;
   long long blocks = (long long)h->sm_count * 2 * (768 / bt); if (blocks > fbs) blocks = fbs;
-  const size_t sm = ((size_t)(E0_KT + 3) * g.Co + (size_t)fpb * g.xp) * sizeof(float);
+  const size_t sm = ((size_t)(E0_KT + 3) * g.Co + (size_t)3 * fpb * g.xp) * sizeof(float);      // (three row buffers: fused_e0.cuh)
   const bool v4 = nx.L / 8 > 3 * G;                       // units of 8 elements per thread: 3 or 4
 #define NPVC_E0_FWD(GG) do { if (v4) launch_k(e0_fwd_kernel<GG, 4>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); else launch_k(e0_fwd_kernel<GG, 3>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); } while (0)
   if (G == 32) NPVC_E0_FWD(32); else if (G == 64) NPVC_E0_FWD(64); else if (G == 128) NPVC_E0_FWD(128); else NPVC_E0_FWD(256);
@@ -608,11 +608,16 @@ int launch_e0_bwd(Ctx& c, const Op& o, const Op& nx) {      // o: OP_LN_BWD of t
   const int bt = E0_BLOCK(G), fpb = bt / G;
   const long long fbs = (c.n + fpb - 1) / fpb;
   long long blocks = (long long)h->sm_count * (512 / bt); if (blocks > fbs) blocks = fbs;
-  const size_t sm = ((size_t)(E0_KT + 5) * g.Co + (size_t)2 * fpb * g.xp) * sizeof(float);      // (staged frames double-buffered)
+  const size_t sm = e0_bwd_smem_floats(g.Co, fpb, g.xp, o.L) * sizeof(float);      // (rows and the prefetched dy / c: fused_e0.cuh)
+  if (sm > 110 * 1024) return fail(NPVC_ERR_ARG, "fused first-layer backward: frame too long for the staging buffers");
   const bool v4 = o.L / 4 > 3 * G;                        // units of 4 elements per thread: 3 or 4
-#define NPVC_E0_BWD(GG) do { if (v4) launch_k(e0_bwd_kernel<GG, 4>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); else launch_k(e0_bwd_kernel<GG, 3>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); } while (0)
+  const bool set_attr = !h->attr_e0_bwd; h->attr_e0_bwd = true;      // (one instantiation per handle: the architecture is fixed)
+#define NPVC_E0_BWD_I(GG, VV) do { if (set_attr) CUDA_TRY(cudaFuncSetAttribute(e0_bwd_kernel<GG, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); \
+                                   launch_k(e0_bwd_kernel<GG, VV>, dim3((unsigned)blocks), dim3(bt), sm, c.st, g); } while (0)
+#define NPVC_E0_BWD(GG) do { if (v4) NPVC_E0_BWD_I(GG, 4); else NPVC_E0_BWD_I(GG, 3); } while (0)
   if (G == 32) NPVC_E0_BWD(32); else if (G == 64) NPVC_E0_BWD(64); else if (G == 128) NPVC_E0_BWD(128); else NPVC_E0_BWD(256);
 #undef NPVC_E0_BWD
+#undef NPVC_E0_BWD_I
   h->launches++;
   return NPVC_OK;
 }

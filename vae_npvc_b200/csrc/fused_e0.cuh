@@ -42,17 +42,32 @@ __host__ __device__ inline int e0_row_floats(int Ho, int s, int pl, int Hi) {
   return (need + 3) / 4 * 4;
 }
 
-// the frame with its SAME padding (zeros) in shared memory: the taps read it without predicates or address math
-__device__ __forceinline__ void e0_stage_x(float* xs, const float* xp, bool fok, int t, int G, int XP, int pl, int Hi) {
-  for (int i = t; i < XP; i += G) { const int xi = i - pl; xs[i] = (fok && xi >= 0 && xi < Hi) ? __ldg(xp + xi) : 0.f; }
+// Ampere-style asynchronous copies (LDGSTS): the next frame is fetched into shared memory while this one is computed
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, int src_bytes) {      // src_bytes 0: writes a zero
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// the frame's input row with its SAME padding (zeros) into shared memory - the taps read it without predicates or
+// address math -, asynchronously: one commit group per call (empty when !fok)
+__device__ __forceinline__ void e0_fetch_x(float* xs, const float* xp, bool fok, int t, int G, int XP, int pl, int Hi) {
+  if (fok)
+    for (int i = t; i < XP; i += G) { const int xi = i - pl; const bool ok = xi >= 0 && xi < Hi; cp_async4_zfill(xs + i, ok ? xp + xi : xp, ok ? 4 : 0); }
+  cp_async_commit();
 }
 
-// G threads per frame, V units of 8 consecutive channels per thread (L <= 8 G V)
+// G threads per frame, V units of 8 consecutive channels per thread (L <= 8 G V); the next frame's input row
+// is in flight while this one is computed (three row buffers: the one written in iteration k was last read in k - 2, and
+// every thread has passed the barriers of k - 1 since)
 template <int G, int V>
 __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(E0FwdArgs g) {
   pdl_prologue();
   constexpr int FPB = E0_BLOCK(G) / G;
-  extern __shared__ __align__(16) float e0sm[];      // [KT][Co] weights | bias | gamma | beta | [FPB][xp] staged frames
+  extern __shared__ __align__(16) float e0sm[];      // [KT][Co] weights | bias | gamma | beta | [3][FPB][xp] staged frames
   __shared__ float red[2 * 8];
   int par = 0;
   const int Co = g.Co, XP = g.xp;
@@ -60,18 +75,22 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(
   for (int i = threadIdx.x; i < E0_KT * Co; i += blockDim.x) sw[i] = (i < g.k * Co) ? g.W[i] : 0.f;
   for (int i = threadIdx.x; i < Co; i += blockDim.x) { sb[i] = g.bias[i]; sg[i] = g.gamma[i]; sbt[i] = g.beta[i]; }
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
-  float* xs = sbt + Co + grp * XP;
+  float* xs0 = sbt + Co + grp * XP;
+  int xb = 0;
   const int cpb = Co >> 3;                             // 8-channel blocks per position (a power of two: divides G)
   const int cshift = 31 - __clz(cpb);
   const int c0 = (t & (cpb - 1)) << 3;                 // this thread's channels
   const int L = g.Ho * Co, L8 = L >> 3, off8 = g.out_off >> 3, F8 = g.out_flen >> 3;
   const float invL = 1.0f / (float)L;
   const float2* w2 = reinterpret_cast<const float2*>(sw + c0);
+  { const long long f0 = (long long)blockIdx.x * FPB + grp; e0_fetch_x(xs0, g.x + f0 * g.Hi, f0 < g.frames, t, G, XP, g.pl, g.Hi); }
   for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
     const long long f = fb * FPB + grp; const bool fok = f < g.frames;
-    __syncthreads();                                   // (first pass: the weights; later: the previous frame's taps are done)
-    e0_stage_x(xs, g.x + f * g.Hi, fok, t, G, XP, g.pl, g.Hi);
-    __syncthreads();
+    const float* xs = xs0 + xb * FPB * XP;
+    xb = xb == 2 ? 0 : xb + 1;
+    { const long long fn = (fb + gridDim.x) * FPB + grp; e0_fetch_x(xs0 + xb * FPB * XP, g.x + fn * g.Hi, fn < g.frames, t, G, XP, g.pl, g.Hi); }
+    cp_async_wait<1>();
+    __syncthreads();                                   // this frame's row (and, first pass, the weights) published
     float2 v[V][4];
     float s[1] = {0.f};
 #pragma unroll
@@ -126,12 +145,21 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(
   }
 }
 
-// G threads per frame, V units of 4 consecutive channels per thread (L <= 4 G V)
+// floats of dynamic shared memory of e0_bwd_kernel (FPB frames per block)
+constexpr int E0_PF = 1;        // frames in flight ahead of the one being computed (backward); 2 measured no faster
+__host__ __device__ inline size_t e0_bwd_smem_floats(int Co, int FPB, int xp, int L) {
+  return (size_t)(E0_KT + 5) * Co + (size_t)(E0_PF + 2) * FPB * xp + (size_t)(E0_PF + 1) * FPB * 2 * L;
+}
+
+// G threads per frame, V units of 4 consecutive channels per thread (L <= 4 G V).  A block's next E0_PF frames (dy, the
+// raw conv output, the input row with its SAME padding, mean / rstd) are in flight while the current one is computed
+// : dy / c land in a per-thread staging ring (a thread copies
+// exactly the units it will read: no barrier), the input row - read by the whole group - in a ring one buffer longer.
 template <int G, int V>
 __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(E0BwdArgs g) {
   pdl_prologue();
   constexpr int FPB = E0_BLOCK(G) / G;
-  extern __shared__ __align__(16) float e0sm[];      // [3 Co] dgamma | dbeta | dbias sums, [KT Co] dW sums, gamma, beta, [2][FPB][xp] frames
+  extern __shared__ __align__(16) float e0sm[];      // [3 Co] dgamma | dbeta | dbias sums, [KT Co] dW sums, gamma, beta, [PF + 2][FPB][xp] rows, [PF + 1][FPB][2][L] dy | c
   __shared__ float red[2][E0_BLOCK(G) / 32][2];
   const int Co = g.Co, XP = g.xp;
   float* chs = e0sm; float* sdw = chs + 3 * Co; float* sgm = sdw + E0_KT * Co; float* sbt = sgm + Co;
@@ -139,35 +167,61 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(
   for (int i = threadIdx.x; i < Co; i += blockDim.x) { sgm[i] = g.gamma[i]; sbt[i] = g.beta[i]; }
   __syncthreads();
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
-  float* xs0 = sbt + Co + grp * XP;                    // staged frames and warp partials are double-buffered by frame parity:
+  float* xs0 = sbt + Co + grp * XP;
   const int qpp = Co >> 2;                             // channel quads per position (a power of two: divides G)
   const int qshift = 31 - __clz(qpp);
   const int c0 = (t & (qpp - 1)) << 2;
   const int L = g.Ho * Co, L4 = L >> 2;
   const float invL = 1.0f / (float)L;
+  float* stg0 = sbt + Co + (E0_PF + 2) * FPB * XP + (size_t)grp * 2 * L;        // this frame slot's [dy | c], + buf * FPB * 2 * L
   float gm[4], bt[4], adg[4], adb[4], adc[4];
   float2 dw[E0_KT][2];
 #pragma unroll
   for (int e = 0; e < 4; e++) { gm[e] = sgm[c0 + e]; bt[e] = sbt[c0 + e]; adg[e] = adb[e] = adc[e] = 0.f; }
 #pragma unroll
   for (int kk = 0; kk < E0_KT; kk++) dw[kk][0] = dw[kk][1] = make_float2(0.f, 0.f);
-  int par = 0;
+  // one commit group per call, empty past the end: group k holds frame-block k of this block
+  auto fetch = [&](long long fbn, int buf, int xb, float& rs_n, float& mu_n) {
+    const long long fn = fbn * FPB + grp;
+    if (fn < g.frames) {
+      float4* sd = reinterpret_cast<float4*>(stg0 + (size_t)buf * FPB * 2 * L) + t;
+      const float4* dyp = reinterpret_cast<const float4*>(g.dy + fn * L) + t;
+      const float4* cp = reinterpret_cast<const float4*>(g.cin + fn * L) + t;
+#pragma unroll
+      for (int i = 0; i < V; i++)
+        if (t + i * G < L4) { cp_async16(sd + i * G, dyp + i * G); cp_async16(sd + L4 + i * G, cp + i * G); }
+      float* xs = xs0 + xb * FPB * XP; const float* xp = g.x + fn * g.Hi;
+      for (int i = t; i < XP; i += G) { const int xi = i - g.pl; const bool ok = xi >= 0 && xi < g.Hi; cp_async4_zfill(xs + i, ok ? xp + xi : xp, ok ? 4 : 0); }
+      rs_n = g.rstd[fn]; mu_n = g.mean[fn];
+    }
+    cp_async_commit();
+  };
+  int par = 0, sb = 0, xb = 0;                          // parity of the warp partials, staging / row ring positions of this frame
+  float rs_n[E0_PF], mu_n[E0_PF];
+#pragma unroll
+  for (int d = 0; d < E0_PF; d++) { rs_n[d] = mu_n[d] = 0.f; fetch(blockIdx.x + (long long)d * gridDim.x, d, d, rs_n[d], mu_n[d]); }
   for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
     const long long f = fb * FPB + grp; const bool fok = f < g.frames;
     float dx[V][4], xh[V][4];
-    float rs = 0.f, mu = 0.f;
-    if (fok) { rs = g.rstd[f]; mu = g.mean[f]; }
-    const float4* dyp = reinterpret_cast<const float4*>(g.dy + f * L) + t;
-    const float4* cp = reinterpret_cast<const float4*>(g.cin + f * L) + t;
+    const float rs = rs_n[0], mu = mu_n[0];
 #pragma unroll
-    for (int i = 0; i < V; i++) {
-      if (fok && t + i * G < L4) {
-        const float4 a = dyp[i * G], b = cp[i * G];
-        dx[i][0] = a.x; dx[i][1] = a.y; dx[i][2] = a.z; dx[i][3] = a.w; xh[i][0] = b.x; xh[i][1] = b.y; xh[i][2] = b.z; xh[i][3] = b.w;
+    for (int d = 0; d + 1 < E0_PF; d++) { rs_n[d] = rs_n[d + 1]; mu_n[d] = mu_n[d + 1]; }
+    // the staging buffer written here is the one this thread read in the previous iteration; the row buffer was last read
+    // two iterations ago, and every thread has since passed a barrier behind those reads (the previous iteration's)
+    fetch(fb + (long long)E0_PF * gridDim.x, (sb + E0_PF) % (E0_PF + 1), (xb + E0_PF) % (E0_PF + 2), rs_n[E0_PF - 1], mu_n[E0_PF - 1]);
+    cp_async_wait<E0_PF>();                            // this frame's group has landed (own copies: visible to this thread)
+    {
+      const float4* sd = reinterpret_cast<const float4*>(stg0 + (size_t)sb * FPB * 2 * L) + t;
+#pragma unroll
+      for (int i = 0; i < V; i++) {
+        if (fok && t + i * G < L4) {
+          const float4 a = sd[i * G], b = sd[L4 + i * G];
+          dx[i][0] = a.x; dx[i][1] = a.y; dx[i][2] = a.z; dx[i][3] = a.w; xh[i][0] = b.x; xh[i][1] = b.y; xh[i][2] = b.z; xh[i][3] = b.w;
+        }
       }
     }
-    float* xs = xs0 + par * FPB * XP;                  // ONE barrier per frame orders both (see below)
-    e0_stage_x(xs, g.x + f * g.Hi, fok, t, G, XP, g.pl, g.Hi);
+    float* xs = xs0 + xb * FPB * XP;                   // (published to the group by the frame's barrier below)
+    sb = (sb + 1) % (E0_PF + 1); xb = (xb + 1) % (E0_PF + 2);
     float s[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < V; i++) {
@@ -185,8 +239,8 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(
       }
     }
     {
-      // frame sums over the group's warps; the barrier also publishes the staged rows.  A buffer written in iteration k is
-      // next written in k + 2, and every thread passes the barrier of k + 1 (after its reads of k) before any gets there.
+      // frame sums over the group's warps (partials double-buffered by parity: written in k, next written in k + 2, and
+      // every thread passes the barrier of k + 1 after its reads of k); the barrier also publishes the input row.
       s[0] = warp_sum(s[0]); s[1] = warp_sum(s[1]);
       const int warp = threadIdx.x >> 5;
       if ((threadIdx.x & 31) == 0) { red[par][warp][0] = s[0]; red[par][warp][1] = s[1]; }
