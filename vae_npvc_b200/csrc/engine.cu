@@ -50,7 +50,7 @@ struct npvc_handle {
   std::string pair_ops;              // NPVC_PAIR_OPS: comma-separated op names for the pair form (overrides the shape rule)
   int wgrad_pair = -1;               // cta_group::2 form of the weight-gradient kernel: -1 (default) where it measured faster (launch_umma_wgrad),
                                      // NPVC_WGRAD_PAIR=0 never, 1 every N >= 128 layer, 2 the same with 256-column N tiles (A/B comparisons)
-  bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false, attr_e0_bwd = false;   // cudaFuncSetAttribute done (per handle = per device)
+  bool attr_fwd = false, attr_pair = false, attr_wgrad = false, attr_wgrad_pair = false, attr_ln_bulk = false, attr_e0_bwd = false, attr_ln_reg = false;   // cudaFuncSetAttribute done (per handle = per device)
   int64_t umma_launches = 0;
   int ln_bulk = 1;                   // double-buffered bulk-copy Layernorm backward for frames > 2048 floats
   int wgrad_smem_kb = 225;           // shared-memory budget of the weight-gradient kernel
@@ -772,11 +772,14 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
       if (G) {
         const long long fbs = (c.n + 256 / G - 1) / (256 / G);
         long long blocks = (long long)h->sm_count * 4; if (blocks > fbs) blocks = fbs;
-        const size_t sm = (size_t)5 * o.Cn * sizeof(float);
+        const size_t sm = ((size_t)5 * o.Cn + (size_t)(256 / G) * 2 * o.L) * sizeof(float);      // + landing zone (<= 64 KB)
+        if (!h->attr_ln_reg) {
+          CUDA_TRY(cudaFuncSetAttribute(ln_bwd_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          CUDA_TRY(cudaFuncSetAttribute(ln_bwd_reg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          h->attr_ln_reg = true;
+        }
         if (G == 32) launch_k(ln_bwd_reg_kernel<32>, dim3((unsigned)blocks), dim3(256), sm, st, g);
-        else if (G == 64) launch_k(ln_bwd_reg_kernel<64>, dim3((unsigned)blocks), dim3(256), sm, st, g);
-        else if (G == 128) launch_k(ln_bwd_reg_kernel<128>, dim3((unsigned)blocks), dim3(256), sm, st, g);
-        else launch_k(ln_bwd_reg_kernel<256>, dim3((unsigned)blocks), dim3(256), sm, st, g);
+        else launch_k(ln_bwd_reg_kernel<64>, dim3((unsigned)blocks), dim3(256), sm, st, g);
       } else if (ln_group(o.L, o.Cn, o.out_off, o.out_flen) && 2048 % o.Cn == 0 && h->ln_bulk &&
                  (size_t)(4 * o.L + 5 * o.Cn) * sizeof(float) <= 100 * 1024) {
         // large frames: double-buffered bulk-async frame stream (3 blocks / SM at L = 4104)

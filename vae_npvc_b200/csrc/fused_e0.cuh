@@ -42,16 +42,6 @@ __host__ __device__ inline int e0_row_floats(int Ho, int s, int pl, int Hi) {
   return (need + 3) / 4 * 4;
 }
 
-// Ampere-style asynchronous copies (LDGSTS): the next frame is fetched into shared memory while this one is computed
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, int src_bytes) {      // src_bytes 0: writes a zero
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // the frame's input row with its SAME padding (zeros) into shared memory - the taps read it without predicates or
 // address math -, asynchronously: one commit group per call (empty when !fok)
 __device__ __forceinline__ void e0_fetch_x(float* xs, const float* xp, bool fok, int t, int G, int XP, int pl, int Hi) {

@@ -943,8 +943,19 @@ __device__ __forceinline__ void zero_pads(float* base, long long f, int flen, in
   for (int p = t; p < npad; p += G) st8(base, f, flen, 8 * (p < off8 ? p : p + L8), z, split);
 }
 
+// Ampere-style asynchronous copies (LDGSTS): the next frame travels to shared memory while this one is computed.
+// A thread copies exactly the units it will read itself, so its own wait_group is all the synchronisation they need.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, int src_bytes) {      // src_bytes 0: writes a zero
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int G>
-__global__ void __launch_bounds__(256) ln_fwd_reg_kernel(LnFwdArgs g) {
+__global__ void __launch_bounds__(256, 3) ln_fwd_reg_kernel(LnFwdArgs g) {
   pdl_prologue();
   constexpr int V = 4, FPB = 256 / G;
   __shared__ float red[2 * 8];
@@ -1001,7 +1012,7 @@ template <int G>
 __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
   pdl_prologue();
   constexpr int V = 4, FPB = 256 / G;
-  extern __shared__ __align__(16) float chs[];   // [3 * Cn] channel sums: dgamma | dbeta | dbias, then [2 * Cn] gamma | beta
+  extern __shared__ __align__(16) float chs[];   // [3 * Cn] channel sums: dgamma | dbeta | dbias, [2 * Cn] gamma | beta, [FPB][2][L] landing zone (dy | c)
   __shared__ float red[2 * 16];
   int par = 0;
   const int t = threadIdx.x % G, grp = threadIdx.x / G;
@@ -1015,15 +1026,34 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
 #pragma unroll
   for (int e = 0; e < 8; e++) adg[e] = adb[e] = adc[e] = 0.f;
   const float invL = 1.0f / (float)g.L;
+  float* stg = sbt + g.Cn + (size_t)grp * 2 * g.L;     // this frame slot's [dy | c] landing zone
+  float rs_n = 0.f, mu_n = 0.f;
+  auto fetch = [&](long long fbn) {                    // one commit group per call (empty past the end)
+    const long long fn = fbn * FPB + grp;
+    if (fn < g.frames) {
+      const float* sd = g.dy + fn * g.L; const float* sc = g.cin + fn * g.L;
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        const int u = t + k * G;
+        if (u < L8) {
+          cp_async16(stg + 8 * u, sd + 8 * u); cp_async16(stg + 8 * u + 4, sd + 8 * u + 4);
+          cp_async16(stg + g.L + 8 * u, sc + 8 * u); cp_async16(stg + g.L + 8 * u + 4, sc + 8 * u + 4);
+        }
+      }
+      rs_n = g.rstd[fn]; mu_n = g.mean[fn];
+    }
+    cp_async_commit();
+  };
+  fetch(blockIdx.x);
   for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
     const long long f = fb * FPB + grp; const bool fok = f < g.frames;
     float dx[V][8], xh[V][8];
-    float rs = 0.f, mu = 0.f;
-    if (fok) { rs = g.rstd[f]; mu = g.mean[f]; }
+    const float rs = rs_n, mu = mu_n;
+    cp_async_wait<0>();
 #pragma unroll
     for (int k = 0; k < V; k++) {
       const int u = t + k * G;
-      if (fok && u < L8) { ld8(g.dy + f * g.L + 8 * u, dx[k]); ld8(g.cin + f * g.L + 8 * u, xh[k]); }
+      if (fok && u < L8) { ld8(stg + 8 * u, dx[k]); ld8(stg + g.L + 8 * u, xh[k]); }
     }
     float s[2] = {0.f, 0.f};
     float gm[8], bt[8];                                           // this thread's 8 channels (fixed: Cn | 8 G)
@@ -1047,6 +1077,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
       }
     }
     group_sum_db<G, 2>(s, red, par);
+    fetch(fb + gridDim.x);                 // (the sums consumed everything this thread read from its landing units)
     if (!fok) continue;
     const float s1 = s[0] * invL, s2 = s[1] * invL;
 #pragma unroll
