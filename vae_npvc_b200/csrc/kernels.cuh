@@ -1331,17 +1331,26 @@ __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float*
   const long long f = (long long)blockIdx.x * nw + w;
   float lp = 0.f, db = 0.f;
   if (f < frames) {
-    for (int i = lane; i < ld; i += 32) {
-      float g = 0.f;
-      if (i < H) {
-        float d = xh[f * H + i] - x[f * H + i];
-        lp += -0.5f * (NPVC_LOG_2PI + d * d / NPVC_ONE_PLUS_EPS);
-        g = d / NPVC_ONE_PLUS_EPS * inv_n;
-        db += g;
-      }
-      if (dxh) {
-        if (out_split) split_st1(reinterpret_cast<uint16_t*>(dxh) + f * 2 * ld + i, ld, g);
-        else dxh[f * ld + i] = g;
+    const float* xr = x + f * H; const float* hr = xh + f * H;
+    for (int i0 = lane; i0 < ld; i0 += 128) {          // 4 x 2 loads in flight per lane (same element order per lane as a plain loop)
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int i = i0 + 32 * u; const bool ok = i < H; a[u] = ok ? hr[i] : 0.f; b[u] = ok ? xr[i] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + 32 * u;
+        if (i >= ld) break;
+        float g = 0.f;
+        if (i < H) {
+          float d = a[u] - b[u];
+          lp += -0.5f * (NPVC_LOG_2PI + d * d / NPVC_ONE_PLUS_EPS);
+          g = d / NPVC_ONE_PLUS_EPS * inv_n;
+          db += g;
+        }
+        if (dxh) {
+          if (out_split) split_st1(reinterpret_cast<uint16_t*>(dxh) + f * 2 * ld + i, ld, g);
+          else dxh[f * ld + i] = g;
+        }
       }
     }
   }
