@@ -172,7 +172,7 @@ void launch_wgrad(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
 // accumulator sets, so the epilogue of a tile overlaps the next tile's mainloop (measured on a B200,
 // profiles/r2a_switches.txt: E4 dgrad 0.099 -> 0.068 ms, E4 0.072 -> 0.064, E3 dgrad 0.078 -> 0.065, heads dgrad
 // 0.049 -> 0.044; the long-K G3 forward and the 4104-column G3 dgrad were faster with wide tiles and keep them)
-inline int bn_cap(const Op& o) { return (o.K <= 1024 && o.N <= 1024) ? 128 : 256; }
+inline int bn_cap(const Op& o) { return ((o.K <= 1024 && o.N <= 1024) || o.K <= 256) ? 128 : 256; }
 int pick_bn(int N, int cap, int* n_tiles) {
   if (N <= cap) { *n_tiles = 1; return (N + 15) / 16 * 16; }
   int best_bn = cap, best_t = (N + cap - 1) / cap; long long best_cost = (long long)best_bn * best_t + (cap < 256 ? 8LL * best_t : 0LL);

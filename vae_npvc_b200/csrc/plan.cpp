@@ -373,7 +373,11 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
   // zs: the sampled z (or the caller's z in decode()) as operand planes for the merge GEMM
   int b_zs = B.add_buf("zs", zk, 0, false, SPLIT);
   int b_dz = B.add_buf("dz", z, 0, true), b_dhz = B.add_buf("dhz", 2 * z, 0, true, SPLIT);
-  const int hm_flen = (-G[0].lo + gh + G[0].hi) * gcp, hm_off = -G[0].lo * gcp;
+  // The merge GEMM writes the interior of the padded frame: a lead of < 16 elements in front of the frame puts the interior
+  // (and, with a frame length that is a multiple of 16, every row of the output) on 32-byte boundaries of both planes, which
+  // is what the epilogue's 32-byte stores need (88 elements of front padding alone left it on 16-byte stores).
+  const int hm_lead = (16 - (-G[0].lo * gcp) % 16) % 16;
+  const int hm_flen = ((-G[0].lo + gh + G[0].hi) * gcp + hm_lead + 15) / 16 * 16, hm_off = -G[0].lo * gcp + hm_lead;
   int b_hm = B.add_buf("hm", hm_flen, 0, false, SPLIT);
   int b_dhm = B.add_buf("dhm", Nm, 0, true, SPLIT);
   std::vector<int> b_cg(nG, -1), b_mg(nG, -1), b_ag(nG, -1), b_rg(nG, -1), b_dcg(nG, -1), b_dag(nG, -1);
@@ -464,7 +468,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
     snprintf(nm, sizeof nm, "convT_g%d", g);
     Op& o = B.op(OP_GEMM, PH_DEC, nm);
     if (!l.dense) {
-      VA_g[g] = B.view(src, l.Hi, sflen, l.Cip, 0, sflen);
+      VA_g[g] = B.view(src, l.Hi, sflen, l.Cip, g == 0 ? hm_lead : 0, sflen);
       o.A = VA_g[g]; o.K = l.wn * l.Cip; o.B = B.aw(A_gf[g]); o.ldb = ld_gf[g]; o.N = l.s * l.Co;
       o.tap_T = l.wn; o.tap_C = l.Cip; o.tap_s = 1;
       o.C = B.view(B.ws(b_cg[g]), l.Hi, l.Ho * l.Co, l.s * l.Co, 0, l.Ho * l.Co);
