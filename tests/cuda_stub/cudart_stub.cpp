@@ -152,6 +152,11 @@ cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind) { 
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind, cudaStream_t st) {
   log_op(4, (uint64_t)(uintptr_t)st, 0, (uint64_t)(uintptr_t)d, n); memmove(d, s, n); return cudaSuccess;
 }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t hgt, enum cudaMemcpyKind, cudaStream_t st) {
+  log_op(4, (uint64_t)(uintptr_t)st, 0, (uint64_t)(uintptr_t)d, hgt ? (hgt - 1) * dp + w : 0);
+  for (size_t r = 0; r < hgt; r++) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+  return cudaSuccess;
+}
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) {
   log_op(3, (uint64_t)(uintptr_t)st, 0, (uint64_t)(uintptr_t)d, n); memset(d, v, n); return cudaSuccess;
 }

@@ -248,7 +248,7 @@ class Interp:
     def op_6(self, op):    # RECON
         H, ld, n = op["i0"], op["i1"], self.n
         x = self.x.reshape(n, H)
-        xh = self.flat(op["r1"])[0][:n * H].reshape(n, H)
+        xh = self.flat(op["r1"])[0][:n * ld].reshape(n, ld)[:, :H]     # (rows at the pitch of dxh; pads never written)
         d = xh - x
         acc = self.buf("acc")
         acc[1] = np.nan_to_num(acc[1]) + (-0.5 * (LOG_2PI + d * d / ONE_PLUS_EPS)).sum()
@@ -282,5 +282,5 @@ class Interp:
         acc = self.buf("acc")
         kl, lp = acc[0] / self.n_total, acc[1] / self.n_total
         return {"mu": self.buf("mu").reshape(self.n, z), "lv": self.buf("lv").reshape(self.n, z),
-                "z": self.buf("z").reshape(self.n, z), "xh": self.buf("xh").reshape(self.n, -1),
+                "z": self.buf("z").reshape(self.n, z), "xh": self.buf("xh").reshape(self.n, -1)[:, :self.plan["out_dim"]],
                 "D_KL": kl, "logP": lp, "G": -lp + kl, "grad": self.grad}

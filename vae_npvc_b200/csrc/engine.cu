@@ -1143,7 +1143,8 @@ int npvc_decode(npvc_handle* h, const float* d_theta, const float* d_z, const in
     Ctx c{h, (float*)d_ws, cap, false, d_theta, nullptr, nullptr, d_y + c0, nullptr, m, n, st};
     CUDA_TRY(cudaMemcpyAsync(c.ws + p.buf_offset(p.buf_z, cap, false), d_z + c0 * z, (size_t)m * z * 4, cudaMemcpyDeviceToDevice, st));
     rc = run_phase(c, PH_DEC); if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d_xh + c0 * H, c.ws + p.buf_offset(p.buf_xh, cap, false), (size_t)m * H * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpy2DAsync(d_xh + c0 * H, (size_t)H * 4, c.ws + p.buf_offset(p.buf_xh, cap, false), (size_t)p.bufs[p.buf_xh].per_frame * 4, (size_t)H * 4, (size_t)m,
+                               cudaMemcpyDeviceToDevice, st));      // (workspace rows at the padded pitch)
   }
   h->last_chunk = cap; h->last_train = false;
   return NPVC_OK;
@@ -1177,8 +1178,9 @@ static int loss_core(npvc_handle* h, const float* d_theta, const float* d_x, con
     for (int ph : {PH_ENC, PH_SAMPLE, PH_DEC, PH_LOSS}) { rc = run_phase(c, ph); if (rc) return rc; }
     if (d_grad) { rc = run_phase(c, PH_BWD); if (rc) return rc; }
     struct { float* dst; int buf; int w; } outs[4] = {{d_z, p.buf_z, z}, {d_mu, p.buf_mu, z}, {d_lv, p.buf_lv, z}, {d_xh, p.buf_xh, H}};
-    for (auto& o : outs)
-      if (o.dst) CUDA_TRY(cudaMemcpyAsync(o.dst + c0 * o.w, wset + p.buf_offset(o.buf, cap, true), (size_t)m * o.w * 4, cudaMemcpyDeviceToDevice, cst));
+    for (auto& o : outs)      // (2-D: the workspace rows of xh are at the padded pitch)
+      if (o.dst) CUDA_TRY(cudaMemcpy2DAsync(o.dst + c0 * o.w, (size_t)o.w * 4, wset + p.buf_offset(o.buf, cap, true), (size_t)p.bufs[o.buf].per_frame * 4, (size_t)o.w * 4, (size_t)m,
+                                            cudaMemcpyDeviceToDevice, cst));
   }
   if (d_grad) {
     Ctx c{h, ws, cap, true, d_theta, d_grad, nullptr, nullptr, nullptr, 0, n, st};

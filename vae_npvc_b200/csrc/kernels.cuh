@@ -1331,7 +1331,7 @@ __global__ void recon_kernel(const float* x, const float* xh, float* dxh, float*
   const long long f = (long long)blockIdx.x * nw + w;
   float lp = 0.f, db = 0.f;
   if (f < frames) {
-    const float* xr = x + f * H; const float* hr = xh + f * H;
+    const float* xr = x + f * H; const float* hr = xh + f * ld;       // (xh rows at the pitch of dxh)
     for (int i0 = lane; i0 < ld; i0 += 128) {          // 4 x 2 loads in flight per lane (same element order per lane as a plain loop)
       float a[4], b[4];
 #pragma unroll

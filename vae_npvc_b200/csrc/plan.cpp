@@ -398,7 +398,9 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
     snprintf(nm, sizeof nm, "dc_g%d", g);   b_dcg[g] = B.add_buf(nm, dcg_flen[g], 0, true, SPLIT);
     snprintf(nm, sizeof nm, "da_g%d", g);   b_dag[g] = B.add_buf(nm, L, 0, true); p.bufs[b_dag[g]].alias = b_da;
   }
-  p.buf_xh = B.add_buf("xh", a.in_h, 0, false);
+  // reconstruction rows at the 32-byte aligned pitch of dxh: the last layer's epilogue stores 32 bytes per thread (a
+  // 513-float pitch left every row on 4-byte stores); the pad floats are never written nor read
+  p.buf_xh = B.add_buf("xh", xhld, 0, false);
   int b_dxh = B.add_buf("dxh", xhld, 0, true, SPLIT);
 
   // ---------------------------------------------------------------- ops
@@ -482,7 +484,7 @@ std::string build_plan(const npvc_arch& a, Plan& p, bool use_umma, bool fuse) {
     } else {
       VA_g[g] = B.view(src, 1, sflen, 0, 0, sflen);
       o.A = VA_g[g]; o.K = l.Hi * l.Ci; o.B = B.aw(A_gf[g]); o.ldb = ld_gf[g]; o.N = l.Ho * l.Co;
-      o.C = B.view(B.ws(p.buf_xh), 1, a.in_h, 0, 0, a.in_h);
+      o.C = B.view(B.ws(p.buf_xh), 1, xhld, 0, 0, xhld);
       o.bias[0] = B.th(poff(P_gb[g])); o.bias_mod = l.Co;
     }
   }
