@@ -33,7 +33,7 @@ struct StubUmma {
   int32_t n_tiles, acc_sets, tapT, tapC, tapP, b_tile_al, d_sw, rows_al, tiles_per_split, ld;
   uint64_t c_ptr; int64_t c_fs; int32_t c_R, c_rs, c_off, c_flen, c_pred, c_split;
   uint64_t out_ptr;
-  int32_t a_boxes, ln_on, ln_store_c, ln_L, ln_Cn, ln_out_flen, ln_out_off, pad_; uint64_t ln_aout;
+  int32_t a_boxes, ln_on, ln_store_c, ln_L, ln_Cn, ln_out_flen, ln_out_off, b_res; uint64_t ln_aout;
 };
 struct StubLaunch {
   char name[192];
@@ -97,7 +97,7 @@ void record_launch(const void* func, dim3 grid, dim3 block, void** args, size_t 
     u.Rb = g.rt.Rb; u.Ra = g.rt.Ra; u.Ab = g.rt.Ab; u.FB = g.rt.FB; u.TA = g.rt.TA; u.RbH = g.rt.RbH; u.rows_tile = g.rt.rows_tile;
     u.frames = g.rt.frames; u.m_tiles = g.rt.m_tiles; u.n_tiles = g.n_tiles; u.acc_sets = g.acc_sets; u.tapT = g.tapT; u.tapC = g.tapC;
     u.tapP = g.tapP; u.b_tile_al = g.b_tile_al; u.d_sw = g.d_sw; u.rows_al = g.rows_al; u.tiles_per_split = g.tiles_per_split; u.ld = g.ld;
-    u.a_boxes = g.a_boxes; u.ln_on = g.ln.on; u.ln_store_c = g.ln.store_c; u.ln_L = g.ln.L; u.ln_Cn = g.ln.Cn; u.ln_out_flen = g.ln.out_flen; u.ln_out_off = g.ln.out_off;
+    u.a_boxes = g.a_boxes; u.b_res = g.b_res; u.ln_on = g.ln.on; u.ln_store_c = g.ln.store_c; u.ln_L = g.ln.L; u.ln_Cn = g.ln.Cn; u.ln_out_flen = g.ln.out_flen; u.ln_out_off = g.ln.out_off;
     u.ln_aout = (uint64_t)(uintptr_t)g.ln.aout;
     u.c_ptr = (uint64_t)(uintptr_t)g.C.p; u.c_fs = g.C.fs; u.c_R = g.C.R; u.c_rs = g.C.rs; u.c_off = g.C.off; u.c_flen = g.C.flen;
     u.c_pred = g.C.pred; u.c_split = g.C.split; u.out_ptr = (uint64_t)(uintptr_t)g.out;

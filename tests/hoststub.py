@@ -34,7 +34,7 @@ class StubUmma(C.Structure):
     _fields_ = [(k, C.c_int32) for k in _UMMA_INTS] + [
         ("c_ptr", C.c_uint64), ("c_fs", C.c_int64), ("c_R", C.c_int32), ("c_rs", C.c_int32), ("c_off", C.c_int32),
         ("c_flen", C.c_int32), ("c_pred", C.c_int32), ("c_split", C.c_int32), ("out_ptr", C.c_uint64)] + [
-        (k, C.c_int32) for k in ("a_boxes", "ln_on", "ln_store_c", "ln_L", "ln_Cn", "ln_out_flen", "ln_out_off", "pad_")] + [("ln_aout", C.c_uint64)]
+        (k, C.c_int32) for k in ("a_boxes", "ln_on", "ln_store_c", "ln_L", "ln_Cn", "ln_out_flen", "ln_out_off", "b_res")] + [("ln_aout", C.c_uint64)]
 
 
 class StubLaunch(C.Structure):

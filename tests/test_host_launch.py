@@ -73,7 +73,11 @@ def check_recording(rec, n):
             else:                                                 # window mode (single CTA or CTA pair)
                 assert sw in (64, 128) and st >= 1 and u["kblocks"] == -(-u["K"] // (sw // 2)), u
                 bt = (BN // 2 if pair else BN) * sw
-                ring = st * (2 * 128 * sw + 2 * bt)
+                if u["b_res"]:                                    # resident weights in front of a ring of activation stages
+                    assert not pair and u["n_tiles"] == 1 and st >= 3 and bt % 1024 == 0 and L["grid"][0] < u["m_tiles"], u
+                    ring = u["kblocks"] * 2 * bt + st * 2 * 128 * sw
+                else:
+                    ring = st * (2 * 128 * sw + 2 * bt)
                 assert box_bytes(tm[0]) == u["rows_tile"] * sw and box_bytes(tm[2]) == bt, (u, tm[0]["box"], tm[2]["box"])
                 if pair:
                     assert sw == 128 and bt % 1024 == 0 and u["m_tiles"] >= 2 and L["grid"][0] <= 148, u
@@ -181,6 +185,7 @@ SWITCHES = {
     "everything": {"NPVC_PAIR": "2", "NPVC_WGRAD_PAIR": "2"},
     "window_only": {"NPVC_UMMA_TAP": "0"},
     "no_overlap": {"NPVC_OVERLAP": "0"},
+    "no_resident_weights": {"NPVC_UMMA_BRES": "0"},
 }
 
 

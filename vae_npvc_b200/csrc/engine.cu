@@ -54,6 +54,7 @@ struct npvc_handle {
   int64_t umma_launches = 0;
   int ln_bulk = 1;                   // double-buffered bulk-copy Layernorm backward for frames > 2048 floats
   int wgrad_smem_kb = 225;           // shared-memory budget of the weight-gradient kernel
+  int umma_bres = 1;                 // NPVC_UMMA_BRES=0: window mode re-loads the weight tiles with every stage (A/B comparisons)
   int overlap_wgrad = 1;             // NPVC_OVERLAP=0: weight gradients on the caller's stream (A/B comparisons, per-op profiling)
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
   bool pack_defer = false, pack_pending = false;   // training call: the pack ops after the first run beside the first layer (run_phase)
@@ -442,11 +443,18 @@ int launch_umma(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool*
   }
   UmmaArgs g; memset(&g, 0, sizeof g);
   g.K = o.K; g.N = o.N; g.BN = BN; g.kblocks = (o.K + bk - 1) / bk; g.rt = rt; g.n_tiles = n_tiles; g.sw = sw;
-  const int stage_bytes = 2 * 128 * sw + 2 * BN * sw;
+  int stage_bytes = 2 * 128 * sw + 2 * BN * sw;
   g.acc_sets = 512 / (2 * BN) >= 4 ? 4 : (512 / (2 * BN) >= 2 ? 2 : 1);   // accumulator ring in TMEM: the epilogue of tile i overlaps the mainloops of the next tiles
   int tc = 32; while (tc < g.acc_sets * 2 * BN) tc *= 2; g.tmem_cols = tc;
   bool fuse_ln = ln_epilogue_ok(c, o, ln, rt, n_tiles) && (225 * 1024 - 6144 - LN_EPI_SMEM) / stage_bytes >= 2;
-  int stages = (225 * 1024 - 6144 - (fuse_ln ? LN_EPI_SMEM : 0)) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
+  const int budget = 225 * 1024 - 6144 - (fuse_ln ? LN_EPI_SMEM : 0);
+  // resident weights (launch_args.h, b_res): one N tile, CTAs that run several tiles, and the tiles of all k-blocks fit in
+  // front of >= 3 activation stages
+  const int bres_bytes = g.kblocks * 2 * BN * sw;
+  if (h->umma_bres && n_tiles == 1 && rt.m_tiles >= 2 * h->sm_count && (budget - bres_bytes) / (2 * 128 * sw) >= 3) {
+    g.b_res = 1; stage_bytes = 2 * 128 * sw;
+  }
+  int stages = (budget - (g.b_res ? bres_bytes : 0)) / stage_bytes; if (stages > 10) stages = 10; if (stages < 1) stages = 1;
   g.stages = stages;
   g.merge = (h->umma_merge && 2 * BN <= 256) ? 1 : 0;
   g.C = dview(c, o.C);
@@ -456,7 +464,7 @@ int launch_umma(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool*
     CUDA_TRY(cudaFuncSetAttribute(umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     h->attr_fwd = true;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 11) + 32 + 4096 + (fuse_ln ? LN_EPI_SMEM : 0);   // + bias_s[4][256]
+  const size_t smem = (size_t)stages * stage_bytes + (g.b_res ? bres_bytes : 0) + 1024 + 8 * (2 * stages + 11) + 32 + 4096 + (fuse_ln ? LN_EPI_SMEM : 0);   // + bias_s[4][256]
   long long total = rt.m_tiles * n_tiles;
   unsigned grid = (unsigned)(total < h->sm_count ? total : h->sm_count);
   if (fuse_ln) {
@@ -986,6 +994,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   { const char* pd = getenv("NPVC_PDL"); g_pdl = (pd && !atoi(pd)) ? 0 : 1; }      // (process-wide: the launch helper has no handle)
   if (const char* nv = getenv("NPVC_NVTX")) h->nvtx = atoi(nv);
   if (const char* mg = getenv("NPVC_UMMA_MERGE")) h->umma_merge = atoi(mg);
+  if (const char* br = getenv("NPVC_UMMA_BRES")) h->umma_bres = atoi(br);
   if (const char* fl = getenv("NPVC_FUSE_LN_TRAIN")) h->fuse_ln_train = atoi(fl);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);

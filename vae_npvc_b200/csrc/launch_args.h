@@ -56,6 +56,10 @@ struct UmmaArgs {
   // and a second adds  Al.Bh  to the correction: two MMAs per K step instead of three.  The few-tap layers are paced by the
   // MMA warp's instruction stream (a small-N MMA costs ~90 cycles whatever its N), so this is a third less of it.
   int merge;
+  // b_res != 0 (window mode, single CTA, one N tile): the weight tiles of ALL k-blocks (hi, lo) are loaded once per CTA and
+  // stay in shared memory in front of the ring, whose stages then hold the activation tiles only -- a persistent CTA's tiles
+  // no longer re-fetch the same weights from L2 (layers whose weights fit beside >= 3 activation stages: G0, its dgrad, ...)
+  int b_res;
   DView C;
   const float* bias0; const float* bias1; const float* bias2; int bias_mod;
   LnEpi ln;

@@ -238,8 +238,10 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   const uint32_t a_tile_bytes = (uint32_t)BM * sw, b_tile_bytes = (uint32_t)(PAIR ? g.BN >> 1 : g.BN) * sw;   // (PAIR: this CTA's half of the B tile)
   const bool tap = !PAIR && g.tapT > 0;        // (the pair form exists in window mode only)
   // tap mode: [resident weights: tapT x (hi, lo) tiles][stages x tapP x (hi, lo) A tiles]
-  const uint32_t bres_bytes = tap ? (uint32_t)g.tapT * 2u * (uint32_t)g.b_tile_al : 0u;
-  const uint32_t stage_bytes = tap ? (uint32_t)g.tapP * 2u * a_tile_bytes : 2u * a_tile_bytes + 2u * b_tile_bytes;
+  // window mode with resident weights (g.b_res): [kblocks x (hi, lo) weight tiles][stages x (hi, lo) A tiles]
+  const bool bres = !PAIR && !tap && g.b_res != 0;
+  const uint32_t bres_bytes = tap ? (uint32_t)g.tapT * 2u * (uint32_t)g.b_tile_al : (bres ? (uint32_t)g.kblocks * 2u * b_tile_bytes : 0u);
+  const uint32_t stage_bytes = tap ? (uint32_t)g.tapP * 2u * a_tile_bytes : 2u * a_tile_bytes + (bres ? 0u : 2u * b_tile_bytes);
   const uint32_t ring = sbase + bres_bytes;
   const uint32_t bar_base = ring + (uint32_t)g.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -366,7 +368,17 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
     // (PAIR: the leader's full barrier counts the bytes of both CTAs' loads)
-    const uint32_t tx = (PAIR ? 2u : 1u) * (2u * (uint32_t)g.rt.rows_tile * sw + 2u * b_tile_bytes);
+    const uint32_t tx = (PAIR ? 2u : 1u) * (2u * (uint32_t)g.rt.rows_tile * sw + (bres ? 0u : 2u * b_tile_bytes));
+    if (bres) {                                      // the weights of every k-block, once per CTA (one N tile: n0 = 0)
+      if (elect_one()) {
+        mbar_expect_tx(bres_bar, (uint32_t)g.kblocks * 2u * b_tile_bytes);
+        for (int kb = 0; kb < g.kblocks; kb++) {
+          tma_load_2d(sbase + (uint32_t)(2 * kb) * b_tile_bytes, &tmBh, bres_bar, kb * bk, 0);
+          tma_load_2d(sbase + (uint32_t)(2 * kb + 1) * b_tile_bytes, &tmBl, bres_bar, kb * bk, 0);
+        }
+      }
+      __syncwarp();
+    }
     RingPos sp(g.stages);
     for (int t = NPVC_TILE0; t < total_tiles; t += NPVC_TILE_STEP) {
       int mt = t / g.n_tiles; int n0 = (t - mt * g.n_tiles) * g.BN;
@@ -378,7 +390,7 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       for (int kb = 0; kb < g.kblocks; kb++, sp.advance()) {
         const int s = sp.idx;
         mbar_wait(empty_bar(s), sp.phase ^ 1u);
-        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        const uint32_t st = ring + (uint32_t)s * stage_bytes;
         if constexpr (PAIR) {
           const uint32_t lead_full = mapa_rank(full_bar(s), 0u);
           if (elect_one()) {
@@ -392,8 +404,10 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           mbar_expect_tx(full_bar(s), tx);
           tma_load_4d(st, &tmAh, full_bar(s), kb * bk, 0, a0, f0);
           tma_load_4d(st + a_tile_bytes, &tmAl, full_bar(s), kb * bk, 0, a0, f0);
-          tma_load_2d(st + 2u * a_tile_bytes, &tmBh, full_bar(s), kb * bk, n0);
-          tma_load_2d(st + 2u * a_tile_bytes + b_tile_bytes, &tmBl, full_bar(s), kb * bk, n0);
+          if (!bres) {
+            tma_load_2d(st + 2u * a_tile_bytes, &tmBh, full_bar(s), kb * bk, n0);
+            tma_load_2d(st + 2u * a_tile_bytes + b_tile_bytes, &tmBl, full_bar(s), kb * bk, n0);
+          }
         }
         __syncwarp();
       }
@@ -410,6 +424,7 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     const uint32_t idesc_m = make_idesc(2 * g.BN, false, BM);          // (merge: single-CTA forms only)
     const bool merge_w = g.merge != 0;
     const uint64_t dbase = sdesc_base(0, sw);
+    if (bres) mbar_wait(bres_bar, 0);
     RingPos sp(g.stages), ap(g.acc_sets);
     for (int t = (PAIR && rank != 0u) ? total_tiles : NPVC_TILE0; t < total_tiles; t += NPVC_TILE_STEP, ap.advance()) {   // (PAIR: the leader issues for both CTAs)
       const int buf = ap.idx;
@@ -420,9 +435,10 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         const int s = sp.idx;
         mbar_wait(full_bar(s), sp.phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = sbase + (uint32_t)s * stage_bytes;
+        const uint32_t st = ring + (uint32_t)s * stage_bytes;
         const uint64_t ah = sdesc_at(dbase, st), al = sdesc_at(dbase, st + a_tile_bytes);
-        const uint64_t bh = sdesc_at(dbase, st + 2u * a_tile_bytes), bl = sdesc_at(dbase, st + 2u * a_tile_bytes + b_tile_bytes);
+        const uint32_t bt = bres ? sbase + (uint32_t)(2 * kb) * b_tile_bytes : st + 2u * a_tile_bytes;
+        const uint64_t bh = sdesc_at(dbase, bt), bl = sdesc_at(dbase, bt + b_tile_bytes);
         if constexpr (PAIR) {
           if (elect_one()) {
             for (int k4 = 0; k4 < ksteps; k4++) {
