@@ -186,6 +186,7 @@ SWITCHES = {
     "window_only": {"NPVC_UMMA_TAP": "0"},
     "no_overlap": {"NPVC_OVERLAP": "0"},
     "no_resident_weights": {"NPVC_UMMA_BRES": "0"},
+    "ln_bwd_prefetch": {"NPVC_PREFETCH_MIN": "0", "NPVC_PREFETCH_E0_MIN": "0"},
 }
 
 

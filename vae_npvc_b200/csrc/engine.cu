@@ -54,6 +54,7 @@ struct npvc_handle {
   int64_t umma_launches = 0;
   int ln_bulk = 1;                   // double-buffered bulk-copy Layernorm backward for frames > 2048 floats
   int wgrad_smem_kb = 225;           // shared-memory budget of the weight-gradient kernel
+  long long prefetch_e0_min = 0, prefetch_min = 0;     // frames from which the Layernorm-backward kernels prefetch (PREFETCH_MIN_FRAMES; set in npvc_create)
   int umma_bres = 1;                 // NPVC_UMMA_BRES=0: window mode re-loads the weight tiles with every stage (A/B comparisons)
   int overlap_wgrad = 1;             // NPVC_OVERLAP=0: weight gradients on the caller's stream (A/B comparisons, per-op profiling)
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
@@ -173,6 +174,14 @@ void launch_wgrad(const WgradArgs& g, bool scalar, int sms, cudaStream_t st) {
 // accumulator sets, so the epilogue of a tile overlaps the next tile's mainloop (measured on a B200,
 // profiles/r2a_switches.txt: E4 dgrad 0.099 -> 0.068 ms, E4 0.072 -> 0.064, E3 dgrad 0.078 -> 0.065, heads dgrad
 // 0.049 -> 0.044; the long-K G3 forward and the 4104-column G3 dgrad were faster with wide tiles and keep them)
+// Frame prefetch of the Layernorm-backward kernels (kernels.cuh ln_bwd_reg_kernel, fused_e0.cuh e0_bwd_kernel): the next
+// frame's dy / c land in shared memory (cp.async) while the current one is computed.  Timed alone the kernels gain (first
+// layer 0.153 -> 0.099 ms, the five register-resident layers -0.02 ms together), but the step does not: their 50-60 KB of
+// shared memory per block keep them from sharing SMs with the side stream's weight-gradient GEMMs (cfg1: 0.955 ms with the
+// prefetch, 0.895 ms without; cfg2, 60-step runs alternated on one box: 3.644 ms without, 3.644 / 3.663 ms with either
+// one), so it is OFF unless NPVC_PREFETCH_MIN / NPVC_PREFETCH_E0_MIN (frames from which it applies) ask for it; the GPU
+// switch-equivalence test runs it.
+constexpr long long PREFETCH_MIN_FRAMES = 1LL << 62;
 inline int bn_cap(const Op& o) { return ((o.K <= 1024 && o.N <= 1024) || o.K <= 256) ? 128 : 256; }
 int pick_bn(int N, int cap, int* n_tiles) {
   if (N <= cap) { *n_tiles = 1; return (N + 15) / 16 * 16; }
@@ -616,7 +625,8 @@ int launch_e0_bwd(Ctx& c, const Op& o, const Op& nx) {      // o: OP_LN_BWD of t
   const int bt = E0_BLOCK(G), fpb = bt / G;
   const long long fbs = (c.n + fpb - 1) / fpb;
   long long blocks = (long long)h->sm_count * (512 / bt); if (blocks > fbs) blocks = fbs;
-  const size_t sm = e0_bwd_smem_floats(g.Co, fpb, g.xp, o.L) * sizeof(float);      // (rows and the prefetched dy / c: fused_e0.cuh)
+  g.prefetch = c.n >= h->prefetch_e0_min ? 1 : 0;
+  const size_t sm = e0_bwd_smem_floats(g.Co, fpb, g.xp, o.L, g.prefetch) * sizeof(float);      // (rows and the prefetched dy / c: fused_e0.cuh)
   if (sm > 110 * 1024) return fail(NPVC_ERR_ARG, "fused first-layer backward: frame too long for the staging buffers");
   const bool v4 = o.L / 4 > 3 * G;                        // units of 4 elements per thread: 3 or 4
   const bool set_attr = !h->attr_e0_bwd; h->attr_e0_bwd = true;      // (one instantiation per handle: the architecture is fixed)
@@ -769,7 +779,7 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
       h->launches++; break;
     }
     case OP_LN_BWD: {
-      LnBwdArgs g; g.dy = resolve(c, o.in); g.cin = resolve(c, o.xhat); g.mean = resolve(c, o.r0); g.rstd = resolve(c, o.rstd);
+      LnBwdArgs g; g.prefetch = 0; g.dy = resolve(c, o.in); g.cin = resolve(c, o.xhat); g.mean = resolve(c, o.r0); g.rstd = resolve(c, o.rstd);
       g.gamma = resolve(c, o.gamma); g.beta = resolve(c, o.beta); g.dc = resolve(c, o.aout);
       g.dgamma = resolve(c, o.dgamma); g.dbeta = resolve(c, o.dbeta); g.dbias = resolve(c, o.dbias);
       g.L = o.L; g.Cn = o.Cn; g.out_flen = o.out_flen; g.out_off = o.out_off; g.frames = c.n;
@@ -780,7 +790,8 @@ int run_op(Ctx& c, const Op& o, int op_index, const Op* ln = nullptr, bool* fuse
       if (G) {
         const long long fbs = (c.n + 256 / G - 1) / (256 / G);
         long long blocks = (long long)h->sm_count * 4; if (blocks > fbs) blocks = fbs;
-        const size_t sm = ((size_t)5 * o.Cn + (size_t)(256 / G) * 2 * o.L) * sizeof(float);      // + landing zone (<= 64 KB)
+        g.prefetch = c.n >= h->prefetch_min ? 1 : 0;
+        const size_t sm = ((size_t)5 * o.Cn + (g.prefetch ? (size_t)(256 / G) * 2 * o.L : (size_t)0)) * sizeof(float);      // + landing zone (<= 64 KB)
         if (!h->attr_ln_reg) {
           CUDA_TRY(cudaFuncSetAttribute(ln_bwd_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
           CUDA_TRY(cudaFuncSetAttribute(ln_bwd_reg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -995,6 +1006,8 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* nv = getenv("NPVC_NVTX")) h->nvtx = atoi(nv);
   if (const char* mg = getenv("NPVC_UMMA_MERGE")) h->umma_merge = atoi(mg);
   if (const char* br = getenv("NPVC_UMMA_BRES")) h->umma_bres = atoi(br);
+  h->prefetch_min = PREFETCH_MIN_FRAMES; if (const char* pm = getenv("NPVC_PREFETCH_MIN")) h->prefetch_min = atoll(pm);
+  h->prefetch_e0_min = PREFETCH_MIN_FRAMES; if (const char* pm = getenv("NPVC_PREFETCH_E0_MIN")) h->prefetch_e0_min = atoll(pm);
   if (const char* fl = getenv("NPVC_FUSE_LN_TRAIN")) h->fuse_ln_train = atoi(fl);
   if (const char* pr = getenv("NPVC_PAIR")) h->umma_pair = atoi(pr);
   if (const char* wp = getenv("NPVC_WGRAD_PAIR")) h->wgrad_pair = atoi(wp);

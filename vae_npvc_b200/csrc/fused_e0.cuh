@@ -32,6 +32,7 @@ struct E0BwdArgs {
   float* dW;                    // [k][Co] packed weight gradient (accumulated)
   float* dgamma; float* dbeta; float* dbias;
   int Hi, Ho, Co, k, s, pl, xp; long long frames;
+  int prefetch;                 // dy / c of the next frame land in shared memory while this one is computed (LnBwdArgs::prefetch)
 };
 
 constexpr int E0_KT = 8;        // taps per position (weights beyond k are zero)
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 768 / E0_BLOCK(G)) e0_fwd_kernel(
 
 // floats of dynamic shared memory of e0_bwd_kernel (FPB frames per block)
 constexpr int E0_PF = 1;        // frames in flight ahead of the one being computed (backward); 2 measured no faster
-__host__ __device__ inline size_t e0_bwd_smem_floats(int Co, int FPB, int xp, int L) {
-  return (size_t)(E0_KT + 5) * Co + (size_t)(E0_PF + 2) * FPB * xp + (size_t)(E0_PF + 1) * FPB * 2 * L;
+__host__ __device__ inline size_t e0_bwd_smem_floats(int Co, int FPB, int xp, int L, int prefetch) {
+  return (size_t)(E0_KT + 5) * Co + (size_t)(E0_PF + 2) * FPB * xp + (prefetch ? (size_t)(E0_PF + 1) * FPB * 2 * L : (size_t)0);
 }
 
 // G threads per frame, V units of 4 consecutive channels per thread (L <= 4 G V).  A block's next E0_PF frames (dy, the
@@ -170,16 +171,19 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(
   for (int e = 0; e < 4; e++) { gm[e] = sgm[c0 + e]; bt[e] = sbt[c0 + e]; adg[e] = adb[e] = adc[e] = 0.f; }
 #pragma unroll
   for (int kk = 0; kk < E0_KT; kk++) dw[kk][0] = dw[kk][1] = make_float2(0.f, 0.f);
+  const bool pf = g.prefetch != 0;                     // (else only the input row travels ahead; dy / c are read in place)
   // one commit group per call, empty past the end: group k holds frame-block k of this block
   auto fetch = [&](long long fbn, int buf, int xb, float& rs_n, float& mu_n) {
     const long long fn = fbn * FPB + grp;
     if (fn < g.frames) {
-      float4* sd = reinterpret_cast<float4*>(stg0 + (size_t)buf * FPB * 2 * L) + t;
-      const float4* dyp = reinterpret_cast<const float4*>(g.dy + fn * L) + t;
-      const float4* cp = reinterpret_cast<const float4*>(g.cin + fn * L) + t;
+      if (pf) {
+        float4* sd = reinterpret_cast<float4*>(stg0 + (size_t)buf * FPB * 2 * L) + t;
+        const float4* dyp = reinterpret_cast<const float4*>(g.dy + fn * L) + t;
+        const float4* cp = reinterpret_cast<const float4*>(g.cin + fn * L) + t;
 #pragma unroll
-      for (int i = 0; i < V; i++)
-        if (t + i * G < L4) { cp_async16(sd + i * G, dyp + i * G); cp_async16(sd + L4 + i * G, cp + i * G); }
+        for (int i = 0; i < V; i++)
+          if (t + i * G < L4) { cp_async16(sd + i * G, dyp + i * G); cp_async16(sd + L4 + i * G, cp + i * G); }
+      }
       float* xs = xs0 + xb * FPB * XP; const float* xp = g.x + fn * g.Hi;
       for (int i = t; i < XP; i += G) { const int xi = i - g.pl; const bool ok = xi >= 0 && xi < g.Hi; cp_async4_zfill(xs + i, ok ? xp + xi : xp, ok ? 4 : 0); }
       rs_n = g.rstd[fn]; mu_n = g.mean[fn];
@@ -201,11 +205,12 @@ __global__ void __launch_bounds__(E0_BLOCK(G), 512 / E0_BLOCK(G)) e0_bwd_kernel(
     fetch(fb + (long long)E0_PF * gridDim.x, (sb + E0_PF) % (E0_PF + 1), (xb + E0_PF) % (E0_PF + 2), rs_n[E0_PF - 1], mu_n[E0_PF - 1]);
     cp_async_wait<E0_PF>();                            // this frame's group has landed (own copies: visible to this thread)
     {
-      const float4* sd = reinterpret_cast<const float4*>(stg0 + (size_t)sb * FPB * 2 * L) + t;
+      const float4* sd = pf ? reinterpret_cast<const float4*>(stg0 + (size_t)sb * FPB * 2 * L) + t : reinterpret_cast<const float4*>(g.dy + f * L) + t;
+      const float4* sc = pf ? sd + L4 : reinterpret_cast<const float4*>(g.cin + f * L) + t;
 #pragma unroll
       for (int i = 0; i < V; i++) {
         if (fok && t + i * G < L4) {
-          const float4 a = sd[i * G], b = sd[L4 + i * G];
+          const float4 a = sd[i * G], b = sc[i * G];
           dx[i][0] = a.x; dx[i][1] = a.y; dx[i][2] = a.z; dx[i][3] = a.w; xh[i][0] = b.x; xh[i][1] = b.y; xh[i][2] = b.z; xh[i][3] = b.w;
         }
       }

@@ -774,6 +774,8 @@ struct LnBwdArgs {
   float* dc; float* dgamma; float* dbeta; float* dbias;
   int L, Cn, out_flen, out_off; long long frames;
   int out_split;      // dc is a split (bf16 hi / lo) buffer
+  int prefetch;       // ln_bwd_reg_kernel: the next frame lands in shared memory while this one is computed (off by default:
+                      // engine.cu, PREFETCH_MIN_FRAMES)
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs g) {
@@ -1026,10 +1028,12 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
 #pragma unroll
   for (int e = 0; e < 8; e++) adg[e] = adb[e] = adc[e] = 0.f;
   const float invL = 1.0f / (float)g.L;
-  float* stg = sbt + g.Cn + (size_t)grp * 2 * g.L;     // this frame slot's [dy | c] landing zone
+  float* stg = sbt + g.Cn + (size_t)grp * 2 * g.L;     // this frame slot's [dy | c] landing zone (g.prefetch)
+  const bool pf = g.prefetch != 0;
   float rs_n = 0.f, mu_n = 0.f;
   auto fetch = [&](long long fbn) {                    // one commit group per call (empty past the end)
     const long long fn = fbn * FPB + grp;
+    if (!pf) return;
     if (fn < g.frames) {
       const float* sd = g.dy + fn * g.L; const float* sc = g.cin + fn * g.L;
 #pragma unroll
@@ -1048,12 +1052,21 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_reg_kernel(LnBwdArgs g) {
   for (long long fb = blockIdx.x; fb * FPB < g.frames; fb += gridDim.x) {
     const long long f = fb * FPB + grp; const bool fok = f < g.frames;
     float dx[V][8], xh[V][8];
-    const float rs = rs_n, mu = mu_n;
-    cp_async_wait<0>();
+    float rs = rs_n, mu = mu_n;
+    if (pf) {
+      cp_async_wait<0>();
 #pragma unroll
-    for (int k = 0; k < V; k++) {
-      const int u = t + k * G;
-      if (fok && u < L8) { ld8(stg + 8 * u, dx[k]); ld8(stg + g.L + 8 * u, xh[k]); }
+      for (int k = 0; k < V; k++) {
+        const int u = t + k * G;
+        if (fok && u < L8) { ld8(stg + 8 * u, dx[k]); ld8(stg + g.L + 8 * u, xh[k]); }
+      }
+    } else {
+      if (fok) { rs = g.rstd[f]; mu = g.mean[f]; }
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        const int u = t + k * G;
+        if (fok && u < L8) { ld8(g.dy + f * g.L + 8 * u, dx[k]); ld8(g.cin + f * g.L + 8 * u, xh[k]); }
+      }
     }
     float s[2] = {0.f, 0.f};
     float gm[8], bt[8];                                           // this thread's 8 channels (fixed: Cn | 8 G)
