@@ -377,3 +377,21 @@ def test_fused_kernels_and_small_batch_tiles_of_the_default_plan():
     small = HS.record_loss_fwd_bwd(arch, 16)
     g3 = [L for L in small.launches if L["umma"] and "umma_fwd" in L["name"] and (L["umma"]["K"], L["umma"]["N"]) == (4104, 513)]
     assert len(g3) == 1 and g3[0]["grid"][0] >= 30 and g3[0]["umma"]["BN"] == 16, g3
+
+
+def test_gemm_output_rows_lie_on_32_byte_boundaries():
+    """An epilogue thread owns one output row, so only whole 32-byte sectors per thread store efficiently (DESIGN.md §6:
+    the merge layer and the last layer were 1.6x / 1.13x slower before their rows were aligned).  Every forward / dgrad
+    launch of the reference architecture must put its rows on 32-byte boundaries of the fp32 buffer / of both bf16 planes;
+    the one known exception (G0's dgrad: 88-element rows of a dense buffer another GEMM reads as K = 1672) is listed."""
+    r = HS.record_loss_fwd_bwd(vcc2016_vae_arch(), 16384)
+    bad = []
+    for L in r.launches:
+        u = L["umma"]
+        if u is None or "umma_fwd_kernel_t" not in L["name"]:
+            continue
+        el = 2 if u["c_split"] else 4                                   # bytes per element of a plane / of the fp32 buffer
+        rows_ok = (u["c_off"] * el) % 32 == 0 and (u["c_fs"] * el) % 32 == 0 and (u["c_R"] == 1 or (u["c_rs"] * el) % 32 == 0)
+        if not (rows_ok and u["c_ptr"] % 32 == 0 and (u["BN"] * el) % 32 == 0):
+            bad.append((u["K"], u["N"]))
+    assert bad == [(288, 88)], bad
