@@ -373,7 +373,7 @@ def test_cta_pair_form_is_bit_identical_to_single_cta(arch, monkeypatch):
 
 EXPERIMENTS = {                    # A/B switches of the library: every form they select must reproduce the default engine
     "wgrad_pair": {"NPVC_WGRAD_PAIR": "1"}, "wgrad_pair_256": {"NPVC_WGRAD_PAIR": "2"}, "wgrad_single": {"NPVC_WGRAD_PAIR": "0"},
-    "no_merge": {"NPVC_UMMA_MERGE": "0"}, "no_pdl": {"NPVC_PDL": "0"}, "no_resident_weights": {"NPVC_UMMA_BRES": "0"},
+    "no_merge": {"NPVC_UMMA_MERGE": "0"}, "no_pdl": {"NPVC_PDL": "0"}, "no_resident_weights": {"NPVC_UMMA_BRES": "0"}, "one_mma_issuer": {"NPVC_UMMA_DUAL": "0"},
     "ln_bwd_prefetch": {"NPVC_PREFETCH_MIN": "0", "NPVC_PREFETCH_E0_MIN": "0"},
 }
 

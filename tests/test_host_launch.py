@@ -61,7 +61,10 @@ def check_recording(rec, n):
             BN, sw, st = u["BN"], u["sw"], u["stages"]
             assert BN % 16 == 0 and 16 <= BN <= 256 and u["acc_sets"] in (1, 2, 4) and tc >= u["acc_sets"] * 2 * BN, u
             groups = (L["block"][0] - 64) // 128
-            assert L["block"][0] == 64 + 128 * groups and groups in (1, 2, 4) and groups <= u["acc_sets"] and u["acc_sets"] % groups == 0, (L["block"], u)
+            issuer2 = L["block"][0] - 64 - 128 * groups                # second MMA issuer warp: tap mode, >= 2 accumulator sets / stages / tiles per CTA
+            assert issuer2 in (0, 32) and groups in (1, 2, 4) and groups <= u["acc_sets"] and u["acc_sets"] % groups == 0, (L["block"], u)
+            if issuer2:
+                assert u["tapT"] > 0 and u["acc_sets"] == 4 and u["stages"] >= 4 and u["m_tiles"] > L["grid"][0], (L["block"], u)
             assert u["n_tiles"] * BN >= u["N"] and (u["n_tiles"] - 1) * BN < u["N"], u
             assert tm[0]["rank"] == 4 and tm[1]["rank"] == 4 and tm[2]["rank"] == 2 and tm[3]["rank"] == 2
             if u["tapT"] > 0:                                     # tap mode
@@ -186,6 +189,7 @@ SWITCHES = {
     "window_only": {"NPVC_UMMA_TAP": "0"},
     "no_overlap": {"NPVC_OVERLAP": "0"},
     "no_resident_weights": {"NPVC_UMMA_BRES": "0"},
+    "one_mma_issuer": {"NPVC_UMMA_DUAL": "0"},
     "ln_bwd_prefetch": {"NPVC_PREFETCH_MIN": "0", "NPVC_PREFETCH_E0_MIN": "0"},
 }
 

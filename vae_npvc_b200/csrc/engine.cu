@@ -55,6 +55,7 @@ struct npvc_handle {
   int ln_bulk = 1;                   // double-buffered bulk-copy Layernorm backward for frames > 2048 floats
   int wgrad_smem_kb = 225;           // shared-memory budget of the weight-gradient kernel
   long long prefetch_e0_min = 0, prefetch_min = 0;     // frames from which the Layernorm-backward kernels prefetch (PREFETCH_MIN_FRAMES; set in npvc_create)
+  int umma_dual = 1;                 // NPVC_UMMA_DUAL=0: one MMA issuer warp in tap mode (A/B comparisons)
   int umma_bres = 1;                 // NPVC_UMMA_BRES=0: window mode re-loads the weight tiles with every stage (A/B comparisons)
   int overlap_wgrad = 1;             // NPVC_OVERLAP=0: weight gradients on the caller's stream (A/B comparisons, per-op profiling)
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
@@ -330,11 +331,17 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg_in, con
   }
   const size_t smem = (size_t)o.tap_T * 2 * tg.b_tile_al + (size_t)tg.stages * tg.P * 2 * 128 * sw + 1024 + 8 * (2 * tg.stages + 11) + 32 + 4096 + (fuse_ln ? LN_EPI_SMEM : 0);
   unsigned grid = (unsigned)(rt.m_tiles < h->sm_count ? rt.m_tiles : h->sm_count);
+  // second MMA issuer warp (umma_gemm.cuh, tap mode): even / odd tiles of a CTA issued by two warps.  Measured at cfg2:
+  // the narrow layers gain (G2 forward 0.145 -> 0.123 ms, its dgrads 0.095 -> 0.074 / 0.097 -> 0.091, G1 dgrad -0.004),
+  // the 96-column ones with 2 accumulator sets lose (E2 dgrad 0.047 -> 0.064, G0 dgrad 0.070 -> 0.087: each issuer then
+  // owns ONE set and ONE or two stages and stalls where a single issuer ran ahead) -- so: 4 sets and >= 4 stages
+  const bool dual = h->umma_dual && g.acc_sets >= 4 && tg.stages >= 4 && rt.m_tiles > (long long)grid;
+  const unsigned threads = 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups) + (dual ? 32 : 0);
   if (fuse_ln) {
     if (!h->attr_fwd_ln) { CUDA_TRY(cudaFuncSetAttribute(umma_fwd_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); h->attr_fwd_ln = true; }
-    launch_k(umma_fwd_ln_kernel, dim3(grid), dim3(64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups)), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+    launch_k(umma_fwd_ln_kernel, dim3(grid), dim3(threads), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   } else
-  launch_k(umma_fwd_kernel, dim3(grid), dim3(64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups)), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
+  launch_k(umma_fwd_kernel, dim3(grid), dim3(threads), smem, st, it->second.tAh, it->second.tAl, it->second.tBh, it->second.tBl, g);
   h->launches++; h->umma_launches++;
   return NPVC_OK;
 }
@@ -1006,6 +1013,7 @@ int npvc_create(const npvc_arch* arch, int64_t max_chunk, npvc_handle** out) {
   if (const char* nv = getenv("NPVC_NVTX")) h->nvtx = atoi(nv);
   if (const char* mg = getenv("NPVC_UMMA_MERGE")) h->umma_merge = atoi(mg);
   if (const char* br = getenv("NPVC_UMMA_BRES")) h->umma_bres = atoi(br);
+  if (const char* du = getenv("NPVC_UMMA_DUAL")) h->umma_dual = atoi(du);
   h->prefetch_min = PREFETCH_MIN_FRAMES; if (const char* pm = getenv("NPVC_PREFETCH_MIN")) h->prefetch_min = atoll(pm);
   h->prefetch_e0_min = PREFETCH_MIN_FRAMES; if (const char* pm = getenv("NPVC_PREFETCH_E0_MIN")) h->prefetch_e0_min = atoll(pm);
   if (const char* fl = getenv("NPVC_FUSE_LN_TRAIN")) h->fuse_ln_train = atoi(fl);

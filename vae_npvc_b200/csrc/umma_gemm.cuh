@@ -226,7 +226,7 @@ __device__ __forceinline__ void issue_taps(uint32_t acc, uint32_t acc2, uint64_t
 // LNF (single-CTA forms only): Layernorm + lrelu in the epilogue (launch_args.h, LnEpi) -- its own instantiation, so the
 //   plain epilogue's code and registers are untouched by it.
 template <bool PAIR, bool LNF = false>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __launch_bounds__(608, 1)
 umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
   pdl_prologue();
@@ -259,6 +259,8 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   float2* ln_blk = reinterpret_cast<float2*>(ln_stats + 4 * 2 * 128);                 // [4 groups][2][128] sums over 8-row blocks of a frame
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a launch of 96 + 128 * groups threads carries a second MMA issuer warp behind the epilogue groups (tap mode), else -1
+  const int mma2_warp = (((int)blockDim.x - 64) & 127) == 32 ? (int)(blockDim.x >> 5) - 1 : -1;
   // PAIR: a "tile" of the loops below is a pair tile (M tiles 2 * pm + rank of the two CTAs, one N tile); the pair
   // (cluster) index and count take the place of blockIdx.x / gridDim.x
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -315,8 +317,15 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       }
       __syncwarp();
     }
-  } else if (warp == 1 && tap) {
-    // ------------------------------------------------------------------ MMA issuer, tap mode
+  } else if ((warp == 1 || warp == mma2_warp) && tap) {
+    // ------------------------------------------------------------------ MMA issuer(s), tap mode
+    // The few MMAs of a tap-mode tile cost the issuing warp ~1000 cycles of its own instruction stream (uniform-datapath
+    // descriptor arithmetic, barrier waits, commits: ~120 dependent instructions per tile) while the tensor pipe is busy
+    // for ~150 -- measured: this warp never waits for data or accumulators, the epilogue warps wait for it
+    // (profiles/r2z_ncu_full_top_ops.txt, convT_g2).  With the second issuer warp of the launch (blockDim = 96 + 128 *
+    // groups) the CTA's even and odd tiles are issued by two warps side by side: stage and accumulator rings are walked
+    // with stride 2, every barrier still has one producer and one consumer per phase.
+    const int nis = mma2_warp > 0 ? 2 : 1, me = warp == 1 ? 0 : 1;
     const uint32_t idesc = make_idesc(g.BN, false), idesc2 = make_idesc(2 * g.BN, false);
     const bool merge = g.merge != 0;
     const uint64_t dbase = sdesc_base(0, sw);
@@ -324,7 +333,8 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     const uint64_t b0d = sdesc_at(dbase, sbase);
     mbar_wait(bres_bar, 0);
     RingPos sp(g.stages), ap(g.acc_sets);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, sp.advance(), ap.advance()) {
+    if (me) { sp.advance(); ap.advance(); }
+    for (int t = blockIdx.x + me * (int)gridDim.x; t < total_tiles; t += nis * (int)gridDim.x) {
       const int buf = ap.idx;
       mbar_wait(acce_bar(buf), ap.phase ^ 1u);
       const int s = sp.idx;
@@ -364,6 +374,7 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         umma_commit(accf_bar(buf));
       }
       __syncwarp();
+      for (int i = 0; i < nis; i++) { sp.advance(); ap.advance(); }
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one lane issues)
@@ -474,6 +485,8 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         __syncwarp();
       }
     }
+  } else if (warp == mma2_warp) {
+    // (second issuer warp outside tap mode: nothing to do)
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int lq = warp & 3;                        // TMEM lane quarter this warp may access
