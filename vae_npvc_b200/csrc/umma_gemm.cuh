@@ -226,7 +226,7 @@ __device__ __forceinline__ void issue_taps(uint32_t acc, uint32_t acc2, uint64_t
 // LNF (single-CTA forms only): Layernorm + lrelu in the epilogue (launch_args.h, LnEpi) -- its own instantiation, so the
 //   plain epilogue's code and registers are untouched by it.
 template <bool PAIR, bool LNF = false>
-__global__ void __launch_bounds__(608, 1)
+__global__ void __maxnreg__(96)      // (up to 608 threads: 64 + 4 epilogue groups + the extra issuer warp; 96 registers as with 576)
 umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, UmmaArgs g) {
   pdl_prologue();
@@ -259,8 +259,9 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   float2* ln_blk = reinterpret_cast<float2*>(ln_stats + 4 * 2 * 128);                 // [4 groups][2][128] sums over 8-row blocks of a frame
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // a launch of 96 + 128 * groups threads carries a second MMA issuer warp behind the epilogue groups (tap mode), else -1
-  const int mma2_warp = (((int)blockDim.x - 64) & 127) == 32 ? (int)(blockDim.x >> 5) - 1 : -1;
+  // a launch of 64 + 128 * groups + 32 * x threads carries x more MMA issuer warps behind the epilogue groups (tap mode)
+  const int n_extra = (((int)blockDim.x - 64) & 127) >> 5;
+  const int mma2_warp = n_extra > 0 ? (int)(blockDim.x >> 5) - n_extra : 1 << 20;       // first extra issuer warp
   // PAIR: a "tile" of the loops below is a pair tile (M tiles 2 * pm + rank of the two CTAs, one N tile); the pair
   // (cluster) index and count take the place of blockIdx.x / gridDim.x
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -317,15 +318,15 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       }
       __syncwarp();
     }
-  } else if ((warp == 1 || warp == mma2_warp) && tap) {
+  } else if ((warp == 1 || warp >= mma2_warp) && tap) {
     // ------------------------------------------------------------------ MMA issuer(s), tap mode
     // The few MMAs of a tap-mode tile cost the issuing warp ~1000 cycles of its own instruction stream (uniform-datapath
     // descriptor arithmetic, barrier waits, commits: ~120 dependent instructions per tile) while the tensor pipe is busy
     // for ~150 -- measured: this warp never waits for data or accumulators, the epilogue warps wait for it
-    // (profiles/r2z_ncu_full_top_ops.txt, convT_g2).  With the second issuer warp of the launch (blockDim = 96 + 128 *
-    // groups) the CTA's even and odd tiles are issued by two warps side by side: stage and accumulator rings are walked
-    // with stride 2, every barrier still has one producer and one consumer per phase.
-    const int nis = mma2_warp > 0 ? 2 : 1, me = warp == 1 ? 0 : 1;
+    // (profiles/r2z_ncu_full_top_ops.txt, convT_g2).  With the extra issuer warp of the launch (engine.cu launches one:
+    // two issuers) the CTA's tiles are issued round-robin by the issuer warps side by side: stage and accumulator rings
+    // are walked with that stride, every barrier still has one producer and one consumer per phase.
+    const int nis = 1 + n_extra, me = warp == 1 ? 0 : 1 + (warp - mma2_warp);
     const uint32_t idesc = make_idesc(g.BN, false), idesc2 = make_idesc(2 * g.BN, false);
     const bool merge = g.merge != 0;
     const uint64_t dbase = sdesc_base(0, sw);
@@ -333,7 +334,7 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     const uint64_t b0d = sdesc_at(dbase, sbase);
     mbar_wait(bres_bar, 0);
     RingPos sp(g.stages), ap(g.acc_sets);
-    if (me) { sp.advance(); ap.advance(); }
+    for (int i = 0; i < me; i++) { sp.advance(); ap.advance(); }
     for (int t = blockIdx.x + me * (int)gridDim.x; t < total_tiles; t += nis * (int)gridDim.x) {
       const int buf = ap.idx;
       mbar_wait(acce_bar(buf), ap.phase ^ 1u);
@@ -485,8 +486,8 @@ umma_fwd_kernel_t(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         __syncwarp();
       }
     }
-  } else if (warp == mma2_warp) {
-    // (second issuer warp outside tap mode: nothing to do)
+  } else if (warp >= mma2_warp) {
+    // (extra issuer warps outside tap mode: nothing to do)
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int lq = warp & 3;                        // TMEM lane quarter this warp may access
