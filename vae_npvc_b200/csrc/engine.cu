@@ -336,7 +336,7 @@ int launch_umma_tap(Ctx& c, const Op& o, int op_index, const TapGeom& tg_in, con
   // the 96-column ones with 2 accumulator sets lose (E2 dgrad 0.047 -> 0.064, G0 dgrad 0.070 -> 0.087: each issuer then
   // owns ONE set and ONE or two stages and stalls where a single issuer ran ahead) -- so: 4 sets and >= 4 stages
   const bool dual = h->umma_dual && g.acc_sets >= 4 && tg.stages >= 4 && rt.m_tiles > (long long)grid;
-  const int issuers = dual ? 2 : 1;        // (four issuers, one per accumulator set, failed the parity tests when tried: not offered)
+  const int issuers = dual ? 2 : 1;        // (four issuers = 21 warps of 96 registers: more than the SM's four 16 K-register partitions hold; not offered)
   const unsigned threads = 64 + 128 * (g.acc_sets < h->umma_groups ? g.acc_sets : h->umma_groups) + 32 * (issuers - 1);
   if (fuse_ln) {
     if (!h->attr_fwd_ln) { CUDA_TRY(cudaFuncSetAttribute(umma_fwd_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); h->attr_fwd_ln = true; }
